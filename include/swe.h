@@ -1,0 +1,202 @@
+/* swe.h -- C-ABI of the B200-native wind-erosion engine (libswe_b200.so).
+ *
+ * Drop-in boundary for the reference's erode cycle. The reference has no FFI layer: its
+ * "operator API" is the static C++ interface World::erode / World::cascade / World::map
+ * accessors / struct Wind (source/world.hpp:9-32, source/wind.hpp:4-26,
+ * source/cellpool.h:432-480). Each entry point below names the reference interface it
+ * replaces; include/swe_world.hpp re-creates those C++ names on top of this ABI and
+ * INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only; every call returns SWE_OK (0) or a negative
+ * swe_status and records a message retrievable with swe_last_error() (per thread). The
+ * reference itself has no error convention (oob -> NULL/false/0.0f, cellpool.h:90-94,
+ * 432-445,472-476); out-of-bounds cell queries here return SWE_ERR_OOB instead.
+ * There is NO CPU fallback: without a CUDA device swe_create fails with SWE_ERR_CUDA.
+ *
+ * Map layout: nx rows (x, slow index) by nz columns (z, fast index), cell index
+ * x*nz + z -- math::flatten (source/include/math.h:11-12). Host-side planes are fp32
+ * with an arbitrary byte stride so the engine can read/write the reference's 36-byte AoS
+ * quad::cell (cellpool.h:226-240) in place: pass &cell[0].height and stride 36.
+ */
+#ifndef SWE_H
+#define SWE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWE_ABI_VERSION 1
+
+typedef enum swe_status {
+  SWE_OK = 0,
+  SWE_ERR_INVALID = -1,   /* bad argument */
+  SWE_ERR_CUDA = -2,      /* CUDA runtime/driver error (message has the detail) */
+  SWE_ERR_OOM = -3,
+  SWE_ERR_OOB = -4,       /* cell coordinate outside the map */
+  SWE_ERR_STATE = -5      /* call not valid in the engine's current state */
+} swe_status;
+
+/* quad::cell members, in declaration order (cellpool.h:226-240). */
+typedef enum swe_plane {
+  SWE_HEIGHT = 0,
+  SWE_MASSFLOW = 1,
+  SWE_MOMENTUMX = 2,
+  SWE_MOMENTUMY = 3,
+  SWE_MOMENTUMZ = 4,
+  SWE_MASSFLOW_TRACK = 5,
+  SWE_MOMENTUMX_TRACK = 6,
+  SWE_MOMENTUMY_TRACK = 7,
+  SWE_MOMENTUMZ_TRACK = 8,
+  SWE_NUM_PLANES = 9
+} swe_plane;
+
+/* How World::erode runs its particles. */
+typedef enum swe_mode {
+  /* One particle at a time in the reference's order with the reference's libc rand()
+   * stream and IEEE fp32 (no FMA contraction): bitwise identical to the reference. */
+  SWE_MODE_DETERMINISTIC = 0,
+  /* All particles of the call in flight at once, one thread per particle, counter-based
+   * RNG, atomic scatter: same physics, statistical parity, exact mass accounting. */
+  SWE_MODE_PARALLEL = 1
+} swe_mode;
+
+/* Tunables. Defaults (swe_params_default) are the reference's statics and constants:
+ * Wind::{maxAge,boundarylayer,suspension,gravity} wind.hpp:23-26,
+ * World::{lrate,maxdiff,settling} world.hpp:30-32, quad::mapscale cellpool.h:184,
+ * Wind::pspeed wind.hpp:13. */
+typedef struct swe_params {
+  int32_t max_age;
+  float boundarylayer;
+  float suspension;
+  float gravity;
+  float lrate;
+  float maxdiff;
+  float settling;
+  int32_t mapscale;
+  float pspeed[3];
+  int32_t reserved[5];  /* must be zero */
+} swe_params;
+
+/* struct Wind (wind.hpp:4-21) as plain data. pos = (x, altitude, z). */
+typedef struct swe_wind {
+  int32_t age;
+  float sediment;
+  float pos[3];
+  float speed[3];
+} swe_wind;
+
+/* Counters accumulated since swe_create / swe_reset_stats. */
+typedef struct swe_stats {
+  uint64_t particles;      /* particles spawned */
+  uint64_t steps;          /* completed Wind::fly calls (returned true) */
+  uint64_t exits_oob;      /* particles that left the map (wind.hpp:32-38) */
+  uint64_t exits_age;      /* particles that exceeded maxAge (wind.hpp:45-46) */
+  double sediment_lost;    /* sum of Wind::sediment at death: mass that left the system */
+  uint64_t cascade_cells;  /* World::cascade centres processed by swe_cascade_sweep */
+  uint64_t erode_calls;
+  double last_erode_ms;    /* device time of the last swe_erode (CUDA events) */
+  double last_sweep_ms;    /* device time of the last swe_cascade_sweep call */
+  uint64_t kernel_launches;/* kernels launched by the engine so far */
+  double last_fly_ms;      /* device time of the particle kernel(s) inside the last swe_erode */
+} swe_stats;
+
+typedef struct swe_engine swe_engine;
+
+/* ---- lifecycle -------------------------------------------------------------------- */
+int swe_abi_version(void);
+const char* swe_last_error(void);
+int swe_params_default(swe_params* p);
+
+/* Replaces cellpool.reserve(quad::area) + World::map.init's node/slice construction
+ * (SimpleWindErosion.cpp:36-38, cellpool.h:139-143,343-352) with device-resident planes;
+ * the map size is a run-time value here (quad::tilesize is compile-time, cellpool.h:186).
+ * All planes start at zero. `device` = CUDA ordinal. */
+int swe_create(swe_engine** out, int nx, int nz, const swe_params* params, int device);
+void swe_destroy(swe_engine* e);
+int swe_set_params(swe_engine* e, const swe_params* params);   /* Wind::maxAge = ...; etc. */
+int swe_get_params(const swe_engine* e, swe_params* out);
+int swe_get_size(const swe_engine* e, int* nx, int* nz);
+
+/* srand(seed) (SimpleWindErosion.cpp:29,33): seeds the deterministic mode's libc-rand
+ * replica and the parallel mode's counter-based generator. */
+int swe_srand(swe_engine* e, uint32_t seed);
+
+/* ---- map transfer (host buffers) --------------------------------------------------- */
+/* Write / read one quad::cell member for every cell. `stride_bytes` is the distance
+ * between consecutive cells in the host buffer (4 = packed plane, 36 = reference AoS). */
+int swe_upload_plane(swe_engine* e, int plane, const float* src, ptrdiff_t stride_bytes);
+int swe_download_plane(swe_engine* e, int plane, float* dst, ptrdiff_t stride_bytes);
+/* Whole reference pool in one go: `cells` points at nx*nz 36-byte quad::cell records. */
+int swe_upload_cells(swe_engine* e, const void* cells);
+int swe_download_cells(swe_engine* e, void* cells);
+/* Pinned host memory for fast transfers (optional; any host pointer is accepted). */
+int swe_host_alloc(void** out, size_t bytes);
+int swe_host_free(void* p);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+/* World::erode(cycles) (world.hpp:36-77): zero the track planes, spawn `cycles`
+ * particles and fly each to its death, then EMA-update the flow fields. The work is
+ * enqueued on the engine's stream; every swe_download_* / swe_get_stats / swe_sync / query
+ * call waits for it, so the map a consumer reads afterwards is always the eroded one. */
+int swe_erode(swe_engine* e, int cycles, int mode);
+
+/* World::cascade(vec2 pos) (world.hpp:79-153) at one cell. */
+int swe_cascade(swe_engine* e, int x, int z);
+
+/* Whole-map cascade: `sweeps` passes; each pass applies World::cascade to every cell in
+ * the conflict-free 3x3 colour order (colour c = 0..8, cx = c/3, cz = c%3, centres with
+ * x%3 == cx and z%3 == cz). Within a colour the 3x3 footprints are disjoint, so the
+ * result is bitwise identical to calling the reference's World::cascade in that order.
+ * If max_excess_out != NULL it receives max over neighbour pairs of |dh| - d*maxdiff
+ * after the last sweep (<= 0 means relaxed to the repose angle). */
+int swe_cascade_sweep(swe_engine* e, int sweeps, float* max_excess_out);
+
+/* Iterate sweeps until max excess < tol or max_sweeps reached; returns sweeps done. */
+int swe_cascade_converge(swe_engine* e, float tol, int max_sweeps, int* sweeps_done,
+                         float* max_excess_out);
+
+/* Wind(vec2 pos) + while(wind.fly()) (wind.hpp:6,28-117) for one particle in
+ * deterministic mode, recording after every completed step 8 floats
+ * {pos.x,pos.y,pos.z,speed.x,speed.y,speed.z,sediment,age} into `records` (capacity
+ * max_records steps; may be NULL). The map is modified exactly as the reference does.
+ * *steps_out = completed steps; *final_out = particle state at death. */
+int swe_trace(swe_engine* e, float x, float z, int max_records, float* records,
+              int* steps_out, swe_wind* final_out);
+
+/* One Wind::fly() call (wind.hpp:28) on a caller-held particle, deterministic mode.
+ * *alive_out = the bool fly() returns. */
+int swe_wind_init(swe_wind* w, float x, float z);                 /* Wind::Wind(vec2) */
+int swe_wind_fly(swe_engine* e, swe_wind* w, int* alive_out);
+
+/* quad::map::normal(p) / height(p) / oob(p) (cellpool.h:432-480). */
+int swe_normal(swe_engine* e, int x, int z, float out3[3]);
+int swe_height(swe_engine* e, int x, int z, float* out);
+/* normals for every cell (what updatenode reads each frame, cellpool.h:302-321):
+ * dst = nx*nz*3 floats. */
+int swe_download_normals(swe_engine* e, float* dst);
+
+/* ---- diagnostics ------------------------------------------------------------------- */
+int swe_get_stats(swe_engine* e, swe_stats* out);
+int swe_reset_stats(swe_engine* e);
+int swe_sum_plane(swe_engine* e, int plane, double* out);   /* fp64 sum over the map */
+int swe_max_excess(swe_engine* e, float* out);
+int swe_hash_height(swe_engine* e, uint64_t* out);          /* FNV-1a-64 of fp32 words */
+int swe_sync(swe_engine* e);
+
+/* ---- device-side plumbing (for a host that already lives on the GPU) ---------------- */
+/* Stream the engine launches on (a cudaStream_t); 0 = the engine's own stream. */
+int swe_set_stream(swe_engine* e, void* cuda_stream);
+void* swe_get_stream(swe_engine* e);
+/* Device pointers of the engine's planes: height = float[nx*nz]; field/track =
+ * float4[nx*nz] {massflow, momentumx, momentumy, momentumz}. Valid until swe_destroy. */
+void* swe_device_height(swe_engine* e);
+void* swe_device_field(swe_engine* e);
+void* swe_device_track(swe_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWE_H */

@@ -1,0 +1,85 @@
+// swe_common.cuh -- shared device-side types of the B200 wind-erosion engine.
+//
+// HBM layout (one GPU, or one row stripe of a multi-GPU map):
+//   height : float [rows*nz]           4 B/cell   -- quad::cell::height
+//   field  : float4[rows*nz]          16 B/cell   -- {massflow, momentumx, momentumy, momentumz}
+//   track  : float4[rows*nz]          16 B/cell   -- the four *_track members
+// (reference: 36-byte AoS quad::cell, source/cellpool.h:226-240). The four track values of
+// a cell are always updated together (wind.hpp:93-96), so they share one 16-byte vector
+// that a single red.global.add.v4.f32 updates; height stays a separate dense plane because
+// the 3x3 neighbourhood reads (normal + cascade) touch nothing else.
+// Index = x*nz + z (math::flatten, source/include/math.h:11-12): x is the slow index.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swe.h"
+
+namespace swe {
+
+struct MapView {
+  float* height;
+  float4* field;
+  float4* track;
+  int nx, nz;   // GLOBAL map extent (bounds tests use these: closed boundary, cellpool.h:432-438)
+  int x0;       // global x of local row 0 (0 on a single GPU)
+  int rows;     // rows stored locally (== nx on a single GPU)
+  __host__ __device__ __forceinline__ size_t idx(int x, int z) const {
+    return (size_t)(x - x0) * (size_t)nz + (size_t)z;
+  }
+  __host__ __device__ __forceinline__ bool oob(int x, int z) const {
+    return x < 0 || z < 0 || x >= nx || z >= nz;
+  }
+};
+
+// Device-resident counters (mirrors the public swe_stats).
+struct DevStats {
+  unsigned long long particles;
+  unsigned long long steps;
+  unsigned long long exits_oob;
+  unsigned long long exits_age;
+  double sediment_lost;
+  unsigned long long cascade_cells;
+};
+
+// glibc TYPE_3 rand() state kept on the device between calls (deterministic mode):
+// the reference's libc stream is process-global and continues across World::erode calls.
+struct DetRand {
+  int32_t r[31];
+  int32_t f, b;
+};
+
+// ---- launchers implemented in the .cu files -------------------------------------------
+// deterministic (bit-exact) path: swe_det.cu
+void launch_det_erode(const MapView& m, const swe_params& p, int cycles, DetRand* rng,
+                      DevStats* stats, cudaStream_t st);
+void launch_det_trace(const MapView& m, const swe_params& p, float x, float z, int max_records,
+                      float* d_records, int* d_steps, swe_wind* d_final, DetRand* rng,
+                      DevStats* stats, cudaStream_t st);
+void launch_det_fly_once(const MapView& m, const swe_params& p, swe_wind* d_wind, int* d_alive,
+                         DetRand* rng, DevStats* stats, cudaStream_t st);
+void launch_det_cascade_one(const MapView& m, const swe_params& p, int x, int z, cudaStream_t st);
+void launch_det_srand(DetRand* rng, uint32_t seed, cudaStream_t st);
+void launch_normals(const MapView& m, const swe_params& p, float* d_out3, cudaStream_t st);
+void launch_normal_one(const MapView& m, const swe_params& p, int x, int z, float* d_out3,
+                       cudaStream_t st);
+
+// whole-map cascade: swe_cascade.cu
+int launch_cascade_sweep(const MapView& m, const swe_params& p, int sweeps, DevStats* stats,
+                         cudaStream_t st);  // returns #kernel launches
+void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st);
+
+// parallel flight: swe_par.cu
+int launch_par_fly(const MapView& m, const swe_params& p, int n_particles, uint64_t seed,
+                   uint32_t call_index, DevStats* stats, cudaStream_t st);
+
+// field passes and utilities: swe_fields.cu
+void launch_ema(const MapView& m, float lrate, cudaStream_t st);
+void launch_pack_plane(const MapView& m, int plane, const float* d_src, cudaStream_t st);
+void launch_unpack_plane(const MapView& m, int plane, float* d_dst, cudaStream_t st);
+void launch_cells_to_planes(const MapView& m, const float* d_cells, cudaStream_t st);
+void launch_planes_to_cells(const MapView& m, float* d_cells, cudaStream_t st);
+void launch_sum_plane(const MapView& m, int plane, double* d_out, cudaStream_t st);
+void launch_hash_height(const MapView& m, unsigned long long* d_out, cudaStream_t st);
+
+}  // namespace swe

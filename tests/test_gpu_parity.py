@@ -1,0 +1,277 @@
+"""GPU: the CUDA path through the C-ABI against the oracle (plain-C restatement pinned to
+the unmodified reference) and the committed golden fixtures.
+
+Bar: BIT-EXACT for everything in deterministic mode (heights, flow fields, tracks,
+trajectories, normals, cascade) -- north star parity (1) asks for 1e-5 relative, but the
+system is chaotic (round() to a cell index, wind.hpp:30) so only bitwise identity holds over
+a whole run; parity (3) (cascade on a frozen map, 1e-6) is likewise met bitwise."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import simplewinderosion_b200 as swe
+from tests.oracle_lib import PortWorld
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FP = json.load(open(os.path.join(G, "fingerprints.json")))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_planes_equal(w, ora, planes=range(9)):
+    for k in planes:
+        got, want = w.download(k), ora.plane(k)
+        assert np.array_equal(bits(got), bits(want)), \
+            f"plane {k}: {np.count_nonzero(bits(got) != bits(want))} cells differ"
+
+
+def mt19937_uniform_map(n, seed=42):
+    rs = np.random.RandomState(seed)
+    u = rs.randint(0, 2 ** 32, size=n * n, dtype=np.uint32)
+    f = (u.astype(np.float32) / np.float32(4294967296.0)).astype(np.float32)
+    f[f >= 1.0] = np.nextafter(np.float32(1), np.float32(0))
+    return f.reshape(n, n)
+
+
+def gaussian(n):
+    o = PortWorld(n)
+    o.init_gaussian()
+    return o
+
+
+# ---- deterministic erode: all nine planes, step counts -------------------------------------
+@pytest.mark.parametrize("n,calls,cycles,seed", [(32, 2, 150, 3), (64, 2, 256, 7), (128, 2, 512, 42),
+                                                 (256, 1, 1024, 1)])
+def test_det_erode_all_planes(n, calls, cycles, seed):
+    ora = gaussian(n)
+    w = swe.World(n)
+    w.upload(ora.plane(0))
+    w.srand(seed); ora.srand(seed)
+    steps = 0
+    for _ in range(calls):
+        w.erode(cycles, swe.MODE_DETERMINISTIC)
+        steps += ora.erode(cycles).steps
+        assert_planes_equal(w, ora)
+    st = w.stats()
+    assert st.steps == steps and st.particles == calls * cycles
+    assert st.exits_oob + st.exits_age == calls * cycles
+
+
+def test_det_erode_nonsquare_and_params():
+    nx, nz = 40, 97
+    ora = PortWorld(nx, nz)
+    rs = np.random.RandomState(2)
+    hm = (0.25 + 0.05 * rs.random_sample((nx, nz))).astype(np.float32)
+    ora.set_plane(0, hm)
+    kw = dict(maxAge=90, boundarylayer=1.5, suspension=0.1, gravity=0.2, lrate=0.3, maxdiff=0.002, settling=0.7)
+    ora.set(**kw)
+    w = swe.World(nx, nz)
+    w.set(**kw)
+    w.upload(hm)
+    w.srand(5); ora.srand(5)
+    w.erode(300, swe.MODE_DETERMINISTIC); ora.erode(300)
+    assert_planes_equal(w, ora)
+
+
+def test_det_golden_all_planes_64():
+    g = np.load(os.path.join(G, "erode64.npz"))
+    w = swe.World(64)
+    w.upload(g["initial"])
+    w.srand(int(g["seed"]))
+    for _ in range(int(g["calls"])):
+        w.erode(int(g["cycles"]), swe.MODE_DETERMINISTIC)
+    for k in range(9):
+        assert np.array_equal(bits(w.download(k)), bits(g["planes"][k])), f"plane {k}"
+
+
+@pytest.mark.parametrize("run", [r for r in FP["erode"] if r["n"] in (64, 256)], ids=lambda r: f"n{r['n']}")
+def test_det_reference_fingerprints(run):
+    """Hashes/step counts produced by the unmodified reference (tests/golden)."""
+    ora = gaussian(run["n"])
+    w = swe.World(run["n"])
+    w.upload(ora.plane(0))
+    w.srand(run["seed"])
+    for _ in range(run["calls"]):
+        w.erode(run["cycles"], swe.MODE_DETERMINISTIC)
+    st = w.stats()
+    assert st.steps == run["steps"]
+    assert st.exits_oob == run["exits_oob"] and st.exits_age == run["exits_age"]
+    assert f"{w.hash_height():016x}" == run["hash"]
+    assert abs(st.sediment_lost - run["sediment_lost"]) < 1e-9
+    assert abs(w.sum_plane(swe.HEIGHT) - run["sum_final"]) < 1e-9
+
+
+def test_det_survey_fingerprint_512_one_call():
+    """First World::erode(4096) of the survey's 512^2 run: 1,164,517 steps."""
+    ora = gaussian(512)
+    w = swe.World(512)
+    w.upload(ora.plane(0))
+    w.srand(1); ora.srand(1)
+    w.erode(4096, swe.MODE_DETERMINISTIC)
+    st_o = ora.erode(4096)
+    assert w.stats().steps == st_o.steps == 1164517
+    assert w.hash_height() == ora.hash_height()
+
+
+# ---- trajectories -----------------------------------------------------------------------------
+def test_trajectories_golden():
+    g = np.load(os.path.join(G, "traj512.npz"))
+    w = swe.World(512)
+    w.upload(gaussian(512).plane(0))
+    for i in range(6):
+        w.srand(100 + i)
+        x, z = g[f"t{i}_start"]
+        rec, n, fin = w.trace(float(x), float(z), 600)
+        assert n == int(g[f"t{i}_steps"]), i
+        assert np.array_equal(bits(rec), bits(g[f"t{i}_rec"])), i
+    assert np.array_equal(bits(w.download()), bits(g["height_after"]))
+
+
+def test_wind_fly_step_by_step():
+    ora = gaussian(64)
+    w = swe.World(64)
+    w.upload(ora.plane(0))
+    w.srand(9); ora.srand(9)
+    want, n = ora.trace(20.3, 31.7, 600)
+    wind = swe.Wind(w, (20.3, 31.7))
+    k = 0
+    while wind.fly():
+        assert np.array_equal(bits(wind.pos), bits(want[k, 0:3])), k
+        assert np.array_equal(bits(wind.speed), bits(want[k, 3:6])), k
+        assert np.float32(wind.sediment).view(np.uint32) == want[k, 6].view(np.uint32)
+        k += 1
+        if k > 40:
+            break
+    assert k == min(n, 41)
+
+
+# ---- normals, heights, accessors ----------------------------------------------------------------
+def test_normals_golden_incl_borders():
+    g = np.load(os.path.join(G, "normals32.npz"))
+    w = swe.World(32)
+    w.upload(g["height"])
+    assert np.array_equal(bits(w.normals()), bits(g["normals"]))
+    for p in [(0, 0), (31, 31), (0, 17), (12, 31), (5, 5)]:
+        assert np.array_equal(bits(w.map.normal(p)), bits(g["normals"][p]))
+        assert w.map.height(p) == g["height"][p]
+    assert w.map.oob((-1, 0)) and w.map.oob((32, 3)) and not w.map.oob((31, 0))
+    assert w.map.height((-1, 5)) == 0.0           # cellpool.h:472-476
+    with pytest.raises(swe.SweError):
+        w.map.normal((40, 1))
+
+
+# ---- cascade ------------------------------------------------------------------------------------
+def test_cascade_single_cells_golden():
+    g = np.load(os.path.join(G, "cascade_cells32.npz"))
+    w = swe.World(32)
+    for before, (x, z), after in zip(g["before"], g["centre"], g["after"]):
+        w.upload(before)
+        w.cascade((int(x), int(z)))
+        assert np.array_equal(bits(w.download()), bits(after)), (x, z)
+
+
+@pytest.mark.parametrize("case", FP["cascade_sweep"], ids=lambda c: f"n{c['n']}")
+def test_cascade_sweep_reference_fingerprints(case):
+    w = swe.World(case["n"])
+    w.upload(mt19937_uniform_map(case["n"], case["seed"]))
+    w.cascade_sweep(case["sweeps"])
+    assert f"{w.hash_height():016x}" == case["hash"]
+
+
+@pytest.mark.parametrize("nx,nz,sweeps", [(1, 1, 1), (1, 7, 2), (2, 2, 2), (3, 5, 2), (64, 64, 3), (100, 259, 2),
+                                          (257, 130, 2), (2048, 2048, 1)])
+def test_cascade_sweep_vs_oracle(nx, nz, sweeps):
+    rs = np.random.RandomState(nx * 1000 + nz)
+    hm = rs.random_sample((nx, nz)).astype(np.float32)
+    if nx >= 64:
+        hm[10:30, 5:40] = 0.5                      # plateau: exact ties
+        hm[40:50, :] = np.round(hm[40:50, :] * 16) / 16
+    ora = PortWorld(nx, nz)
+    ora.set_plane(0, hm)
+    w = swe.World(nx, nz)
+    w.upload(hm)
+    for _ in range(sweeps):
+        ex = w.cascade_sweep(1, want_excess=True)
+        ora.cascade_sweep(1)
+        assert np.array_equal(bits(w.download()), bits(ora.plane(0)))
+        assert np.float32(ex).view(np.uint32) == np.float32(ora.max_excess()).view(np.uint32)
+
+
+def test_cascade_properties_full_size():
+    """cfg5 size (8192^2): mass conserved to fp32 round-off, worst excess shrinks, relaxed
+    map is a fixed point (idempotence) -- size-independent properties where the CPU oracle
+    would take minutes."""
+    n = 8192
+    rs = np.random.RandomState(1)
+    w = swe.World(n)
+    hm = rs.random_sample((n, n)).astype(np.float32)
+    w.upload(hm)
+    s0 = w.sum_plane()
+    e0 = w.max_excess()
+    e1 = w.cascade_sweep(3, want_excess=True)
+    assert e1 < e0
+    assert abs(w.sum_plane() - s0) < 1e-6 * s0
+    flat = np.full((n, n), 0.25, dtype=np.float32)
+    flat += (0.001 * rs.random_sample((n, n))).astype(np.float32)   # |dh| < maxdiff everywhere
+    w.upload(flat)
+    w.cascade_sweep(1)
+    assert np.array_equal(bits(w.download()), bits(flat))
+
+
+# ---- boundary: transfers ---------------------------------------------------------------------
+def test_strided_aos_roundtrip():
+    """Read/write the reference's 36-byte AoS quad::cell in place (stride 36) and in bulk."""
+    n = 48
+    rs = np.random.RandomState(0)
+    cells = np.zeros((n, n), dtype=swe.CELL_DTYPE)
+    for name in swe.CELL_DTYPE.names:
+        cells[name] = rs.random_sample((n, n)).astype(np.float32)
+    w = swe.World(n)
+    base = cells.ctypes.data
+    for k, name in enumerate(swe.CELL_DTYPE.names):
+        w.upload_strided(k, base + 4 * k, 36)
+    for k, name in enumerate(swe.CELL_DTYPE.names):
+        assert np.array_equal(w.download(k), cells[name]), name
+    out = np.zeros_like(cells)
+    for k in range(9):
+        w.download_strided(k, out.ctypes.data + 4 * k, 36)
+    assert out.tobytes() == cells.tobytes()
+    w2 = swe.World(n)
+    w2.upload_cells(cells)
+    assert w2.download_cells().tobytes() == cells.tobytes()
+    assert np.array_equal(w2.download(swe.MOMENTUMY_TRACK), cells["momentumy_track"])
+
+
+def test_error_paths():
+    w = swe.World(16)
+    with pytest.raises(swe.SweError):
+        w.erode(-1)
+    with pytest.raises(swe.SweError):
+        w.erode(1, mode=7)
+    with pytest.raises(swe.SweError):
+        w.cascade((16, 0))
+    with pytest.raises(ValueError):
+        w.upload(np.zeros((4, 4), np.float32))
+    w.erode(0, swe.MODE_DETERMINISTIC)     # empty call: tracks reset, fields decay, nothing else
+    assert w.stats().steps == 0
+
+
+def test_device_expf_matches_host_libm():
+    """The deterministic kernel's expf restatement vs this host's libm, through a particle
+    step: a particle starting above the surface makes hfac = expf(-(y-h)/2) observable."""
+    # covered end-to-end by the trajectory tests; here a direct high-altitude case
+    ora = gaussian(64)
+    w = swe.World(64)
+    w.upload(ora.plane(0))
+    for x, z in [(10.0, 10.0), (16.0, 32.0), (40.2, 33.3)]:
+        w.srand(4); ora.srand(4)
+        a, na, _ = w.trace(x, z, 600)
+        b, nb = ora.trace(x, z, 600)
+        assert na == nb and np.array_equal(bits(a), bits(b))
