@@ -103,8 +103,12 @@ class PortWorld:
             setattr(self.w.contents.p, k, v)
 
     def plane(self, k: int) -> np.ndarray:
-        """numpy VIEW of plane k (0=height ... 8=momentumz_track)."""
-        return np.ctypeslib.as_array(self.w.contents.plane[k], shape=(self.nx, self.nz))
+        """numpy VIEW of plane k (0=height ... 8=momentumz_track); the view keeps this
+        world alive."""
+        addr = C.addressof(self.w.contents.plane[k].contents)
+        buf = (C.c_float * (self.nx * self.nz)).from_address(addr)
+        buf._owner = self
+        return np.frombuffer(buf, dtype=np.float32).reshape(self.nx, self.nz)
 
     def set_plane(self, k: int, a) -> None:
         self.plane(k)[...] = np.asarray(a, dtype=np.float32).reshape(self.nx, self.nz)
