@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the erode-cycle hot path (BASELINE.json metric:
+wind particle-steps/s @4096^2 map; cascade % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA arm
+    python bench.py --impl reference [--gpus N] ...                # the reference's CPU arm
+
+A "step" is one World::erode call (track reset + all particles + EMA) in parallel mode on
+the 4096^2 dune-field workload with 4,194,304 particles (BASELINE.json configs[2], in its
+reference-pinned form: single height layer; rock/abrasion are engine extensions absent from
+the reference snapshot). One JSON line is printed by rank 0.
+
+  value     particle-steps/s with the map resident in HBM (CUDA events on the launch stream,
+            barrier + synchronize on both sides, max over ranks)
+  e2e       the same metric through the host-buffer C-ABI: every step uploads the height
+            plane from pinned host memory, erodes, and downloads height + the four flow
+            fields (what the reference's renderer reads each frame)
+  roofline  the particle kernel: 104 algorithmic B/step / its device time,
+            against MEASURED_PEAKS.json hbm_gbs; cascade_roofline is the same for the
+            whole-map cascade sweep (8 B/cell/sweep) on the 8192^2 random-slope workload
+  cpu_baseline  the unmodified reference (oracle/_ref) timed on one host core on a bounded
+            sample of the same workload (the reference is single-threaded, world.hpp:100)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_MAP = 4096
+PARTICLES = 4 * 1024 * 1024
+CASCADE_N = 8192
+BYTES_PER_STEP = 104.0          # 9x4 read + 9x4 write + 4 tracks x (4+4)
+BYTES_PER_CELL_SWEEP = 8.0      # read h + write h
+METRIC = "wind particle-steps/sec @4096^2 map"
+UNIT = "particle-steps/s"
+WORKLOAD = ("cfg3-pinned: 4096x4096 FBm dune field (seed 1), 4194304 particles per World::erode, "
+            "parallel mode, single height layer (rock/abrasion extension off)")
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks / throttle sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.p, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference workers (oracle/_ref = the unmodified reference compiled headless; test
+# infrastructure executed here only as the reported baseline, never as the product)
+# ------------------------------------------------------------------------------------------
+def _ref_lib_path(n: int) -> str | None:
+    p = os.path.join(ROOT, "oracle", "_ref", f"libswe_ref_{n}.so")
+    return p if os.path.exists(p) else None
+
+
+def _cpu_worker(kind, n, map_path, cycles, n_steps, barrier, queue, core):
+    """One single-threaded replica of the reference erode loop on its own copy of the map."""
+    import numpy as np
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    hm = np.load(map_path)
+    if kind == "reference":
+        L = C.CDLL(_ref_lib_path(n))
+        L.ref_set_plane.argtypes = [C.c_int, C.c_void_p]
+        L.ref_erode_counted.argtypes = [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+        L.ref_init(1)
+        L.ref_set_plane(0, np.ascontiguousarray(hm).ctypes.data)
+        st, lost = (C.c_longlong * 3)(), C.c_double()
+
+        def step():
+            L.ref_erode_counted(cycles, st, C.byref(lost))
+            return int(st[0])
+    else:
+        from tests.oracle_lib import PortWorld
+        w = PortWorld(n)
+        w.set_plane(0, hm)
+        w.srand(1)
+
+        def step():
+            return int(w.erode(cycles).steps)
+    for _ in range(n_steps):
+        barrier.wait()
+        t0 = time.monotonic()
+        s = step()
+        t1 = time.monotonic()
+        queue.put((s, t0, t1))
+
+
+def run_cpu_reference(n: int, map_path: str, cycles: int, n_steps: int, replicas: int):
+    """Returns (kind, per-step list of (total_steps, seconds))."""
+    import multiprocessing as mp
+    kind = "reference" if _ref_lib_path(n) else "port"
+    ctx = mp.get_context("spawn")
+    barrier, queue = ctx.Barrier(replicas + 1), ctx.Queue()
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except Exception:
+        cores = list(range(os.cpu_count() or 1))
+    procs = [ctx.Process(target=_cpu_worker, daemon=True,
+                         args=(kind, n, map_path, cycles, n_steps, barrier, queue, cores[i % len(cores)]))
+             for i in range(replicas)]
+    for p in procs:
+        p.start()
+    out = []
+    for _ in range(n_steps):
+        barrier.wait()
+        rs = [queue.get() for _ in range(replicas)]
+        out.append((sum(r[0] for r in rs), max(r[2] for r in rs) - min(r[1] for r in rs)))
+    for p in procs:
+        p.join(timeout=30)
+    return kind, out
+
+
+def host_threads_for_reference(n: int) -> int:
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        ncpu = os.cpu_count() or 1
+    per_replica = 9 * 4 * n * n + 3 * 4 * n * n + (256 << 20)   # AoS pool + staging + runtime
+    try:
+        import psutil
+        by_mem = int(psutil.virtual_memory().available * 0.5 // per_replica)
+    except Exception:
+        by_mem = 8
+    return max(1, min(ncpu, by_mem, 64))
+
+
+def make_map(n: int):
+    from simplewinderosion_b200 import generate
+    return generate.fbm(n, seed=1)
+
+
+def save_map_tmp(hm) -> str:
+    import tempfile
+    import numpy as np
+    fd, path = tempfile.mkstemp(prefix="swe_bench_map_", suffix=".npy")
+    os.close(fd)
+    np.save(path, hm)
+    return path
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    hm = make_map(N_MAP)
+    path = save_map_tmp(hm)
+    replicas = host_threads_for_reference(N_MAP)
+    cycles = args.ref_cycles     # bounded sample of the 4,194,304-particle call, per replica
+    try:
+        kind, steps = run_cpu_reference(N_MAP, path, cycles, args.warmup + args.steps, replicas)
+    finally:
+        os.unlink(path)
+    timed = steps[args.warmup:]
+    tot_steps = sum(s for s, _ in timed)
+    tot_time = sum(t for _, t in timed)
+    value = tot_steps / tot_time
+    sample = (f"{replicas} independent single-threaded replicas of the reference erode loop "
+              f"(the reference is non-reentrant, world.hpp:100), each World::erode({cycles}) per step "
+              f"on its own copy of the 4096^2 map")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_time / len(timed),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": replicas, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def cascade_roofline(swe, device: int, peak: float, peak_src: str, quick: bool) -> dict:
+    from simplewinderosion_b200 import generate
+    n = CASCADE_N
+    w = swe.World(n, device=device)
+    w.upload(generate.random_slopes(n, seed=42))
+    bytes_per_sweep = BYTES_PER_CELL_SWEEP * n * n
+    first, total_ms, sweeps = [], 0.0, 0
+    ex = w.max_excess()
+    for i in range(3):                       # warm-up sweeps are part of the relaxation: timed too
+        w.cascade_sweep(1); ms = w.stats().last_sweep_ms
+        first.append(ms); total_ms += ms; sweeps += 1
+    max_sweeps = 40 if quick else 400
+    while sweeps < max_sweeps:
+        k = 8
+        ex = w.cascade_sweep(k, want_excess=True)
+        ms = w.stats().last_sweep_ms
+        total_ms += ms; sweeps += k
+        last_ms = ms / k
+        if ex < 1e-4:
+            break
+    w.cascade_sweep(8); relaxed_ms = w.stats().last_sweep_ms / 8
+    w.close()
+    achieved = bytes_per_sweep * sweeps / (total_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "workload": f"cfg5: {n}x{n} U(0,1) random-slope map relaxed until max excess < 1e-4",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_src, "traffic": None, "sweeps": sweeps, "final_max_excess": ex,
+            "ms_per_sweep_mean": total_ms / sweeps, "ms_first_sweep": first[0],
+            "ms_per_sweep_relaxed": relaxed_ms,
+            "frac_relaxed": bytes_per_sweep / (relaxed_ms * 1e-3) / 1e9 / peak}
+
+
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import simplewinderosion_b200 as swe
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peak, peak_src = measured_peak_gbs()
+    n, particles = args.size, args.particles
+    hm = make_map(n)
+
+    w = swe.World(n, device=local)
+    stream = torch.cuda.Stream()
+    w.set_stream(stream.cuda_stream)
+    w.upload(hm)
+    w.srand(1 + rank)
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        w.erode(particles, swe.MODE_PARALLEL)
+    w.sync()
+    st0 = w.stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fly_ms = 0.0
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            w.erode(particles, swe.MODE_PARALLEL)
+        ev1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = w.stats()
+    steps_done = st1.steps - st0.steps
+    launches = st1.kernel_launches - st0.kernel_launches
+    total_steps = sum_over_ranks(float(steps_done))
+    value = total_steps / (dev_ms * 1e-3)
+
+    # per-kernel time of the particle kernel (events on the launch stream, one extra pass so
+    # the per-call event pair can be read back after each call)
+    fly_ms, fly_steps = 0.0, 0
+    for _ in range(args.steps):
+        s_before = w.stats().steps
+        w.erode(particles, swe.MODE_PARALLEL)
+        s = w.stats()
+        fly_ms += s.last_fly_ms; fly_steps += s.steps - s_before
+    achieved = BYTES_PER_STEP * fly_steps / (fly_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI ---------------------------------------------
+    def pinned(shape):
+        ptr = C.c_void_p()
+        nbytes = int(np.prod(shape)) * 4
+        swe._capi.check(swe.lib.swe_host_alloc(C.byref(ptr), nbytes))
+        buf = (C.c_float * (nbytes // 4)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape(shape), ptr
+
+    h_in, p_in = pinned((n, n))
+    h_out, p_out = pinned((5, n, n))
+    h_in[...] = w.download()
+    planes = (swe.HEIGHT, swe.MASSFLOW, swe.MOMENTUMX, swe.MOMENTUMY, swe.MOMENTUMZ)
+
+    def e2e_step():
+        w.upload(h_in)
+        w.erode(particles, swe.MODE_PARALLEL)
+        for i, pl in enumerate(planes):
+            w.download(pl, out=h_out[i])
+        h_in[...] = h_out[0]          # the host owns the canonical map between calls
+
+    e2e_step()
+    s0 = w.stats().steps
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_steps = sum_over_ranks(float(w.stats().steps - s0))
+    e2e_value = e2e_steps / e2e_s
+    mean_h = float(h_out[0].mean())
+    for p in (p_in, p_out):
+        swe.lib.swe_host_free(p)
+    w.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD if (n == N_MAP and particles == PARTICLES) else
+            f"{n}x{n} FBm dune field, {particles} particles per World::erode, parallel mode",
+            "map": [n, n], "particles_per_step": particles,
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one map per GPU)",
+            "l2": "working set 576 MiB (height 64 + track 256 + field 256) > 126 MB L2; no flush needed",
+            "steps_per_particle": steps_done / max(1, (st1.particles - st0.particles)),
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * n * n),
+                "d2h_bytes_per_step": int(5 * 4 * n * n), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "result_check_mean_height": mean_h},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "par_fly_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_step": BYTES_PER_STEP,
+                     "kernel_ms_per_launch": fly_ms / args.steps,
+                     "note": "latency/atomic-bound scatter kernel; HBM is the stated bound of SURVEY 8(d)"},
+    }
+    if not args.skip_cascade:
+        line["cascade_roofline"] = cascade_roofline(swe, local, peak, peak_src, args.quick)
+    if world == 1 and not args.skip_cpu:
+        path = save_map_tmp(hm)
+        try:
+            kind, steps = run_cpu_reference(n, path, args.cpu_cycles, 1, 1)
+        finally:
+            os.unlink(path)
+        s, t = steps[0]
+        line["cpu_baseline"] = {
+            "value": s / t, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"one World::erode({args.cpu_cycles}) = {s} particle-steps on the same {n}^2 map, "
+                      f"1 thread (the reference is single-threaded), {t:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=N_MAP)
+    ap.add_argument("--particles", type=int, default=PARTICLES)
+    ap.add_argument("--cpu-cycles", type=int, default=32768, help="particles of the 1-core CPU baseline sample")
+    ap.add_argument("--ref-cycles", type=int, default=4096, help="particles per replica per step, --impl reference")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-cascade", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="shorter cascade relaxation")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

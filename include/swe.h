@@ -59,9 +59,21 @@ typedef enum swe_mode {
    * stream and IEEE fp32 (no FMA contraction): bitwise identical to the reference. */
   SWE_MODE_DETERMINISTIC = 0,
   /* All particles of the call in flight at once, one thread per particle, counter-based
-   * RNG, atomic scatter: same physics, statistical parity, exact mass accounting. */
+   * RNG, atomic erode/deposit scatter; after every round of steps World::cascade runs once at
+   * each touched cell in conflict-free colour order. Same physics, statistical parity, exact
+   * mass accounting. */
   SWE_MODE_PARALLEL = 1
 } swe_mode;
+
+/* Engine options (swe_set_option). */
+typedef enum swe_option {
+  /* 0 (default) = fused nine-colour shared-memory tile kernel; 1 = one global-memory launch per
+   * colour. Both are bitwise identical to the reference order; 1 exists for cross-checking. */
+  SWE_OPT_CASCADE_VARIANT = 1,
+  /* Parallel mode: Wind::fly steps each particle takes between two cascade passes (default 1:
+   * like the reference, a touched cell is relaxed before any particle steps again). */
+  SWE_OPT_CASCADE_INTERVAL = 2
+} swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:
  * Wind::{maxAge,boundarylayer,suspension,gravity} wind.hpp:23-26,
@@ -119,6 +131,7 @@ void swe_destroy(swe_engine* e);
 int swe_set_params(swe_engine* e, const swe_params* params);   /* Wind::maxAge = ...; etc. */
 int swe_get_params(const swe_engine* e, swe_params* out);
 int swe_get_size(const swe_engine* e, int* nx, int* nz);
+int swe_set_option(swe_engine* e, int option, int value);
 
 /* srand(seed) (SimpleWindErosion.cpp:29,33): seeds the deterministic mode's libc-rand
  * replica and the parallel mode's counter-based generator. */

@@ -76,6 +76,7 @@ PROTOTYPES = {
     "swe_set_params": (C.c_int, [_E, C.POINTER(Params)]),
     "swe_get_params": (C.c_int, [_E, C.POINTER(Params)]),
     "swe_get_size": (C.c_int, [_E, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "swe_set_option": (C.c_int, [_E, C.c_int, C.c_int]),
     "swe_srand": (C.c_int, [_E, C.c_uint32]),
     "swe_upload_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_download_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),

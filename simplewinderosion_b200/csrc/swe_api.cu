@@ -66,6 +66,12 @@ struct swe_engine {
   size_t h_stage_bytes = 0;
   uint64_t seed = 1;
   uint32_t call_index = 0;
+  // parallel-mode state
+  ParticleBuf pbuf{};
+  unsigned char* d_stamp = nullptr;   // per-cell "touched in round" byte
+  unsigned stamp_counter = 0;
+  int opt_cascade_variant = 0;        // 0 fused tile kernel, 1 per-colour launches
+  int opt_cascade_interval = 1;       // Wind::fly steps per particle between cascade passes
   uint64_t launches = 0, erode_calls = 0;
   double last_erode_ms = 0.0, last_sweep_ms = 0.0, last_fly_ms = 0.0;
 
@@ -95,6 +101,27 @@ int need_stage(swe_engine* e, size_t bytes) {
   e->h_stage = nullptr; e->h_stage_bytes = 0;
   SWE_CUDA(cudaMallocHost(&e->h_stage, bytes));
   e->h_stage_bytes = bytes;
+  return SWE_OK;
+}
+
+int need_particles(swe_engine* e, int n) {
+  const int slots = e->p.max_age + 8;
+  if (e->pbuf.capacity >= n && e->pbuf.live_slots >= slots) return SWE_OK;
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(e->pbuf.a); cudaFree(e->pbuf.b); cudaFree(e->pbuf.live);
+  e->pbuf = ParticleBuf{};
+  SWE_CUDA(cudaMalloc(&e->pbuf.a, (size_t)n * sizeof(float4)));
+  SWE_CUDA(cudaMalloc(&e->pbuf.b, (size_t)n * sizeof(float4)));
+  SWE_CUDA(cudaMalloc(&e->pbuf.live, (size_t)slots * sizeof(unsigned)));
+  e->pbuf.capacity = n; e->pbuf.live_slots = slots;
+  return SWE_OK;
+}
+
+int need_stamp(swe_engine* e) {
+  if (e->d_stamp) return SWE_OK;
+  SWE_CUDA(cudaMalloc(&e->d_stamp, e->cells()));
+  SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
+  e->stamp_counter = 0;
   return SWE_OK;
 }
 
@@ -199,6 +226,7 @@ void swe_destroy(swe_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->m.height); cudaFree(e->m.field); cudaFree(e->m.track);
   cudaFree(e->d_stats); cudaFree(e->d_rng); cudaFree(e->d_small); cudaFree(e->d_scratch);
+  cudaFree(e->pbuf.a); cudaFree(e->pbuf.b); cudaFree(e->pbuf.live); cudaFree(e->d_stamp);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
   if (e->ev_b) cudaEventDestroy(e->ev_b);
@@ -345,9 +373,25 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
   if (mode == SWE_MODE_DETERMINISTIC) {
     launch_det_erode(e->m, e->p, cycles, e->d_rng, e->d_stats, e->stream);
     if (int rc = check_launch(e, "det_erode")) return rc;
-  } else {
-    const int n = launch_par_fly(e->m, e->p, cycles, e->seed, e->call_index, e->d_stats, e->stream);
-    if (int rc = check_launch(e, "par_fly", n)) return rc;
+  } else if (cycles > 0) {
+    if (int rc = need_particles(e, cycles)) return rc;
+    if (int rc = need_stamp(e)) return rc;
+    const int k = e->opt_cascade_interval;
+    const int rounds = (e->p.max_age + 2 + k - 1) / k;   // every particle is dead after maxAge+2 calls
+    launch_par_begin(e->pbuf, e->m, cycles, e->seed, e->call_index, e->d_stats, e->stream);
+    if (int rc = check_launch(e, "par_begin", 2)) return rc;
+    for (int r = 0; r < rounds; r++) {
+      if (++e->stamp_counter > 255u) {   // stamp values 1..255; recycle with a clean plane
+        SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
+        e->stamp_counter = 1;
+      }
+      const unsigned char now = (unsigned char)e->stamp_counter;
+      launch_par_round(e->pbuf, e->m, e->p, cycles, r, k, e->seed, e->call_index, e->d_stamp, now,
+                       e->d_stats, e->stream);
+      // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
+      launch_cascade_stamped(e->m, e->p, e->d_stamp, now, e->pbuf.live + r, e->stream);
+      if (int rc = check_launch(e, "par_round", 2)) return rc;
+    }
   }
   SWE_CUDA(cudaEventRecord(e->ev_f1, e->stream));
   // world.hpp:70-76: EMA of the flow fields
@@ -383,7 +427,7 @@ int swe_cascade_sweep(swe_engine* e, int sweeps, float* max_excess_out) {
   if (sweeps < 0) return fail(SWE_ERR_INVALID, "sweeps < 0");
   finish_timers(e);
   SWE_CUDA(cudaEventRecord(e->ev_c, e->stream));
-  const int n = launch_cascade_sweep(e->m, e->p, sweeps, e->d_stats, e->stream);
+  const int n = launch_cascade_sweep(e->m, e->p, sweeps, e->d_stats, e->stream, e->opt_cascade_variant);
   if (int rc = check_launch(e, "cascade_sweep", n)) return rc;
   SWE_CUDA(cudaEventRecord(e->ev_d, e->stream));
   e->sweep_timed = true;
@@ -550,6 +594,20 @@ int swe_hash_height(swe_engine* e, uint64_t* out) {
   for (uint32_t w : host) { h ^= w; h *= 1099511628211ull; }
   *out = h;
   return SWE_OK;
+}
+
+int swe_set_option(swe_engine* e, int option, int value) {
+  if (!e) return fail(SWE_ERR_INVALID, "engine is NULL");
+  switch (option) {
+    case SWE_OPT_CASCADE_VARIANT:
+      if (value != 0 && value != 1) return fail(SWE_ERR_INVALID, "cascade variant must be 0 or 1");
+      e->opt_cascade_variant = value; return SWE_OK;
+    case SWE_OPT_CASCADE_INTERVAL:
+      if (value < 1) return fail(SWE_ERR_INVALID, "cascade interval must be >= 1");
+      e->opt_cascade_interval = value; return SWE_OK;
+    default:
+      return fail(SWE_ERR_INVALID, "unknown option %d", option);
+  }
 }
 
 // ---- device-side plumbing -------------------------------------------------------------------

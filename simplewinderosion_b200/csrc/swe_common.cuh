@@ -65,13 +65,31 @@ void launch_normal_one(const MapView& m, const swe_params& p, int x, int z, floa
                        cudaStream_t st);
 
 // whole-map cascade: swe_cascade.cu
+// variant 0 = fused 9-colour shared-memory tile kernel, 1 = one global-memory launch per colour
 int launch_cascade_sweep(const MapView& m, const swe_params& p, int sweeps, DevStats* stats,
-                         cudaStream_t st);  // returns #kernel launches
+                         cudaStream_t st, int variant);  // returns #kernel launches
+// one fused sweep restricted to cells whose stamp byte equals stamp_now (flight pipeline)
+// (gate: device counter; the sweep is skipped when *gate == 0, i.e. no particle flew)
+void launch_cascade_stamped(const MapView& m, const swe_params& p, const unsigned char* stamp,
+                            unsigned char stamp_now, const unsigned* gate, cudaStream_t st);
 void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st);
 
 // parallel flight: swe_par.cu
-int launch_par_fly(const MapView& m, const swe_params& p, int n_particles, uint64_t seed,
-                   uint32_t call_index, DevStats* stats, cudaStream_t st);
+// Particle records of one World::erode call, 32 B each, SoA of two float4:
+//   a = {pos.x, pos.y, pos.z, sediment}   b = {speed.x, speed.y, speed.z, age (int bits; <0 = dead)}
+// live[r] = particles alive before round r (device counters, live_slots of them).
+struct ParticleBuf {
+  float4* a;
+  float4* b;
+  unsigned* live;
+  int live_slots;
+  int capacity;
+};
+void launch_par_begin(const ParticleBuf& buf, const MapView& m, int n, uint64_t seed, uint32_t call,
+                      DevStats* stats, cudaStream_t st);
+void launch_par_round(const ParticleBuf& buf, const MapView& m, const swe_params& p, int n, int round,
+                      int steps_per_round, uint64_t seed, uint32_t call, unsigned char* stamp,
+                      unsigned char stamp_now, DevStats* stats, cudaStream_t st);
 
 // field passes and utilities: swe_fields.cu
 void launch_ema(const MapView& m, float lrate, cudaStream_t st);
@@ -80,6 +98,5 @@ void launch_unpack_plane(const MapView& m, int plane, float* d_dst, cudaStream_t
 void launch_cells_to_planes(const MapView& m, const float* d_cells, cudaStream_t st);
 void launch_planes_to_cells(const MapView& m, float* d_cells, cudaStream_t st);
 void launch_sum_plane(const MapView& m, int plane, double* d_out, cudaStream_t st);
-void launch_hash_height(const MapView& m, unsigned long long* d_out, cudaStream_t st);
 
 }  // namespace swe

@@ -1,23 +1,32 @@
 // swe_par.cu -- parallel flight: all particles of a World::erode call in flight at once.
 //
-// One thread per particle (persistent, grid-stride respawn), same physics as Wind::fly
-// (source/wind.hpp:28-117) and World::cascade (source/world.hpp:79-153) with
-//   * a counter-based RNG (Philox4x32-10, counter = particle id / call / age) instead of the
-//     sequential libc rand() stream -- same distributions (rand()%1001, rand()%1000, rand()%n),
-//   * L2-coherent neighbourhood reads (ld.global.cg: other SMs' atomics are visible),
-//   * atomic scatter: one red.global.add.v4.f32 for the four track values (wind.hpp:93-96),
-//     red.global.add.f32 for the erosion/deposition of the centre cell (wind.hpp:110-112)
-//     and for every cascade transfer (world.hpp:142-149); each transfer is applied as a
-//     +t/-t pair so sand mass is conserved to fp32 round-off whatever the interleaving,
-//   * fast-math (FMA contraction, rsqrt, ex2-based exp): parity here is statistical.
+// Pipeline of one parallel World::erode(cycles) (the launcher is in swe_api.cu):
+//     spawn  ->  [ round kernel (K Wind::fly steps per live particle)  ->  stamped cascade sweep ] x R  -> EMA
+// with R = ceil((maxAge+2)/K) rounds. A round kernel thread owns one particle: it loads the
+// 32-byte particle record, runs K steps of the Wind::fly physics (source/wind.hpp:28-112)
+// against the current map and stores the record back. Map updates are atomic scatter:
+//   * one red.global.add.v4.f32 for the four track values (wind.hpp:93-96),
+//   * one red.global.add.f32 for the erosion/deposition of the centre cell (wind.hpp:110-112),
+//   * a byte stamp marking the cell as touched in this round.
+// The slope relaxation the reference runs after every step (World::cascade at the particle's
+// cell, wind.hpp:114) is NOT done per particle: concurrent particles applying full pairwise
+// corrections from the same stale snapshot overshoot and diverge (measured: heights reach
+// 1e10 within 40 steps). Instead, after each round every stamped cell gets World::cascade
+// exactly once, in the conflict-free 3x3 colour order, by the shared-memory tile kernel of
+// swe_cascade.cu -- exact Gauss-Seidel, unconditionally stable, deterministic given the map.
+//
+// Differences from the sequential reference (parity here is statistical, by construction):
+// counter-based RNG (Philox4x32-10, counter = particle id / call / age; same distributions
+// rand()%1001, rand()%1000, rand()%n), particles of a call see each other's deposits only
+// through the map, fast-math arithmetic, one cascade per touched cell per round.
 // Sediment carried by a particle when it dies leaves the system, as in the reference; it is
-// accumulated in DevStats::sediment_lost so tests can close the mass balance.
+// accumulated in DevStats::sediment_lost so the mass balance closes exactly.
 #include "swe_common.cuh"
 
 namespace swe {
 
 struct ParConst {
-  float inv_boundarylayer, suspension, gravity, settling_half, thr_ortho, thr_diag, mapscale;
+  float inv_boundarylayer, suspension, gravity, mapscale;
   float px, py, pz;      // pspeed
   float pnx, pny, pnz;   // normalize(pspeed)
   int max_age;
@@ -48,47 +57,32 @@ struct PState {
   int age;
 };
 
-// compare-exchange for a descending sort of (height, slot) pairs
-__device__ __forceinline__ void cex(float& ha, int& ia, float& hb, int& ib) {
-  const bool sw = hb > ha;
-  const float th = sw ? hb : ha, tl = sw ? ha : hb;
-  const int ti = sw ? ib : ia, tj = sw ? ia : ib;
-  ha = th; hb = tl; ia = ti; ib = tj;
-}
-
-// One Wind::fly step. Returns 0 = alive, 1 = left the map, 2 = too old.
-__device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PState& q,
-                                        uint32_t pid, uint2 key, uint32_t call) {
+// One Wind::fly step without the cascade. Returns 0 = alive, 1 = left the map, 2 = too old.
+__device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PState& q, uint32_t pid,
+                                        uint2 key, uint32_t call, unsigned char* stamp,
+                                        unsigned char stamp_now) {
   const int ix = __float2int_rd(q.px + 0.5f), iz = __float2int_rd(q.pz + 0.5f);  // wind.hpp:30
   if (m.oob(ix, iz)) return 1;                                                    // :32-38
   const int nz = m.nz;
-  float* hc_ptr = m.height + m.idx(ix, iz);
+  const size_t ci = m.idx(ix, iz);
+  float* hc_ptr = m.height + ci;
   const bool xm = ix > 0, xp = ix + 1 < m.nx, zm = iz > 0, zp = iz + 1 < nz;
 
-  // 3x3 neighbourhood, reference slot order (world.hpp:83-92); oob -> centre value, masked
+  // the five heights quad::_normal reads (cellpool.h:200-223); ld.global.cg = L2-coherent
   const float hc = __ldcg(hc_ptr);
-  float h[8];
-  h[0] = (xm && zm) ? __ldcg(hc_ptr - nz - 1) : hc;
-  h[1] = xm ? __ldcg(hc_ptr - nz) : hc;
-  h[2] = (xm && zp) ? __ldcg(hc_ptr - nz + 1) : hc;
-  h[3] = zm ? __ldcg(hc_ptr - 1) : hc;
-  h[4] = zp ? __ldcg(hc_ptr + 1) : hc;
-  h[5] = (xp && zm) ? __ldcg(hc_ptr + nz - 1) : hc;
-  h[6] = xp ? __ldcg(hc_ptr + nz) : hc;
-  h[7] = (xp && zp) ? __ldcg(hc_ptr + nz + 1) : hc;
+  const float hxm = xm ? __ldcg(hc_ptr - nz) : hc, hxp = xp ? __ldcg(hc_ptr + nz) : hc;
+  const float hzm = zm ? __ldcg(hc_ptr - 1) : hc, hzp = zp ? __ldcg(hc_ptr + 1) : hc;
 
-  // quad::_normal (cellpool.h:200-223) in closed form: plane (sx,sz) in {+,-}^2 counts iff
-  // the diagonal (ix+sx, iz+sz) is in bounds; each plane is (-sx*S*dhx, 1, -sz*S*dhz).
+  // closed form of the four-triangle normal: plane (sx,sz) in {+,-}^2 counts iff the diagonal
+  // (ix+sx, iz+sz) is in bounds; each plane is (-sx*S*dhx, 1, -sz*S*dhz).
   float nxv, nyv, nzv;
   {
     const float S = C.mapscale;
     const float cz = (zp ? 1.0f : 0.0f) + (zm ? 1.0f : 0.0f);
     const float cx = (xp ? 1.0f : 0.0f) + (xm ? 1.0f : 0.0f);
-    const float a = xp ? (h[6] - hc) : 0.0f, b = xm ? (h[1] - hc) : 0.0f;
-    const float c = zp ? (h[4] - hc) : 0.0f, d = zm ? (h[3] - hc) : 0.0f;
-    nxv = S * cz * (b - a);
+    nxv = S * cz * ((hxm - hc) - (hxp - hc));
     nyv = cx * cz;
-    nzv = S * cx * (d - c);
+    nzv = S * cx * ((hzm - hc) - (hzp - hc));
     const float l2 = nxv * nxv + nyv * nyv + nzv * nzv;
     if (l2 > 0.0f) { const float il = rsqrtf(l2); nxv *= il; nyv *= il; nzv *= il; }
   }
@@ -144,127 +138,129 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
   q.px += sx; q.py += sy; q.pz += sz;                                             // :91
   q.sx = sx; q.sy = sy; q.sz = sz;
 
-  red_add_v4(m.track + m.idx(ix, iz), q.sed, sx, sy, sz);                         // :93-96
-
-  float c;  // centre height as this particle sees it
+  red_add_v4(m.track + ci, q.sed, sx, sy, sz);                                    // :93-96
   {
     const float len = sqrtf(sx * sx + sy * sy + sz * sz);
     const float force = fmaxf(-(sx * nxv + sy * nyv + sz * nzv), 0.0f);           // :100-102
     const float lift = (1.0f - collision) * len;                                  // :104
     const float capacity = hfac * (force + 0.02f * lift);                         // :106
     const float dh = C.suspension * (capacity - q.sed);                           // :110-112
-    c = hc - dh;
     q.sed += dh;
+    if (dh != 0.0f) red_add_f32(hc_ptr, -dh);
   }
-
-  // World::cascade (world.hpp:79-153) on the register snapshot.
-  {
-    const unsigned valid = (xm && zm ? 1u : 0u) | (xm ? 2u : 0u) | (xm && zp ? 4u : 0u) |
-                           (zm ? 8u : 0u) | (zp ? 16u : 0u) | (xp && zm ? 32u : 0u) |
-                           (xp ? 64u : 0u) | (xp && zp ? 128u : 0u);
-    float worst = -1.0f;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const float t = ((0xA5u >> k) & 1u) ? C.thr_diag : C.thr_ortho;
-      const float e = fabsf(c - h[k]) - t;
-      worst = fmaxf(worst, ((valid >> k) & 1u) ? e : -1.0f);
-    }
-    if (worst > 0.0f) {
-      int s0 = 0, s1 = 1, s2 = 2, s3 = 3, s4 = 4, s5 = 5, s6 = 6, s7 = 7;
-      // 19-comparator network for 8 keys, descending (world.hpp:118-120)
-      cex(h[0], s0, h[1], s1); cex(h[2], s2, h[3], s3); cex(h[4], s4, h[5], s5); cex(h[6], s6, h[7], s7);
-      cex(h[0], s0, h[2], s2); cex(h[1], s1, h[3], s3); cex(h[4], s4, h[6], s6); cex(h[5], s5, h[7], s7);
-      cex(h[1], s1, h[2], s2); cex(h[5], s5, h[6], s6); cex(h[0], s0, h[4], s4); cex(h[3], s3, h[7], s7);
-      cex(h[1], s1, h[5], s5); cex(h[2], s2, h[6], s6);
-      cex(h[1], s1, h[4], s4); cex(h[3], s3, h[6], s6);
-      cex(h[2], s2, h[4], s4); cex(h[3], s3, h[5], s5);
-      cex(h[3], s3, h[4], s4);
-      const int slots[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
-#pragma unroll
-      for (int i = 0; i < 8; i++) {                                               // :122-151
-        const int k = slots[i];
-        const bool ok = (valid >> k) & 1u;
-        const float t = ((0xA5u >> k) & 1u) ? C.thr_diag : C.thr_ortho;
-        const float diff = c - h[i];
-        const float excess = fabsf(diff) - t;
-        if (ok && excess > 0.0f) {
-          const float tr = copysignf(C.settling_half * excess, diff);
-          c -= tr;
-          const int m9 = k + (k >> 2);            // 0,1,2,3,5,6,7,8: position in the 3x3 block
-          const int q3 = (m9 * 11) >> 5;          // m9 / 3
-          const int off = (q3 - 1) * nz + (m9 - 3 * q3 - 1);
-          red_add_f32(hc_ptr + off, tr);
-        }
-      }
-    }
-  }
-  const float dc = c - hc;
-  if (dc != 0.0f) red_add_f32(hc_ptr, dc);
+  stamp[ci] = stamp_now;                                                          // :114 (deferred)
   return 0;
 }
 
+// Wind ctor + spawn (world.hpp:52-54): cell = (rand()%nx, rand()%nz) + (rand()%1000)/1000
+__global__ void par_spawn_kernel(float4* __restrict__ pa, float4* __restrict__ pb, int n, int nx,
+                                 int nz, uint2 key, uint32_t call) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)i, call, 0u, 0x5u), key);
+  const float px = (float)__umulhi(r.x, (uint32_t)nx) + (float)__umulhi(r.z, 1000u) / 1000.0f;
+  const float pz = (float)__umulhi(r.y, (uint32_t)nz) + (float)__umulhi(r.w, 1000u) / 1000.0f;
+  pa[i] = make_float4(px, 0.0f, pz, 0.0f);
+  pb[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
+}
+
+// K steps for every live particle. live_in/live_out: device counters of particles alive
+// before/after this round (trailing rounds of a call exit at once when nothing is alive).
 __global__ void __launch_bounds__(256)
-par_fly_kernel(MapView m, ParConst C, int n_particles, uint2 key, uint32_t call, DevStats* stats) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  uint32_t next = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned steps = 0, n_oob = 0, n_age = 0, n_spawn = 0;
+par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restrict__ pb, int n,
+                 int steps_per_round, uint2 key, uint32_t call, unsigned char* stamp,
+                 unsigned char stamp_now, const unsigned* live_in, unsigned* live_out,
+                 DevStats* stats) {
+  if (live_in && *live_in == 0u) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned steps = 0, n_oob = 0, n_age = 0, alive = 0;
   float lost = 0.0f;
-  PState q;
-  uint32_t pid = 0;
-  bool alive = false;
-  while (true) {
-    if (!alive) {
-      if (next >= (uint32_t)n_particles) break;
-      pid = next; next += stride;
-      // world.hpp:52-54: cell = (rand()%nx, rand()%nz), plus (rand()%1000)/1000 in each axis
-      const uint4 r = philox4x32_10(make_uint4(pid, call, 0u, 0x5u), key);
-      q.px = (float)__umulhi(r.x, (uint32_t)m.nx) + (float)__umulhi(r.z, 1000u) / 1000.0f;
-      q.pz = (float)__umulhi(r.y, (uint32_t)m.nz) + (float)__umulhi(r.w, 1000u) / 1000.0f;
-      q.py = 0.0f; q.sx = q.sy = q.sz = 0.0f; q.sed = 0.0f; q.age = 0;
-      alive = true; n_spawn++;
+  if (i < n) {
+    const float4 b = pb[i];
+    PState q;
+    q.age = __float_as_int(b.w);
+    if (q.age >= 0) {
+      const float4 a = pa[i];
+      q.px = a.x; q.py = a.y; q.pz = a.z; q.sed = a.w;
+      q.sx = b.x; q.sy = b.y; q.sz = b.z;
+      int r = 0;
+      for (int s = 0; s < steps_per_round; s++) {
+        r = par_step(m, C, q, (uint32_t)i, key, call, stamp, stamp_now);
+        if (r != 0) break;
+        steps++;
+      }
+      if (r != 0) {
+        lost = q.sed;
+        if (r == 1) n_oob = 1; else n_age = 1;
+        q.age = -1;
+      } else {
+        alive = 1;
+      }
+      pa[i] = make_float4(q.px, q.py, q.pz, q.sed);
+      pb[i] = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
     }
-    const int r = par_step(m, C, q, pid, key, call);
-    if (r == 0) { steps++; }
-    else { alive = false; lost += q.sed; if (r == 1) n_oob++; else n_age++; }
   }
-  // warp-aggregate the counters, one atomic per warp
-  double lostd = (double)lost;
+  // block-aggregate the counters: one set of atomics per block
+  __shared__ unsigned s_cnt[4];
+  __shared__ float s_lost;
+  if (threadIdx.x == 0) { s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0u; s_lost = 0.0f; }
+  __syncthreads();
   for (int o = 16; o > 0; o >>= 1) {
     steps += __shfl_xor_sync(0xffffffffu, steps, o);
     n_oob += __shfl_xor_sync(0xffffffffu, n_oob, o);
     n_age += __shfl_xor_sync(0xffffffffu, n_age, o);
-    n_spawn += __shfl_xor_sync(0xffffffffu, n_spawn, o);
-    lostd += __shfl_xor_sync(0xffffffffu, lostd, o);
+    alive += __shfl_xor_sync(0xffffffffu, alive, o);
+    lost += __shfl_xor_sync(0xffffffffu, lost, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&stats->steps, (unsigned long long)steps);
-    atomicAdd(&stats->exits_oob, (unsigned long long)n_oob);
-    atomicAdd(&stats->exits_age, (unsigned long long)n_age);
-    atomicAdd(&stats->particles, (unsigned long long)n_spawn);
-    atomicAdd(&stats->sediment_lost, lostd);
+    if (steps) atomicAdd(&s_cnt[0], steps);
+    if (n_oob) atomicAdd(&s_cnt[1], n_oob);
+    if (n_age) atomicAdd(&s_cnt[2], n_age);
+    if (alive) atomicAdd(&s_cnt[3], alive);
+    if (lost != 0.0f) atomicAdd(&s_lost, lost);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_cnt[0]) atomicAdd(&stats->steps, (unsigned long long)s_cnt[0]);
+    if (s_cnt[1]) atomicAdd(&stats->exits_oob, (unsigned long long)s_cnt[1]);
+    if (s_cnt[2]) atomicAdd(&stats->exits_age, (unsigned long long)s_cnt[2]);
+    if (s_cnt[3]) atomicAdd(live_out, s_cnt[3]);
+    if (s_lost != 0.0f) atomicAdd(&stats->sediment_lost, (double)s_lost);
   }
 }
 
-int launch_par_fly(const MapView& m, const swe_params& p, int n_particles, uint64_t seed,
-                   uint32_t call_index, DevStats* stats, cudaStream_t st) {
-  if (n_particles <= 0) return 0;
+__global__ void par_begin_kernel(DevStats* stats, unsigned* live, int n_live_slots, unsigned n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { stats->particles += n; live[0] = n; }
+  else if (i < n_live_slots) live[i] = 0u;
+}
+
+static ParConst make_const(const swe_params& p) {
   ParConst C;
   C.inv_boundarylayer = 1.0f / p.boundarylayer;
   C.suspension = p.suspension; C.gravity = p.gravity;
-  C.settling_half = 0.5f * p.settling;
-  C.thr_ortho = p.maxdiff; C.thr_diag = sqrtf(2.0f) * p.maxdiff;
   C.mapscale = (float)p.mapscale;
   C.px = p.pspeed[0]; C.py = p.pspeed[1]; C.pz = p.pspeed[2];
   const float pl = sqrtf(C.px * C.px + C.py * C.py + C.pz * C.pz);
   C.pnx = C.px / pl; C.pny = C.py / pl; C.pnz = C.pz / pl;
   C.max_age = p.max_age;
+  return C;
+}
+
+void launch_par_begin(const ParticleBuf& buf, const MapView& m, int n, uint64_t seed, uint32_t call,
+                      DevStats* stats, cudaStream_t st) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  const int block = 256;
-  long long blocks = ((long long)n_particles + block - 1) / block;
-  const long long cap = 148LL * 8;  // persistent: 8 CTAs of 256 threads per SM
-  if (blocks > cap) blocks = cap;
-  par_fly_kernel<<<(int)blocks, block, 0, st>>>(m, C, n_particles, key, call_index, stats);
-  return 1;
+  par_begin_kernel<<<(buf.live_slots + 255) / 256, 256, 0, st>>>(stats, buf.live, buf.live_slots, (unsigned)n);
+  par_spawn_kernel<<<(n + 255) / 256, 256, 0, st>>>(buf.a, buf.b, n, m.nx, m.nz, key, call);
+}
+
+void launch_par_round(const ParticleBuf& buf, const MapView& m, const swe_params& p, int n, int round,
+                      int steps_per_round, uint64_t seed, uint32_t call, unsigned char* stamp,
+                      unsigned char stamp_now, DevStats* stats, cudaStream_t st) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  par_round_kernel<<<(n + 255) / 256, 256, 0, st>>>(m, make_const(p), buf.a, buf.b, n, steps_per_round,
+                                                    key, call, stamp, stamp_now, buf.live + round,
+                                                    buf.live + round + 1, stats);
 }
 
 }  // namespace swe

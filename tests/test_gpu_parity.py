@@ -185,23 +185,44 @@ def test_cascade_sweep_reference_fingerprints(case):
     assert f"{w.hash_height():016x}" == case["hash"]
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["tile", "percolour"])
 @pytest.mark.parametrize("nx,nz,sweeps", [(1, 1, 1), (1, 7, 2), (2, 2, 2), (3, 5, 2), (64, 64, 3), (100, 259, 2),
-                                          (257, 130, 2), (2048, 2048, 1)])
-def test_cascade_sweep_vs_oracle(nx, nz, sweeps):
+                                          (257, 130, 2), (59, 217, 2), (61, 215, 2), (2048, 2048, 1)])
+def test_cascade_sweep_vs_oracle(nx, nz, sweeps, variant):
     rs = np.random.RandomState(nx * 1000 + nz)
     hm = rs.random_sample((nx, nz)).astype(np.float32)
-    if nx >= 64:
+    if nx >= 59:
         hm[10:30, 5:40] = 0.5                      # plateau: exact ties
         hm[40:50, :] = np.round(hm[40:50, :] * 16) / 16
+        # heights that differ only in their last few bits (the tile kernel's sort keys give
+        # up 4 mantissa bits: these centres must take its exact fallback), incl. -0.0 / +0.0
+        blk = hm[30:40, 50:120]
+        base = np.float32(0.3) + np.float32(0.05) * rs.randint(0, 3, size=blk.shape).astype(np.float32)
+        hm[30:40, 50:120] = (base.view(np.uint32) + rs.randint(0, 12, size=blk.shape).astype(np.uint32)).view(np.float32)
+        hm[50:58, 10:60] = np.where(rs.random_sample((8, 50)) < 0.5, np.float32(-0.0), np.float32(0.0))
+        hm[52, 20] = -0.3; hm[55, 40] = 0.2
     ora = PortWorld(nx, nz)
     ora.set_plane(0, hm)
     w = swe.World(nx, nz)
+    w.set_option(swe.OPT_CASCADE_VARIANT, variant)
     w.upload(hm)
     for _ in range(sweeps):
         ex = w.cascade_sweep(1, want_excess=True)
         ora.cascade_sweep(1)
-        assert np.array_equal(bits(w.download()), bits(ora.plane(0)))
+        got, want = w.download(), ora.plane(0)
+        assert np.array_equal(bits(got), bits(want)), np.argwhere(bits(got) != bits(want))[:5]
         assert np.float32(ex).view(np.uint32) == np.float32(ora.max_excess()).view(np.uint32)
+
+
+def test_cascade_sweep_negative_heights_and_params():
+    nx, nz = 130, 222
+    rs = np.random.RandomState(8)
+    hm = (rs.random_sample((nx, nz)) - 0.5).astype(np.float32)
+    for kw in (dict(maxdiff=0.02, settling=0.6), dict(maxdiff=0.0, settling=1.0), dict(maxdiff=-0.01, settling=0.5)):
+        ora = PortWorld(nx, nz); ora.set(**kw); ora.set_plane(0, hm)
+        w = swe.World(nx, nz); w.set(**kw); w.upload(hm)
+        w.cascade_sweep(2); ora.cascade_sweep(2)
+        assert np.array_equal(bits(w.download()), bits(ora.plane(0))), kw
 
 
 def test_cascade_properties_full_size():
