@@ -67,8 +67,9 @@ typedef enum swe_mode {
 
 /* Engine options (swe_set_option). */
 typedef enum swe_option {
-  /* 0 (default) = fused nine-colour shared-memory tile kernel; 1 = one global-memory launch per
-   * colour. Both are bitwise identical to the reference order; 1 exists for cross-checking. */
+  /* 0 (default) = fused nine-colour shared-memory tile kernel, tile loaded by TMA when the row
+   * pitch allows; 1 = one global-memory launch per colour; 2 = fused tile kernel, plain loads.
+   * All are bitwise identical to the reference order; 1 and 2 exist for cross-checking. */
   SWE_OPT_CASCADE_VARIANT = 1,
   /* Parallel mode: Wind::fly steps each particle takes between two cascade passes (default 1:
    * like the reference, a touched cell is relaxed before any particle steps again). */

@@ -68,6 +68,7 @@ struct swe_engine {
   uint32_t call_index = 0;
   // parallel-mode state
   ParticleBuf pbuf{};
+  HeightTensorMap tmap{};
   unsigned char* d_stamp = nullptr;   // per-cell "touched in round" byte
   unsigned stamp_counter = 0;
   int opt_cascade_variant = 0;        // 0 fused tile kernel, 1 per-colour launches
@@ -202,6 +203,7 @@ int swe_create(swe_engine** out, int nx, int nz, const swe_params* params, int d
   TRY(cudaMemsetAsync(e->m.field, 0, n * sizeof(float4), e->stream));
   TRY(cudaMemsetAsync(e->m.track, 0, n * sizeof(float4), e->stream));
   TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(DevStats), e->stream));
+  make_height_tensor_map(e->m, &e->tmap);   // optional: plain-load kernels are used when it fails
   launch_det_srand(e->d_rng, 1u, e->stream);
   TRY(cudaGetLastError());
   e->launches++;
@@ -389,7 +391,7 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
       launch_par_round(e->pbuf, e->m, e->p, cycles, r, k, e->seed, e->call_index, e->d_stamp, now,
                        e->d_stats, e->stream);
       // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
-      launch_cascade_stamped(e->m, e->p, e->d_stamp, now, e->pbuf.live + r, e->stream);
+      launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, e->stream);
       if (int rc = check_launch(e, "par_round", 2)) return rc;
     }
   }
@@ -427,7 +429,7 @@ int swe_cascade_sweep(swe_engine* e, int sweeps, float* max_excess_out) {
   if (sweeps < 0) return fail(SWE_ERR_INVALID, "sweeps < 0");
   finish_timers(e);
   SWE_CUDA(cudaEventRecord(e->ev_c, e->stream));
-  const int n = launch_cascade_sweep(e->m, e->p, sweeps, e->d_stats, e->stream, e->opt_cascade_variant);
+  const int n = launch_cascade_sweep(e->m, e->p, &e->tmap, sweeps, e->d_stats, e->stream, e->opt_cascade_variant);
   if (int rc = check_launch(e, "cascade_sweep", n)) return rc;
   SWE_CUDA(cudaEventRecord(e->ev_d, e->stream));
   e->sweep_timed = true;
@@ -600,7 +602,7 @@ int swe_set_option(swe_engine* e, int option, int value) {
   if (!e) return fail(SWE_ERR_INVALID, "engine is NULL");
   switch (option) {
     case SWE_OPT_CASCADE_VARIANT:
-      if (value != 0 && value != 1) return fail(SWE_ERR_INVALID, "cascade variant must be 0 or 1");
+      if (value < 0 || value > 2) return fail(SWE_ERR_INVALID, "cascade variant must be 0, 1 or 2");
       e->opt_cascade_variant = value; return SWE_OK;
     case SWE_OPT_CASCADE_INTERVAL:
       if (value < 1) return fail(SWE_ERR_INVALID, "cascade interval must be >= 1");

@@ -15,6 +15,9 @@
 //   max_excess_kernel       -- convergence metric
 //
 // Compiled with -fmad=false; arithmetic through swe_exact.cuh.
+#include <cuda.h>
+#include <cstring>
+
 #include "swe_exact.cuh"
 
 namespace swe {
@@ -55,14 +58,23 @@ __global__ void cascade_colour_kernel(MapView m, swe_params P, int cx, int cz, i
 // Keys that differ only in the 4 bits given up to the code cannot be ordered this way; those
 // (rare) centres and NaN-free-ness are delegated to the generic exact core.
 // =============================================================================================
-constexpr int TILE_TX = 60, TILE_TZ = 216;
+constexpr int TILE_TX = 60, TILE_TZ = 216;                  // TZ: multiple of 3 and of 4
 constexpr int TILE_LX = TILE_TX + 6, TILE_PITCH = TILE_TZ + 24;
 constexpr int TILE_BX = TILE_TZ / 3 + 8, TILE_BY = 6;       // 80 x 6 = 480 threads
-constexpr int TILE_SMEM_BYTES = TILE_LX * TILE_PITCH * 4;   // 63,360 B
+constexpr int TILE_THREADS = TILE_BX * TILE_BY;
+constexpr int TILE_OX = -2, TILE_OZ = -8;                   // tile grid origin: == 1 (mod 3); z also == 0 (mod 4)
+constexpr int TILE_FLOAT_BYTES = TILE_LX * TILE_PITCH * 4;  // 63,360 B   height tile
+constexpr int TILE_STAMP_BYTES = TILE_LX * TILE_PITCH;      // 15,840 B   stamp tile (stamped sweeps only)
+constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + 16;      // + mbarrier
+constexpr int TILE_SMEM_STAMPED = TILE_FLOAT_BYTES + TILE_STAMP_BYTES + 16;
 
 __device__ __forceinline__ void cswap_desc(unsigned& a, unsigned& b) {
   const unsigned hi = max(a, b), lo = min(a, b);
   a = hi; b = lo;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
 }
 
 // generic exact fallback on the tile (same routine the single-cell path uses)
@@ -87,27 +99,78 @@ __device__ __noinline__ bool tile_cascade_generic(float* tile_c, int gx, int gz,
   return true;
 }
 
-template <bool USE_STAMP>
-__global__ void __launch_bounds__(TILE_BX * TILE_BY, 2)
-cascade_tile_kernel(MapView m, float settling, CascadeThr thr, const unsigned char* __restrict__ stamp,
-                    unsigned char stamp_now, const unsigned* __restrict__ gate) {
-  extern __shared__ float tile[];
+// USE_TMA: the height tile arrives by one cp.async.bulk.tensor.2d (UTMALDG) with hardware
+// zero-fill outside the map; needs nz % 4 == 0 (16-byte row pitch). Otherwise plain loads.
+template <bool USE_STAMP, bool USE_TMA>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
+                    const unsigned char* __restrict__ stamp, unsigned char stamp_now,
+                    const unsigned* __restrict__ gate) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   if (USE_STAMP && gate && *gate == 0u) return;
-  const int ox0 = -2 + (int)blockIdx.y * TILE_TX, oz0 = -2 + (int)blockIdx.x * TILE_TZ;
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  unsigned char* stile = smem_raw + TILE_FLOAT_BYTES;
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(
+      smem_raw + TILE_FLOAT_BYTES + (USE_STAMP ? TILE_STAMP_BYTES : 0));
+  const int ox0 = TILE_OX + (int)blockIdx.y * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
   const int gx0 = ox0 - 2, gz0 = oz0 - 8;          // global coords of tile[0][0]
   const int tid = threadIdx.y * TILE_BX + threadIdx.x;
   const int nx = m.nx, nz = m.nz;
   const bool generic_only = !(thr.ortho >= 0.0f) || !(thr.diag >= 0.0f);
+  const bool vec_ok = (nz & 3) == 0;               // rows are 16-byte aligned, tiles 4-aligned in z
 
-  // ---- load R_0 (cells outside the map are never read as neighbours) -------------------------
-  for (int i = tid; i < TILE_LX * TILE_PITCH; i += TILE_BX * TILE_BY) {
-    const int lx = i / TILE_PITCH, lz = i - lx * TILE_PITCH;
-    const int gx = gx0 + lx, gz = gz0 + lz;
-    float v = 0.0f;
-    if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) v = __ldg(m.height + m.idx(gx, gz));
-    tile[i] = v;
+  // ---- load R_0 ---------------------------------------------------------------------------
+  if (USE_TMA) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)),
+                   "r"(TILE_FLOAT_BYTES) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+          ::"r"(smem_u32(tile)), "l"(&tmap), "r"(gz0), "r"(gx0 - m.x0), "r"(smem_u32(mbar)) : "memory");
+    }
+  } else {
+    for (int i = tid; i < TILE_LX * TILE_PITCH; i += TILE_THREADS) {
+      const int lx = i / TILE_PITCH, lz = i - lx * TILE_PITCH;
+      const int gx = gx0 + lx, gz = gz0 + lz;
+      float v = 0.0f;
+      if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) v = __ldg(m.height + m.idx(gx, gz));
+      tile[i] = v;
+    }
   }
-  __syncthreads();
+  if (USE_STAMP) {
+    if (vec_ok) {   // 4 stamps per 32-bit load, whole words are inside or outside the map
+      unsigned* sw = reinterpret_cast<unsigned*>(stile);
+      for (int i = tid; i < TILE_LX * (TILE_PITCH / 4); i += TILE_THREADS) {
+        const int lx = i / (TILE_PITCH / 4), q = i - lx * (TILE_PITCH / 4);
+        const int gx = gx0 + lx, gz = gz0 + 4 * q;
+        unsigned v = 0u;
+        if (gx >= 0 && gx < nx && gz >= 0 && gz < nz)
+          v = __ldcg(reinterpret_cast<const unsigned*>(stamp + m.idx(gx, gz)));
+        sw[i] = v;
+      }
+    } else {
+      for (int i = tid; i < TILE_LX * TILE_PITCH; i += TILE_THREADS) {
+        const int lx = i / TILE_PITCH, lz = i - lx * TILE_PITCH;
+        const int gx = gx0 + lx, gz = gz0 + lz;
+        unsigned char v = 0;
+        if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) v = __ldcg(stamp + m.idx(gx, gz));
+        stile[i] = v;
+      }
+    }
+  }
+  __syncthreads();   // mbarrier init visible to all; plain loads / stamps complete
+  if (USE_TMA) {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(smem_u32(mbar)) : "memory");
+    }
+  }
 
   bool any_change = false;
 #pragma unroll 1
@@ -121,7 +184,7 @@ cascade_tile_kernel(MapView m, float settling, CascadeThr thr, const unsigned ch
         for (int cxi = threadIdx.y; cxi < ncx; cxi += TILE_BY) {
           const int lx = cxc + 1 + 3 * cxi, gx = gx0 + lx;
           if (gx < 0 || gx >= nx) continue;
-          if (USE_STAMP && stamp[m.idx(gx, gz)] != stamp_now) continue;
+          if (USE_STAMP && stile[lx * TILE_PITCH + lz] != stamp_now) continue;
           float* tc = tile + lx * TILE_PITCH + lz;
           const bool xm = gx > 0, xp = gx + 1 < nx;
           const float cen = tc[0];
@@ -193,11 +256,21 @@ cascade_tile_kernel(MapView m, float settling, CascadeThr thr, const unsigned ch
 
   // ---- store O if anything in this tile moved -----------------------------------------------
   if (__syncthreads_or(any_change ? 1 : 0)) {
-    for (int i = tid; i < TILE_TX * TILE_TZ; i += TILE_BX * TILE_BY) {
-      const int ox = i / TILE_TZ, oz = i - ox * TILE_TZ;
-      const int gx = ox0 + ox, gz = oz0 + oz;
-      if (gx >= 0 && gx < nx && gz >= 0 && gz < nz)
-        m.height[m.idx(gx, gz)] = tile[(ox + 2) * TILE_PITCH + (oz + 8)];
+    if (vec_ok) {
+      for (int i = tid; i < TILE_TX * (TILE_TZ / 4); i += TILE_THREADS) {
+        const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);
+        const int gx = ox0 + ox, gz = oz0 + 4 * q;
+        if (gx >= 0 && gx < nx && gz >= 0 && gz < nz)
+          *reinterpret_cast<float4*>(m.height + m.idx(gx, gz)) =
+              *reinterpret_cast<const float4*>(tile + (ox + 2) * TILE_PITCH + 8 + 4 * q);
+      }
+    } else {
+      for (int i = tid; i < TILE_TX * TILE_TZ; i += TILE_THREADS) {
+        const int ox = i / TILE_TZ, oz = i - ox * TILE_TZ;
+        const int gx = ox0 + ox, gz = oz0 + oz;
+        if (gx >= 0 && gx < nx && gz >= 0 && gz < nz)
+          m.height[m.idx(gx, gz)] = tile[(ox + 2) * TILE_PITCH + (oz + 8)];
+      }
     }
   }
 }
@@ -234,36 +307,83 @@ __global__ void set_float_kernel(float* p, float v) { *p = v; }
 
 __global__ void add_cascade_cells_kernel(DevStats* s, unsigned long long n) { s->cascade_cells += n; }
 
-static void launch_tile_sweep(const MapView& m, const swe_params& p, const unsigned char* stamp,
-                              unsigned char stamp_now, const unsigned* gate, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(cascade_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES);
-    cudaFuncSetAttribute(cascade_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES);
-    attr_set = true;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link needed)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+bool make_height_tensor_map(const MapView& m, HeightTensorMap* out) {
+  out->valid = false;
+  if ((m.nz & 3) != 0) return false;                        // row pitch must be a multiple of 16 B
+  static EncodeTiledFn encode = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
+  if (!encode) return false;
+  static_assert(sizeof(CUtensorMap) == sizeof(out->opaque), "tensor map size");
+  const cuuint64_t dims[2] = {(cuuint64_t)m.nz, (cuuint64_t)m.rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)m.nz * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)TILE_PITCH, (cuuint32_t)TILE_LX};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out->opaque), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                            m.height, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  out->valid = (r == CUDA_SUCCESS);
+  return out->valid;
+}
+
+template <bool S, bool T>
+static void tile_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, const CUtensorMap& tm,
+                        const MapView& m, float settling, CascadeThr thr, const unsigned char* stamp,
+                        unsigned char now, const unsigned* gate) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(cascade_tile_kernel<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  cascade_tile_kernel<S, T><<<grid, block, smem, st>>>(tm, m, settling, thr, stamp, now, gate);
+}
+
+static void launch_tile_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
+                              const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
+                              cudaStream_t st) {
   CascadeThr thr;
   thr.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;      // host IEEE fp32: same values as the device helper
   thr.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
-  const dim3 grid((m.nz + 2 + TILE_TZ - 1) / TILE_TZ, (m.nx + 2 + TILE_TX - 1) / TILE_TX);
+  const dim3 grid((m.nz - TILE_OZ + TILE_TZ - 1) / TILE_TZ, (m.nx - TILE_OX + TILE_TX - 1) / TILE_TX);
   const dim3 block(TILE_BX, TILE_BY);
-  if (stamp)
-    cascade_tile_kernel<true><<<grid, block, TILE_SMEM_BYTES, st>>>(m, p.settling, thr, stamp, stamp_now, gate);
-  else
-    cascade_tile_kernel<false><<<grid, block, TILE_SMEM_BYTES, st>>>(m, p.settling, thr, nullptr, 0, nullptr);
+  const bool tma = tmap && tmap->valid;
+  CUtensorMap tm;
+  if (tma) memcpy(&tm, tmap->opaque, sizeof tm); else memset(&tm, 0, sizeof tm);
+  if (stamp) {
+    if (tma) tile_launch<true, true>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate);
+    else     tile_launch<true, false>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate);
+  } else {
+    if (tma) tile_launch<false, true>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr);
+    else     tile_launch<false, false>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr);
+  }
 }
 
-void launch_cascade_stamped(const MapView& m, const swe_params& p, const unsigned char* stamp,
-                            unsigned char stamp_now, const unsigned* gate, cudaStream_t st) {
-  launch_tile_sweep(m, p, stamp, stamp_now, gate, st);
+void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
+                            const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
+                            cudaStream_t st) {
+  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, st);
 }
 
-int launch_cascade_sweep(const MapView& m, const swe_params& p, int sweeps, DevStats* stats,
-                         cudaStream_t st, int variant) {
+int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap, int sweeps,
+                         DevStats* stats, cudaStream_t st, int variant) {
   int launches = 0;
   for (int s = 0; s < sweeps; s++) {
-    if (variant == 0) {
-      launch_tile_sweep(m, p, nullptr, 0, nullptr, st);
+    if (variant == 0 || variant == 2) {
+      launch_tile_sweep(m, p, variant == 2 ? nullptr : tmap, nullptr, 0, nullptr, st);
       launches++;
       continue;
     }

@@ -65,13 +65,21 @@ void launch_normal_one(const MapView& m, const swe_params& p, int x, int z, floa
                        cudaStream_t st);
 
 // whole-map cascade: swe_cascade.cu
-// variant 0 = fused 9-colour shared-memory tile kernel, 1 = one global-memory launch per colour
-int launch_cascade_sweep(const MapView& m, const swe_params& p, int sweeps, DevStats* stats,
-                         cudaStream_t st, int variant);  // returns #kernel launches
+// TMA descriptor of the height plane (CUtensorMap, kept opaque here), built once per engine.
+struct alignas(64) HeightTensorMap {
+  unsigned char opaque[128];
+  bool valid;
+};
+bool make_height_tensor_map(const MapView& m, HeightTensorMap* out);
+// variant 0 = fused 9-colour shared-memory tile kernel (TMA tile load when the descriptor is
+// valid), 1 = one global-memory launch per colour, 2 = fused tile kernel with plain loads
+int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap, int sweeps,
+                         DevStats* stats, cudaStream_t st, int variant);  // returns #kernel launches
 // one fused sweep restricted to cells whose stamp byte equals stamp_now (flight pipeline)
 // (gate: device counter; the sweep is skipped when *gate == 0, i.e. no particle flew)
-void launch_cascade_stamped(const MapView& m, const swe_params& p, const unsigned char* stamp,
-                            unsigned char stamp_now, const unsigned* gate, cudaStream_t st);
+void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
+                            const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
+                            cudaStream_t st);
 void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st);
 
 // parallel flight: swe_par.cu

@@ -17,8 +17,9 @@
 //
 // Differences from the sequential reference (parity here is statistical, by construction):
 // counter-based RNG (Philox4x32-10, counter = particle id / call / age; same distributions
-// rand()%1001, rand()%1000, rand()%n), particles of a call see each other's deposits only
-// through the map, fast-math arithmetic, one cascade per touched cell per round.
+// rand()%1001, rand()%1000; spawn cells stratified-uniform, see par_spawn_kernel), particles of
+// a call see each other's deposits only through the map, fast-math arithmetic, one cascade per
+// touched cell per round.
 // Sediment carried by a particle when it dies leaves the system, as in the reference; it is
 // accumulated in DevStats::sediment_lost so the mass balance closes exactly.
 #include "swe_common.cuh"
@@ -152,14 +153,29 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
   return 0;
 }
 
-// Wind ctor + spawn (world.hpp:52-54): cell = (rand()%nx, rand()%nz) + (rand()%1000)/1000
+// Wind ctor + spawn (world.hpp:52-54: cell = (rand()%nx, rand()%nz), plus (rand()%1000)/1000 per
+// axis). The reference draws iid uniform cells; here the n particles of a call are a STRATIFIED
+// uniform sample: the cells are ordered strip-major (strips of 4 rows, z-major inside a strip)
+// and particle i takes the cell of rank floor((i + u) * ncells / n), u ~ U[0,1). Every cell is
+// equally likely, as in the reference, and particles adjacent in memory start adjacent on the map
+// (a warp covers ~4 rows x 32 columns at 0.25 particles/cell), so a warp's neighbourhood reads
+// and atomics fall into a handful of 32-byte sectors instead of 32 scattered ones.
 __global__ void par_spawn_kernel(float4* __restrict__ pa, float4* __restrict__ pb, int n, int nx,
                                  int nz, uint2 key, uint32_t call) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint4 r = philox4x32_10(make_uint4((uint32_t)i, call, 0u, 0x5u), key);
-  const float px = (float)__umulhi(r.x, (uint32_t)nx) + (float)__umulhi(r.z, 1000u) / 1000.0f;
-  const float pz = (float)__umulhi(r.y, (uint32_t)nz) + (float)__umulhi(r.w, 1000u) / 1000.0f;
+  const unsigned long long ncells = (unsigned long long)nx * (unsigned long long)nz;
+  unsigned long long rank =
+      ((unsigned long long)i * ncells + (((unsigned long long)r.x * ncells) >> 32)) / (unsigned long long)n;
+  if (rank >= ncells) rank = ncells - 1;
+  const unsigned long long strip_cells = 4ull * (unsigned long long)nz;
+  const int strip = (int)(rank / strip_cells);
+  const unsigned q = (unsigned)(rank - (unsigned long long)strip * strip_cells);
+  const int rows = min(4, nx - 4 * strip);
+  const int cz = (int)(q / (unsigned)rows), cx = 4 * strip + (int)(q - (unsigned)cz * (unsigned)rows);
+  const float px = (float)cx + (float)__umulhi(r.z, 1000u) / 1000.0f;
+  const float pz = (float)cz + (float)__umulhi(r.w, 1000u) / 1000.0f;
   pa[i] = make_float4(px, 0.0f, pz, 0.0f);
   pb[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
 }

@@ -185,9 +185,9 @@ def test_cascade_sweep_reference_fingerprints(case):
     assert f"{w.hash_height():016x}" == case["hash"]
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["tile", "percolour"])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["tile-tma", "percolour", "tile-plain"])
 @pytest.mark.parametrize("nx,nz,sweeps", [(1, 1, 1), (1, 7, 2), (2, 2, 2), (3, 5, 2), (64, 64, 3), (100, 259, 2),
-                                          (257, 130, 2), (59, 217, 2), (61, 215, 2), (2048, 2048, 1)])
+                                          (257, 130, 2), (59, 217, 2), (61, 216, 2), (300, 1000, 2), (2048, 2048, 1)])
 def test_cascade_sweep_vs_oracle(nx, nz, sweeps, variant):
     rs = np.random.RandomState(nx * 1000 + nz)
     hm = rs.random_sample((nx, nz)).astype(np.float32)
