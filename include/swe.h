@@ -73,7 +73,10 @@ typedef enum swe_option {
   SWE_OPT_CASCADE_VARIANT = 1,
   /* Parallel mode: Wind::fly steps each particle takes between two cascade passes (default 1:
    * like the reference, a touched cell is relaxed before any particle steps again). */
-  SWE_OPT_CASCADE_INTERVAL = 2
+  SWE_OPT_CASCADE_INTERVAL = 2,
+  /* 1 = record CUDA events around every particle-round and cascade launch of swe_erode so that
+   * swe_stats.last_round_ms / last_cascade_ms report each kernel's share (default 0). */
+  SWE_OPT_KERNEL_TIMING = 3
 } swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:
@@ -113,7 +116,9 @@ typedef struct swe_stats {
   double last_erode_ms;    /* device time of the last swe_erode (CUDA events) */
   double last_sweep_ms;    /* device time of the last swe_cascade_sweep call */
   uint64_t kernel_launches;/* kernels launched by the engine so far */
-  double last_fly_ms;      /* device time of the particle kernel(s) inside the last swe_erode */
+  double last_fly_ms;      /* device time of the particle phase (rounds + cascades) of the last swe_erode */
+  double last_round_ms;    /* with SWE_OPT_KERNEL_TIMING: sum over the particle-round kernels */
+  double last_cascade_ms;  /* with SWE_OPT_KERNEL_TIMING: sum over the per-round cascade kernels */
 } swe_stats;
 
 typedef struct swe_engine swe_engine;

@@ -61,6 +61,8 @@ class Stats(C.Structure):
         ("last_sweep_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
         ("last_fly_ms", C.c_double),
+        ("last_round_ms", C.c_double),
+        ("last_cascade_ms", C.c_double),
     ]
 
 

@@ -73,6 +73,10 @@ struct swe_engine {
   unsigned stamp_counter = 0;
   int opt_cascade_variant = 0;        // 0 fused tile kernel, 1 per-colour launches
   int opt_cascade_interval = 1;       // Wind::fly steps per particle between cascade passes
+  int opt_kernel_timing = 0;          // record an event pair around every round / cascade launch
+  std::vector<cudaEvent_t> kt_events; // [3*r] before round, [3*r+1] between, [3*r+2] after cascade
+  int kt_rounds = 0;
+  double last_round_ms = 0.0, last_cascade_ms = 0.0;
   uint64_t launches = 0, erode_calls = 0;
   double last_erode_ms = 0.0, last_sweep_ms = 0.0, last_fly_ms = 0.0;
 
@@ -138,6 +142,15 @@ void finish_timers(swe_engine* e) {
   if (e->erode_timed && cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->last_erode_ms = ms;
   if (e->erode_timed && cudaEventElapsedTime(&ms, e->ev_f0, e->ev_f1) == cudaSuccess) e->last_fly_ms = ms;
   if (e->sweep_timed && cudaEventElapsedTime(&ms, e->ev_c, e->ev_d) == cudaSuccess) e->last_sweep_ms = ms;
+  if (e->erode_timed && e->kt_rounds > 0) {
+    double r_ms = 0.0, c_ms = 0.0;
+    for (int r = 0; r < e->kt_rounds; r++) {
+      if (cudaEventElapsedTime(&ms, e->kt_events[3 * r], e->kt_events[3 * r + 1]) == cudaSuccess) r_ms += ms;
+      if (cudaEventElapsedTime(&ms, e->kt_events[3 * r + 1], e->kt_events[3 * r + 2]) == cudaSuccess) c_ms += ms;
+    }
+    e->last_round_ms = r_ms; e->last_cascade_ms = c_ms;
+    e->kt_rounds = 0;
+  }
   e->erode_timed = e->sweep_timed = false;
 }
 
@@ -236,6 +249,7 @@ void swe_destroy(swe_engine* e) {
   if (e->ev_d) cudaEventDestroy(e->ev_d);
   if (e->ev_f0) cudaEventDestroy(e->ev_f0);
   if (e->ev_f1) cudaEventDestroy(e->ev_f1);
+  for (cudaEvent_t ev : e->kt_events) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -388,10 +402,19 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
         e->stamp_counter = 1;
       }
       const unsigned char now = (unsigned char)e->stamp_counter;
+      const bool kt = e->opt_kernel_timing != 0;
+      if (kt) {
+        while ((int)e->kt_events.size() < 3 * (r + 1)) {
+          cudaEvent_t ev; SWE_CUDA(cudaEventCreate(&ev)); e->kt_events.push_back(ev);
+        }
+        SWE_CUDA(cudaEventRecord(e->kt_events[3 * r], e->stream));
+      }
       launch_par_round(e->pbuf, e->m, e->p, cycles, r, k, e->seed, e->call_index, e->d_stamp, now,
                        e->d_stats, e->stream);
+      if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
       // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
       launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, e->stream);
+      if (kt) { SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 2], e->stream)); e->kt_rounds = r + 1; }
       if (int rc = check_launch(e, "par_round", 2)) return rc;
     }
   }
@@ -564,6 +587,8 @@ int swe_get_stats(swe_engine* e, swe_stats* out) {
   out->last_erode_ms = e->last_erode_ms; out->last_sweep_ms = e->last_sweep_ms;
   out->kernel_launches = e->launches;
   out->last_fly_ms = e->last_fly_ms;
+  out->last_round_ms = e->last_round_ms;
+  out->last_cascade_ms = e->last_cascade_ms;
   return SWE_OK;
 }
 
@@ -607,6 +632,8 @@ int swe_set_option(swe_engine* e, int option, int value) {
     case SWE_OPT_CASCADE_INTERVAL:
       if (value < 1) return fail(SWE_ERR_INVALID, "cascade interval must be >= 1");
       e->opt_cascade_interval = value; return SWE_OK;
+    case SWE_OPT_KERNEL_TIMING:
+      e->opt_kernel_timing = value ? 1 : 0; return SWE_OK;
     default:
       return fail(SWE_ERR_INVALID, "unknown option %d", option);
   }

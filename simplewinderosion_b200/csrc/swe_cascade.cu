@@ -65,8 +65,9 @@ constexpr int TILE_THREADS = TILE_BX * TILE_BY;
 constexpr int TILE_OX = -2, TILE_OZ = -8;                   // tile grid origin: == 1 (mod 3); z also == 0 (mod 4)
 constexpr int TILE_FLOAT_BYTES = TILE_LX * TILE_PITCH * 4;  // 63,360 B   height tile
 constexpr int TILE_STAMP_BYTES = TILE_LX * TILE_PITCH;      // 15,840 B   stamp tile (stamped sweeps only)
-constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + 16;      // + mbarrier
-constexpr int TILE_SMEM_STAMPED = TILE_FLOAT_BYTES + TILE_STAMP_BYTES + 16;
+constexpr int TILE_QUEUE_BYTES = ((TILE_LX / 3) * (TILE_PITCH / 3) * 2 + 15) / 16 * 16;  // centres of one colour
+constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 16;   // + queue counters, mbarrier
+constexpr int TILE_SMEM_STAMPED = TILE_SMEM_PLAIN + TILE_STAMP_BYTES;
 
 __device__ __forceinline__ void cswap_desc(unsigned& a, unsigned& b) {
   const unsigned hi = max(a, b), lo = min(a, b);
@@ -99,8 +100,108 @@ __device__ __noinline__ bool tile_cascade_generic(float* tile_c, int gx, int gz,
   return true;
 }
 
+// ---- per-centre pieces ----------------------------------------------------------------------
+// INTERIOR tiles lie wholly inside the map (all eight neighbours of every centre exist), so the
+// validity predicates vanish at compile time; border tiles use the same code with them.
+struct Valid8 { bool v0, v1, v2, v3, v4, v5, v6, v7; };
+
+template <bool INTERIOR>
+__device__ __forceinline__ Valid8 centre_valid(int gx, int gz, int nx, int nz) {
+  Valid8 v;
+  if (INTERIOR) { v.v0 = v.v1 = v.v2 = v.v3 = v.v4 = v.v5 = v.v6 = v.v7 = true; return v; }
+  const bool xm = gx > 0, xp = gx + 1 < nx, zm = gz > 0, zp = gz + 1 < nz;
+  v.v0 = xm && zm; v.v1 = xm; v.v2 = xm && zp; v.v3 = zm; v.v4 = zp; v.v5 = xp && zm; v.v6 = xp; v.v7 = xp && zp;
+  return v;
+}
+
+// exact early-out test (thresholds >= 0): does any in-map neighbour exceed its repose gap?
+// If none does, the reference's loop (world.hpp:122-151) transfers nothing.
+template <bool INTERIOR>
+__device__ __forceinline__ bool centre_needs(const float* tc, const CascadeThr thr, const Valid8 v) {
+  const float cen = tc[0];
+  const float e0 = fsub(fabsf(fsub(cen, tc[-TILE_PITCH - 1])), thr.diag);
+  const float e1 = fsub(fabsf(fsub(cen, tc[-TILE_PITCH])), thr.ortho);
+  const float e2 = fsub(fabsf(fsub(cen, tc[-TILE_PITCH + 1])), thr.diag);
+  const float e3 = fsub(fabsf(fsub(cen, tc[-1])), thr.ortho);
+  const float e4 = fsub(fabsf(fsub(cen, tc[1])), thr.ortho);
+  const float e5 = fsub(fabsf(fsub(cen, tc[TILE_PITCH - 1])), thr.diag);
+  const float e6 = fsub(fabsf(fsub(cen, tc[TILE_PITCH])), thr.ortho);
+  const float e7 = fsub(fabsf(fsub(cen, tc[TILE_PITCH + 1])), thr.diag);
+  if (INTERIOR) {
+    // !(e <= 0) for any e  <=>  !(all e <= 0); NaN excesses count as "needs" like the reference
+    return !((e0 <= 0.0f) & (e1 <= 0.0f) & (e2 <= 0.0f) & (e3 <= 0.0f) & (e4 <= 0.0f) & (e5 <= 0.0f) &
+             (e6 <= 0.0f) & (e7 <= 0.0f));
+  }
+  return (v.v0 && !(e0 <= 0.0f)) || (v.v1 && !(e1 <= 0.0f)) || (v.v2 && !(e2 <= 0.0f)) ||
+         (v.v3 && !(e3 <= 0.0f)) || (v.v4 && !(e4 <= 0.0f)) || (v.v5 && !(e5 <= 0.0f)) ||
+         (v.v6 && !(e6 <= 0.0f)) || (v.v7 && !(e7 <= 0.0f));
+}
+
+// order-preserving key of a neighbour height: descending float order == descending unsigned
+// order; (h + 0) folds -0 onto +0 (they tie in the reference's comparison); the low 4 bits carry
+// 15 - code, code = (dx+1)*4 + (dz+1) = reference slot order, so equal heights keep slot order
+// (std::sort on <= 16 elements is a stable insertion sort) and the chain can find the cell.
+__device__ __forceinline__ unsigned height_key(float h, bool valid, unsigned code) {
+  const unsigned u = __float_as_uint(fadd(h, 0.0f));
+  const unsigned k = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+  return valid ? ((k & ~15u) | (15u - code)) : 0u;
+}
+
+// one element of the transfer chain (world.hpp:122-151), branch-free; thresholds >= 0 so that
+// diff == 0 implies excess <= 0 and the reference's explicit diff == 0 test is subsumed.
+__device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, const CascadeThr thr,
+                                           float settling) {
+  const unsigned code = 15u - (k & 15u);
+  float* hp = tc + ((int)(code >> 2) - 1) * TILE_PITCH + ((int)(code & 3u) - 1);
+  const float hv = *hp;
+  const float t = (code & 5u) ? thr.ortho : thr.diag;
+  const float diff = fsub(cc, hv);
+  const float excess = fsub(fabsf(diff), t);
+  const bool go = (k != 0u) && !(excess <= 0.0f);
+  const float transfer = fmul(fmul(settling, excess), 0.5f);     // (settling*excess)/2.0f
+  const float sgn = (diff > 0.0f) ? transfer : -transfer;        // diff > 0: centre gives, else takes
+  if (go) { cc = fsub(cc, sgn); *hp = fadd(hv, sgn); }
+}
+
+// World::cascade at one centre of the tile whose early-out test failed.
+template <bool INTERIOR>
+__device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, float settling, const Valid8 v,
+                                             int gx, int gz, int nx, int nz) {
+  unsigned k0 = height_key(tc[-TILE_PITCH - 1], v.v0, 0), k1 = height_key(tc[-TILE_PITCH], v.v1, 1),
+           k2 = height_key(tc[-TILE_PITCH + 1], v.v2, 2), k3 = height_key(tc[-1], v.v3, 4),
+           k4 = height_key(tc[1], v.v4, 6), k5 = height_key(tc[TILE_PITCH - 1], v.v5, 8),
+           k6 = height_key(tc[TILE_PITCH], v.v6, 9), k7 = height_key(tc[TILE_PITCH + 1], v.v7, 10);
+  // 19-comparator network, descending (world.hpp:118-120)
+  cswap_desc(k0, k2); cswap_desc(k1, k3); cswap_desc(k4, k6); cswap_desc(k5, k7);
+  cswap_desc(k0, k4); cswap_desc(k1, k5); cswap_desc(k2, k6); cswap_desc(k3, k7);
+  cswap_desc(k0, k1); cswap_desc(k2, k3); cswap_desc(k4, k5); cswap_desc(k6, k7);
+  cswap_desc(k2, k4); cswap_desc(k3, k5);
+  cswap_desc(k1, k4); cswap_desc(k3, k6);
+  cswap_desc(k1, k2); cswap_desc(k3, k4); cswap_desc(k5, k6);
+  // heights that agree in everything but the 4 bits given up to the code cannot be ordered by
+  // the keys: hand those (rare) centres to the generic exact core
+  unsigned close = min(min(k0 ^ k1, (k2 ? k1 ^ k2 : ~0u)), min((k3 ? k2 ^ k3 : ~0u), (k4 ? k3 ^ k4 : ~0u)));
+  close = min(close, min(min((k5 ? k4 ^ k5 : ~0u), (k6 ? k5 ^ k6 : ~0u)), (k7 ? k6 ^ k7 : ~0u)));
+  if ((INTERIOR || k1) && close < 16u) {
+    tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
+    return;
+  }
+  float cc = tc[0];
+  chain_step(tc, k0, cc, thr, settling); chain_step(tc, k1, cc, thr, settling);
+  chain_step(tc, k2, cc, thr, settling); chain_step(tc, k3, cc, thr, settling);
+  chain_step(tc, k4, cc, thr, settling); chain_step(tc, k5, cc, thr, settling);
+  chain_step(tc, k6, cc, thr, settling); chain_step(tc, k7, cc, thr, settling);
+  tc[0] = cc;
+}
+
 // USE_TMA: the height tile arrives by one cp.async.bulk.tensor.2d (UTMALDG) with hardware
 // zero-fill outside the map; needs nz % 4 == 0 (16-byte row pitch). Otherwise plain loads.
+//
+// Each colour phase is split in two so that the expensive part runs on full warps:
+//   scan  : every thread tests its centres (stamp, early-out) and appends the ones that need
+//           World::cascade to a shared-memory queue (warp-aggregated append);
+//   relax : the queue is processed densely, one entry per thread.
+// On a map close to the repose angle only a few per cent of the centres reach the queue.
 template <bool USE_STAMP, bool USE_TMA>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
@@ -109,17 +210,20 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (USE_STAMP && gate && *gate == 0u) return;
   float* tile = reinterpret_cast<float*>(smem_raw);
-  unsigned char* stile = smem_raw + TILE_FLOAT_BYTES;
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(
-      smem_raw + TILE_FLOAT_BYTES + (USE_STAMP ? TILE_STAMP_BYTES : 0));
+  unsigned short* queue = reinterpret_cast<unsigned short*>(smem_raw + TILE_FLOAT_BYTES);
+  unsigned* qcount = reinterpret_cast<unsigned*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES);  // [2]
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 8);
+  unsigned char* stile = smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 16;
   const int ox0 = TILE_OX + (int)blockIdx.y * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
   const int gx0 = ox0 - 2, gz0 = oz0 - 8;          // global coords of tile[0][0]
   const int tid = threadIdx.y * TILE_BX + threadIdx.x;
   const int nx = m.nx, nz = m.nz;
   const bool generic_only = !(thr.ortho >= 0.0f) || !(thr.diag >= 0.0f);
   const bool vec_ok = (nz & 3) == 0;               // rows are 16-byte aligned, tiles 4-aligned in z
+  const bool interior = gx0 >= 0 && gz0 >= 0 && gx0 + TILE_LX <= nx && gz0 + TILE_PITCH <= nz;
 
   // ---- load R_0 ---------------------------------------------------------------------------
+  if (tid == 0) { qcount[0] = 0u; qcount[1] = 0u; }
   if (USE_TMA) {
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -160,7 +264,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       }
     }
   }
-  __syncthreads();   // mbarrier init visible to all; plain loads / stamps complete
+  __syncthreads();   // mbarrier init + queue counters visible; plain loads / stamps complete
   if (USE_TMA) {
     unsigned done = 0;
     while (!done) {
@@ -173,89 +277,60 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   }
 
   bool any_change = false;
+  const unsigned lane = tid & 31;
 #pragma unroll 1
   for (int c = 0; c < 9; c++) {
     const int cxc = c / 3;
     const int ncx = TILE_TX / 3 + 2 - cxc, ncz = TILE_TZ / 3 + 8 - c;
-    if ((int)threadIdx.x < ncz) {
+    unsigned* qc = qcount + (c & 1);
+    // ---- scan --------------------------------------------------------------------------------
+    {
       const int lz = c + 1 + 3 * (int)threadIdx.x, gz = gz0 + lz;
-      if (gz >= 0 && gz < nz) {
-        const bool zm = gz > 0, zp = gz + 1 < nz;
-        for (int cxi = threadIdx.y; cxi < ncx; cxi += TILE_BY) {
-          const int lx = cxc + 1 + 3 * cxi, gx = gx0 + lx;
-          if (gx < 0 || gx >= nx) continue;
-          if (USE_STAMP && stile[lx * TILE_PITCH + lz] != stamp_now) continue;
-          float* tc = tile + lx * TILE_PITCH + lz;
-          const bool xm = gx > 0, xp = gx + 1 < nx;
-          const float cen = tc[0];
-          // reference slot order (world.hpp:83-92) = lexicographic in (dx, dz)
-          const float h0 = tc[-TILE_PITCH - 1], h1 = tc[-TILE_PITCH], h2 = tc[-TILE_PITCH + 1];
-          const float h3 = tc[-1], h4 = tc[1];
-          const float h5 = tc[TILE_PITCH - 1], h6 = tc[TILE_PITCH], h7 = tc[TILE_PITCH + 1];
-          const bool v0 = xm && zm, v1 = xm, v2 = xm && zp, v3 = zm, v4 = zp, v5 = xp && zm, v6 = xp,
-                     v7 = xp && zp;
-          // (2) exact early-out: no neighbour exceeds its repose gap -> nothing moves
-          bool need = false;
-          need |= v0 && !(fsub(fabsf(fsub(cen, h0)), thr.diag) <= 0.0f);
-          need |= v1 && !(fsub(fabsf(fsub(cen, h1)), thr.ortho) <= 0.0f);
-          need |= v2 && !(fsub(fabsf(fsub(cen, h2)), thr.diag) <= 0.0f);
-          need |= v3 && !(fsub(fabsf(fsub(cen, h3)), thr.ortho) <= 0.0f);
-          need |= v4 && !(fsub(fabsf(fsub(cen, h4)), thr.ortho) <= 0.0f);
-          need |= v5 && !(fsub(fabsf(fsub(cen, h5)), thr.diag) <= 0.0f);
-          need |= v6 && !(fsub(fabsf(fsub(cen, h6)), thr.ortho) <= 0.0f);
-          need |= v7 && !(fsub(fabsf(fsub(cen, h7)), thr.diag) <= 0.0f);
-          if (!need) continue;
-          if (generic_only) { any_change |= tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling); continue; }
-          // (3) sort: key = order-preserving bits of (h + 0) [folds -0 onto +0], low 4 bits
-          // = 15 - code, code = (dx+1)*4 + (dz+1); out-of-map neighbours get key 0 (last).
-          auto mk = [](float h, bool valid, unsigned code) -> unsigned {
-            const unsigned u = __float_as_uint(fadd(h, 0.0f));
-            const unsigned k = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
-            return valid ? ((k & ~15u) | (15u - code)) : 0u;
-          };
-          unsigned k0 = mk(h0, v0, 0), k1 = mk(h1, v1, 1), k2 = mk(h2, v2, 2), k3 = mk(h3, v3, 4),
-                   k4 = mk(h4, v4, 6), k5 = mk(h5, v5, 8), k6 = mk(h6, v6, 9), k7 = mk(h7, v7, 10);
-          cswap_desc(k0, k2); cswap_desc(k1, k3); cswap_desc(k4, k6); cswap_desc(k5, k7);
-          cswap_desc(k0, k4); cswap_desc(k1, k5); cswap_desc(k2, k6); cswap_desc(k3, k7);
-          cswap_desc(k0, k1); cswap_desc(k2, k3); cswap_desc(k4, k5); cswap_desc(k6, k7);
-          cswap_desc(k2, k4); cswap_desc(k3, k5);
-          cswap_desc(k1, k4); cswap_desc(k3, k6);
-          cswap_desc(k1, k2); cswap_desc(k3, k4); cswap_desc(k5, k6);
-          // heights that agree in everything but the 4 bits given to the code: order unknown
-          const bool ambiguous =
-              (k1 && (k0 ^ k1) < 16u) || (k2 && (k1 ^ k2) < 16u) || (k3 && (k2 ^ k3) < 16u) ||
-              (k4 && (k3 ^ k4) < 16u) || (k5 && (k4 ^ k5) < 16u) || (k6 && (k5 ^ k6) < 16u) ||
-              (k7 && (k6 ^ k7) < 16u);
-          if (ambiguous) { any_change |= tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling); continue; }
-          float cc = cen;
-          bool moved = false;
-          const unsigned ks[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
-#pragma unroll
-          for (int j = 0; j < 8; j++) {                                    // world.hpp:122-151
-            const unsigned k = ks[j];
-            if (k == 0u) break;                                            // only out-of-map left
-            const unsigned code = 15u - (k & 15u);
-            float* hp = tc + ((int)(code >> 2) - 1) * TILE_PITCH + ((int)(code & 3u) - 1);
-            const float hv = *hp;
-            const float t = (code & 5u) ? thr.ortho : thr.diag;
-            const float diff = fsub(cc, hv);
-            if (diff == 0.0f) continue;
-            const float excess = fsub(fabsf(diff), t);
-            if (excess <= 0.0f) continue;
-            const float transfer = fmul(fmul(settling, excess), 0.5f);     // (settling*excess)/2
-            if (diff > 0.0f) { cc = fsub(cc, transfer); *hp = fadd(hv, transfer); }
-            else             { cc = fadd(cc, transfer); *hp = fsub(hv, transfer); }
-            moved = true;
-          }
-          if (moved) { tc[0] = cc; any_change = true; }
+      const bool z_ok = (int)threadIdx.x < ncz && (interior || (gz >= 0 && gz < nz));
+#pragma unroll 1
+      for (int cx_base = 0; cx_base < ncx; cx_base += TILE_BY) {      // same trip count for all threads
+        const int cxi = cx_base + (int)threadIdx.y;
+        const int lx = cxc + 1 + 3 * cxi, gx = gx0 + lx;
+        bool need = z_ok && cxi < ncx && (interior || (gx >= 0 && gx < nx));
+        const int off = lx * TILE_PITCH + lz;
+        if (USE_STAMP) need = need && stile[need ? off : 0] == stamp_now;
+        if (need && !generic_only) {
+          const float* tc = tile + off;
+          need = interior ? centre_needs<true>(tc, thr, centre_valid<true>(gx, gz, nx, nz))
+                          : centre_needs<false>(tc, thr, centre_valid<false>(gx, gz, nx, nz));
         }
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+          unsigned base = 0;
+          if (lane == (unsigned)(__ffs(mask) - 1)) base = atomicAdd(qc, (unsigned)__popc(mask));
+          base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+          if (need) queue[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)off;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- relax -------------------------------------------------------------------------------
+    const unsigned nq = *qc;
+    if (tid == 0) qcount[(c + 1) & 1] = 0u;          // the other counter is idle during this phase
+    any_change |= nq != 0u;                          // a queued centre always moves sand
+    for (unsigned i = tid; i < nq; i += TILE_THREADS) {
+      const int off = queue[i];
+      float* tc = tile + off;
+      if (interior && !generic_only) {
+        // interior: every neighbour exists; (1,1) in a 3x3 map tells the generic fallback so
+        centre_relax<true>(tc, thr, settling, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
+      } else {
+        const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
+        const int gx = gx0 + lx, gz = gz0 + lz;
+        if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
+        else centre_relax<false>(tc, thr, settling, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
       }
     }
     __syncthreads();
   }
 
   // ---- store O if anything in this tile moved -----------------------------------------------
-  if (__syncthreads_or(any_change ? 1 : 0)) {
+  if (any_change) {                                  // CTA-uniform (derived from shared counters)
     if (vec_ok) {
       for (int i = tid; i < TILE_TX * (TILE_TZ / 4); i += TILE_THREADS) {
         const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);

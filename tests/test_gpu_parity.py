@@ -201,6 +201,11 @@ def test_cascade_sweep_vs_oracle(nx, nz, sweeps, variant):
         hm[30:40, 50:120] = (base.view(np.uint32) + rs.randint(0, 12, size=blk.shape).astype(np.uint32)).view(np.float32)
         hm[50:58, 10:60] = np.where(rs.random_sample((8, 50)) < 0.5, np.float32(-0.0), np.float32(0.0))
         hm[52, 20] = -0.3; hm[55, 40] = 0.2
+    if nx >= 257 and nz >= 1000:   # the same stress inside an INTERIOR tile (no map edge in its halo)
+        blk = hm[150:170, 300:420]
+        base = np.float32(0.3) + np.float32(0.05) * rs.randint(0, 3, size=blk.shape).astype(np.float32)
+        hm[150:170, 300:420] = (base.view(np.uint32) + rs.randint(0, 12, size=blk.shape).astype(np.uint32)).view(np.float32)
+        hm[180:200, 500:700] = np.round(hm[180:200, 500:700] * 16) / 16
     ora = PortWorld(nx, nz)
     ora.set_plane(0, hm)
     w = swe.World(nx, nz)
