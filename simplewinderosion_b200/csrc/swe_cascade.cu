@@ -69,6 +69,13 @@ constexpr int TILE_QUEUE_BYTES = ((TILE_LX / 3) * (TILE_PITCH / 3) * 2 + 15) / 1
 constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 16;   // + queue counters, mbarrier
 constexpr int TILE_SMEM_STAMPED = TILE_SMEM_PLAIN + TILE_STAMP_BYTES;
 
+#ifdef SWE_TILE_STATS
+__device__ unsigned long long g_tile_stats[4];   // [0] queued centres, [1] generic fallbacks, [2] scanned centres
+#define TILE_STAT(i, n) atomicAdd(&g_tile_stats[i], (unsigned long long)(n))
+#else
+#define TILE_STAT(i, n) ((void)0)
+#endif
+
 __device__ __forceinline__ void cswap_desc(unsigned& a, unsigned& b) {
   const unsigned hi = max(a, b), lo = min(a, b);
   a = hi; b = lo;
@@ -114,27 +121,38 @@ __device__ __forceinline__ Valid8 centre_valid(int gx, int gz, int nx, int nz) {
   return v;
 }
 
-// exact early-out test (thresholds >= 0): does any in-map neighbour exceed its repose gap?
-// If none does, the reference's loop (world.hpp:122-151) transfers nothing.
-template <bool INTERIOR>
-__device__ __forceinline__ bool centre_needs(const float* tc, const CascadeThr thr, const Valid8 v) {
+// Exact early-out tests (thresholds >= 0). World::cascade leaves the 3x3 block untouched iff no
+// transfer of its loop (world.hpp:122-151) changes a value; as long as nothing has changed the
+// centre keeps its initial height, so the test can be made against the initial centre:
+//   coarse : some in-map neighbour has excess = |c-h| - t > 0        (cheap, a superset)
+//   refined: ... and its transfer (settling*excess)/2 actually changes c or h in fp32.
+// On a map relaxed to the repose angle most pairs sit within an ulp of the gap: ~87 % of the
+// centres pass the coarse test but only a few per cent the refined one (measured, 4096^2).
+template <bool REFINED>
+__device__ __forceinline__ bool pair_moves(float cen, float h, float t, float half_settling) {
+  const float diff = fsub(cen, h);
+  const float excess = fsub(fabsf(diff), t);
+  if (!REFINED) return !(excess <= 0.0f);
+  const float transfer = fmul(excess, half_settling);           // == (settling*excess)/2.0f
+  const float sgn = (diff > 0.0f) ? transfer : -transfer;
+  return !(excess <= 0.0f) && ((fsub(cen, sgn) != cen) || (fadd(h, sgn) != h));
+}
+
+template <bool INTERIOR, bool REFINED>
+__device__ __forceinline__ bool centre_needs(const float* tc, const CascadeThr thr, float settling,
+                                             const Valid8 v) {   // settling: already halved
   const float cen = tc[0];
-  const float e0 = fsub(fabsf(fsub(cen, tc[-TILE_PITCH - 1])), thr.diag);
-  const float e1 = fsub(fabsf(fsub(cen, tc[-TILE_PITCH])), thr.ortho);
-  const float e2 = fsub(fabsf(fsub(cen, tc[-TILE_PITCH + 1])), thr.diag);
-  const float e3 = fsub(fabsf(fsub(cen, tc[-1])), thr.ortho);
-  const float e4 = fsub(fabsf(fsub(cen, tc[1])), thr.ortho);
-  const float e5 = fsub(fabsf(fsub(cen, tc[TILE_PITCH - 1])), thr.diag);
-  const float e6 = fsub(fabsf(fsub(cen, tc[TILE_PITCH])), thr.ortho);
-  const float e7 = fsub(fabsf(fsub(cen, tc[TILE_PITCH + 1])), thr.diag);
-  if (INTERIOR) {
-    // !(e <= 0) for any e  <=>  !(all e <= 0); NaN excesses count as "needs" like the reference
-    return !((e0 <= 0.0f) & (e1 <= 0.0f) & (e2 <= 0.0f) & (e3 <= 0.0f) & (e4 <= 0.0f) & (e5 <= 0.0f) &
-             (e6 <= 0.0f) & (e7 <= 0.0f));
-  }
-  return (v.v0 && !(e0 <= 0.0f)) || (v.v1 && !(e1 <= 0.0f)) || (v.v2 && !(e2 <= 0.0f)) ||
-         (v.v3 && !(e3 <= 0.0f)) || (v.v4 && !(e4 <= 0.0f)) || (v.v5 && !(e5 <= 0.0f)) ||
-         (v.v6 && !(e6 <= 0.0f)) || (v.v7 && !(e7 <= 0.0f));
+  const bool m0 = pair_moves<REFINED>(cen, tc[-TILE_PITCH - 1], thr.diag, settling);
+  const bool m1 = pair_moves<REFINED>(cen, tc[-TILE_PITCH], thr.ortho, settling);
+  const bool m2 = pair_moves<REFINED>(cen, tc[-TILE_PITCH + 1], thr.diag, settling);
+  const bool m3 = pair_moves<REFINED>(cen, tc[-1], thr.ortho, settling);
+  const bool m4 = pair_moves<REFINED>(cen, tc[1], thr.ortho, settling);
+  const bool m5 = pair_moves<REFINED>(cen, tc[TILE_PITCH - 1], thr.diag, settling);
+  const bool m6 = pair_moves<REFINED>(cen, tc[TILE_PITCH], thr.ortho, settling);
+  const bool m7 = pair_moves<REFINED>(cen, tc[TILE_PITCH + 1], thr.diag, settling);
+  if (INTERIOR) return m0 | m1 | m2 | m3 | m4 | m5 | m6 | m7;
+  return (v.v0 & m0) | (v.v1 & m1) | (v.v2 & m2) | (v.v3 & m3) | (v.v4 & m4) | (v.v5 & m5) | (v.v6 & m6) |
+         (v.v7 & m7);
 }
 
 // order-preserving key of a neighbour height: descending float order == descending unsigned
@@ -158,15 +176,17 @@ __device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, con
   const float diff = fsub(cc, hv);
   const float excess = fsub(fabsf(diff), t);
   const bool go = (k != 0u) && !(excess <= 0.0f);
-  const float transfer = fmul(fmul(settling, excess), 0.5f);     // (settling*excess)/2.0f
+  // (settling*excess)/2.0f == excess*(settling/2): halving is exact and commutes with the
+  // rounding of the product (sub-normal products excluded: tiny thresholds use the generic core)
+  const float transfer = fmul(excess, settling);                 // settling: already halved
   const float sgn = (diff > 0.0f) ? transfer : -transfer;        // diff > 0: centre gives, else takes
   if (go) { cc = fsub(cc, sgn); *hp = fadd(hv, sgn); }
 }
 
 // World::cascade at one centre of the tile whose early-out test failed.
 template <bool INTERIOR>
-__device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, float settling, const Valid8 v,
-                                             int gx, int gz, int nx, int nz) {
+__device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, float settling, float hs,
+                                             const Valid8 v, int gx, int gz, int nx, int nz) {
   unsigned k0 = height_key(tc[-TILE_PITCH - 1], v.v0, 0), k1 = height_key(tc[-TILE_PITCH], v.v1, 1),
            k2 = height_key(tc[-TILE_PITCH + 1], v.v2, 2), k3 = height_key(tc[-1], v.v3, 4),
            k4 = height_key(tc[1], v.v4, 6), k5 = height_key(tc[TILE_PITCH - 1], v.v5, 8),
@@ -183,14 +203,15 @@ __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, fl
   unsigned close = min(min(k0 ^ k1, (k2 ? k1 ^ k2 : ~0u)), min((k3 ? k2 ^ k3 : ~0u), (k4 ? k3 ^ k4 : ~0u)));
   close = min(close, min(min((k5 ? k4 ^ k5 : ~0u), (k6 ? k5 ^ k6 : ~0u)), (k7 ? k6 ^ k7 : ~0u)));
   if ((INTERIOR || k1) && close < 16u) {
+    TILE_STAT(1, 1);
     tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
     return;
   }
   float cc = tc[0];
-  chain_step(tc, k0, cc, thr, settling); chain_step(tc, k1, cc, thr, settling);
-  chain_step(tc, k2, cc, thr, settling); chain_step(tc, k3, cc, thr, settling);
-  chain_step(tc, k4, cc, thr, settling); chain_step(tc, k5, cc, thr, settling);
-  chain_step(tc, k6, cc, thr, settling); chain_step(tc, k7, cc, thr, settling);
+  chain_step(tc, k0, cc, thr, hs); chain_step(tc, k1, cc, thr, hs);
+  chain_step(tc, k2, cc, thr, hs); chain_step(tc, k3, cc, thr, hs);
+  chain_step(tc, k4, cc, thr, hs); chain_step(tc, k5, cc, thr, hs);
+  chain_step(tc, k6, cc, thr, hs); chain_step(tc, k7, cc, thr, hs);
   tc[0] = cc;
 }
 
@@ -218,7 +239,10 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   const int gx0 = ox0 - 2, gz0 = oz0 - 8;          // global coords of tile[0][0]
   const int tid = threadIdx.y * TILE_BX + threadIdx.x;
   const int nx = m.nx, nz = m.nz;
-  const bool generic_only = !(thr.ortho >= 0.0f) || !(thr.diag >= 0.0f);
+  const float hs = fmul(settling, 0.5f);
+  // negative or vanishing thresholds / sub-normal products: the lean paths' shortcuts do not hold
+  const bool generic_only = !(thr.ortho >= 0.0f) || !(thr.diag >= 0.0f) || !(fabsf(settling) >= 1e-18f) ||
+                            !(fabsf(settling) <= 1e18f) || (thr.ortho != 0.0f && thr.ortho < 1e-18f);
   const bool vec_ok = (nz & 3) == 0;               // rows are 16-byte aligned, tiles 4-aligned in z
   const bool interior = gx0 >= 0 && gz0 >= 0 && gx0 + TILE_LX <= nx && gz0 + TILE_PITCH <= nz;
 
@@ -277,6 +301,13 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   }
 
   bool any_change = false;
+  // which early-out test the scan uses: the refined test costs ~64 more instructions per
+  // scanned centre and saves ~250 per centre it keeps out of the queue, so it pays unless more
+  // than ~3/4 of the centres pass it. Colour 0 always probes with it; a tile whose refined
+  // queue fills beyond 3/4 falls back to the coarse test for its remaining colours. Stamped
+  // sweeps (flight pipeline) scan only the touched cells, few of which sit at the repose gap:
+  // measured, the coarse test is the faster filter there.
+  bool refined = !USE_STAMP;
   const unsigned lane = tid & 31;
 #pragma unroll 1
   for (int c = 0; c < 9; c++) {
@@ -296,8 +327,12 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
         if (USE_STAMP) need = need && stile[need ? off : 0] == stamp_now;
         if (need && !generic_only) {
           const float* tc = tile + off;
-          need = interior ? centre_needs<true>(tc, thr, centre_valid<true>(gx, gz, nx, nz))
-                          : centre_needs<false>(tc, thr, centre_valid<false>(gx, gz, nx, nz));
+          if (interior)
+            need = refined ? centre_needs<true, true>(tc, thr, hs, centre_valid<true>(gx, gz, nx, nz))
+                           : centre_needs<true, false>(tc, thr, hs, centre_valid<true>(gx, gz, nx, nz));
+          else
+            need = refined ? centre_needs<false, true>(tc, thr, hs, centre_valid<false>(gx, gz, nx, nz))
+                           : centre_needs<false, false>(tc, thr, hs, centre_valid<false>(gx, gz, nx, nz));
         }
         const unsigned mask = __ballot_sync(0xffffffffu, need);
         if (mask) {
@@ -313,17 +348,19 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     const unsigned nq = *qc;
     if (tid == 0) qcount[(c + 1) & 1] = 0u;          // the other counter is idle during this phase
     any_change |= nq != 0u;                          // a queued centre always moves sand
+    if (!USE_STAMP) refined = refined && (nq * 4u < (unsigned)(ncx * ncz) * 3u);
+    if (tid == 0) { TILE_STAT(0, nq); TILE_STAT(2, ncx * ncz); }
     for (unsigned i = tid; i < nq; i += TILE_THREADS) {
       const int off = queue[i];
       float* tc = tile + off;
       if (interior && !generic_only) {
         // interior: every neighbour exists; (1,1) in a 3x3 map tells the generic fallback so
-        centre_relax<true>(tc, thr, settling, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
+        centre_relax<true>(tc, thr, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
       } else {
         const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
         const int gx = gx0 + lx, gz = gz0 + lz;
         if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
-        else centre_relax<false>(tc, thr, settling, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
+        else centre_relax<false>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
       }
     }
     __syncthreads();
@@ -476,6 +513,14 @@ int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTens
   add_cascade_cells_kernel<<<1, 1, 0, st>>>(stats, (unsigned long long)sweeps * m.nx * m.nz);
   return launches + 1;
 }
+
+#ifdef SWE_TILE_STATS
+extern "C" void swe_debug_tile_stats(unsigned long long* out4, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(unsigned long long) * 4);
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_tile_stats, z, sizeof z); }
+}
+#endif
 
 void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st) {
   set_float_kernel<<<1, 1, 0, st>>>(d_out, -INFINITY);

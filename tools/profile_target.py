@@ -20,3 +20,6 @@ elif what == "cascade8192":
 elif what == "cascade8192relaxed":
     w = swe.World(8192); w.upload(generate.flat_sand(8192))
     w.cascade_sweep(3); w.sync(); print(w.stats().last_sweep_ms)
+elif what == "cascade4096conv":
+    w = swe.World(4096); w.upload(generate.random_slopes(4096))
+    w.cascade_sweep(164); w.sync(); print(w.stats().last_sweep_ms / 164)
