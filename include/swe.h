@@ -119,6 +119,7 @@ typedef struct swe_stats {
   double last_fly_ms;      /* device time of the particle phase (rounds + cascades) of the last swe_erode */
   double last_round_ms;    /* with SWE_OPT_KERNEL_TIMING: sum over the particle-round kernels */
   double last_cascade_ms;  /* with SWE_OPT_KERNEL_TIMING: sum over the per-round cascade kernels */
+  uint64_t stripe_overflow;/* stripe engines: particles dropped for lack of buffer space (must be 0) */
 } swe_stats;
 
 typedef struct swe_engine swe_engine;
@@ -204,6 +205,38 @@ int swe_sum_plane(swe_engine* e, int plane, double* out);   /* fp64 sum over the
 int swe_max_excess(swe_engine* e, float* out);
 int swe_hash_height(swe_engine* e, uint64_t* out);          /* FNV-1a-64 of fp32 words */
 int swe_sync(swe_engine* e);
+
+/* ---- multi-GPU row stripes --------------------------------------------------------------
+ * The map is cut into row stripes (x is the slow index, math.h:11-12), one engine per GPU /
+ * process. A stripe engine owns the global rows [own_lo, own_hi) (>= 8 rows) and keeps ghost
+ * rows of its neighbours; inside swe_erode / swe_cascade_sweep the neighbours exchange boundary
+ * rows and hand over particles by kernels writing peer memory (NVLink P2P), synchronised by
+ * flags -- no host round trip per exchange. Every rank must issue the same sequence of
+ * swe_erode / swe_cascade_sweep / swe_stripe_sync_halos calls with the same arguments;
+ * `cycles` of swe_erode is the GLOBAL particle count of the call. Host transfers
+ * (swe_upload_plane, swe_download_plane, swe_sum_plane, ...) act on the owned rows only. Parallel mode only.
+ *   1. swe_stripe_create on every rank (max_particles >= the largest global `cycles`; the same
+ *      value on every rank)
+ *   2. exchange links: same process -> swe_stripe_export; other processes -> swe_stripe_export_ipc,
+ *      ship the SWE_STRIPE_IPC_BYTES blob (e.g. torch.distributed all_gather), swe_stripe_open_ipc
+ *   3. swe_stripe_connect(below, above)  (NULL at the map edges)
+ *   4. swe_upload_plane(owned rows) on every rank, then swe_stripe_sync_halos */
+#define SWE_STRIPE_IPC_BYTES 256
+typedef struct swe_stripe_link {   /* a neighbour's buffers as device pointers valid on THIS GPU */
+  void* height;
+  void* stamp;
+  void* arena;
+  int32_t x0;              /* global row of the neighbour's first stored row */
+  int32_t inbox_capacity;
+} swe_stripe_link;
+int swe_stripe_create(swe_engine** out, int nx, int nz, int own_lo, int own_hi, int max_particles,
+                      const swe_params* params, int device);
+int swe_stripe_export(swe_engine* e, swe_stripe_link* out);
+int swe_stripe_export_ipc(swe_engine* e, void* buf, size_t buf_bytes);
+int swe_stripe_open_ipc(swe_engine* e, const void* buf, size_t buf_bytes, swe_stripe_link* out);
+int swe_stripe_connect(swe_engine* e, const swe_stripe_link* below, const swe_stripe_link* above);
+int swe_stripe_sync_halos(swe_engine* e);
+int swe_stripe_rows(const swe_engine* e, int* own_lo, int* own_hi);
 
 /* ---- device-side plumbing (for a host that already lives on the GPU) ---------------- */
 /* Stream the engine launches on (a cudaStream_t); 0 = the engine's own stream. */

@@ -63,8 +63,17 @@ class Stats(C.Structure):
         ("last_fly_ms", C.c_double),
         ("last_round_ms", C.c_double),
         ("last_cascade_ms", C.c_double),
+        ("stripe_overflow", C.c_uint64),
     ]
 
+
+class StripeLink(C.Structure):
+    """struct swe_stripe_link (include/swe.h)"""
+    _fields_ = [("height", C.c_void_p), ("stamp", C.c_void_p), ("arena", C.c_void_p),
+                ("x0", C.c_int32), ("inbox_capacity", C.c_int32)]
+
+
+STRIPE_IPC_BYTES = 256
 
 # name -> (restype, argtypes); must list every symbol include/swe.h declares
 _E = C.c_void_p
@@ -79,6 +88,14 @@ PROTOTYPES = {
     "swe_get_params": (C.c_int, [_E, C.POINTER(Params)]),
     "swe_get_size": (C.c_int, [_E, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "swe_set_option": (C.c_int, [_E, C.c_int, C.c_int]),
+    "swe_stripe_create": (C.c_int, [C.POINTER(_E), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(Params), C.c_int]),
+    "swe_stripe_export": (C.c_int, [_E, C.POINTER(StripeLink)]),
+    "swe_stripe_export_ipc": (C.c_int, [_E, C.c_void_p, C.c_size_t]),
+    "swe_stripe_open_ipc": (C.c_int, [_E, C.c_void_p, C.c_size_t, C.POINTER(StripeLink)]),
+    "swe_stripe_connect": (C.c_int, [_E, C.POINTER(StripeLink), C.POINTER(StripeLink)]),
+    "swe_stripe_sync_halos": (C.c_int, [_E]),
+    "swe_stripe_rows": (C.c_int, [_E, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "swe_srand": (C.c_int, [_E, C.c_uint32]),
     "swe_upload_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_download_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),

@@ -80,8 +80,56 @@ struct swe_engine {
   uint64_t launches = 0, erode_calls = 0;
   double last_erode_ms = 0.0, last_sweep_ms = 0.0, last_fly_ms = 0.0;
 
-  size_t cells() const { return (size_t)m.rows * (size_t)m.nz; }
+  // multi-GPU row stripe; disabled on a single-GPU engine
+  struct Stripe {
+    bool enabled = false, connected = false;
+    int own_lo = 0, own_hi = 0;
+    int inbox_capacity = 0, max_particles = 0;
+    unsigned char* arena = nullptr;      // flags + inboxes: ONE allocation = one IPC handle
+    size_t arena_bytes = 0;
+    uint32_t* d_pid = nullptr;
+    unsigned* d_vars = nullptr;          // [0] n_used [1] overflow [2] error [3] merge base
+    bool has_below = false, has_above = false;
+    swe_stripe_link below{}, above{};
+    unsigned seq = 0;
+    std::vector<void*> ipc_opened;       // peer mappings to close at destroy
+  } st;
+
+  size_t cells() const { return (size_t)m.rows * (size_t)m.nz; }           // stored (owned + ghosts)
+  int own_lo() const { return st.enabled ? st.own_lo : 0; }
+  int own_hi() const { return st.enabled ? st.own_hi : m.nx; }
+  size_t host_cells() const { return (size_t)(own_hi() - own_lo()) * (size_t)m.nz; }   // what the host sees
+  // view of the rows the host owns: transfers, sums and hashes never touch ghost rows
+  MapView owned(int extra_above = 0) const {
+    MapView v = m;
+    const size_t off = (size_t)(own_lo() - m.x0) * (size_t)m.nz;
+    v.height = m.height + off; v.field = m.field + off; v.track = m.track + off;
+    v.x0 = own_lo(); v.rows = own_hi() - own_lo() + extra_above;
+    return v;
+  }
 };
+
+// ---- stripe arena layout (identical on every rank, so a peer base pointer is enough) ----------
+namespace {
+constexpr size_t ARENA_FLAGS = 256;   // 4 flags, 64 B apart
+enum { FLAG_READY_FROM_BELOW = 0, FLAG_READY_FROM_ABOVE = 1, FLAG_CONSUMED_BY_BELOW = 2, FLAG_CONSUMED_BY_ABOVE = 3 };
+enum { FROM_BELOW = 0, FROM_ABOVE = 1 };
+inline size_t inbox_bytes(int cap) { return 256 + (size_t)cap * (16 + 16 + 4); }
+inline size_t arena_size(int cap) { return ARENA_FLAGS + 4 * inbox_bytes(cap); }
+inline unsigned* arena_flag(void* base, int which) {
+  return reinterpret_cast<unsigned*>(static_cast<unsigned char*>(base) + 64 * which);
+}
+inline StripeOutbox arena_inbox(void* base, int cap, int dir, int parity) {
+  unsigned char* p = static_cast<unsigned char*>(base) + ARENA_FLAGS + (size_t)(dir * 2 + parity) * inbox_bytes(cap);
+  StripeOutbox b;
+  b.count = reinterpret_cast<unsigned*>(p);
+  b.a = reinterpret_cast<float4*>(p + 256);
+  b.b = b.a + cap;
+  b.pid = reinterpret_cast<uint32_t*>(b.b + cap);
+  b.capacity = cap;
+  return b;
+}
+}  // namespace
 
 namespace {
 
@@ -137,6 +185,45 @@ int check_launch(swe_engine* e, const char* what, int n = 1) {
   return SWE_OK;
 }
 
+// One neighbour exchange of a stripe engine (all on the engine's stream, no host sync):
+// wait until the neighbours consumed the previous ghosts, push my boundary rows, signal, wait.
+// Returns the sequence number; the caller signals "consumed" with it after using the ghosts.
+unsigned stripe_exchange_begin(swe_engine* e, bool with_stamps, int* launches) {
+  auto& S = e->st;
+  const unsigned s = ++S.seq;
+  unsigned* err = S.d_vars + 2;
+  const int nz = e->m.nz;
+  launch_stripe_wait(S.has_below ? arena_flag(S.arena, FLAG_CONSUMED_BY_BELOW) : nullptr,
+                     S.has_above ? arena_flag(S.arena, FLAG_CONSUMED_BY_ABOVE) : nullptr, s - 1, err, e->stream);
+  if (S.has_below) {   // my first 5 owned rows are the below neighbour's ghost rows above its stripe
+    const size_t src = (size_t)(S.own_lo - e->m.x0) * nz, dst = (size_t)(S.own_lo - S.below.x0) * nz;
+    launch_stripe_push(e->m.height + src, static_cast<float*>(S.below.height) + dst,
+                       with_stamps ? e->d_stamp + src : nullptr,
+                       with_stamps ? static_cast<unsigned char*>(S.below.stamp) + dst : nullptr,
+                       (size_t)5 * nz, e->stream);
+  }
+  if (S.has_above) {   // my last 3 owned rows are the above neighbour's ghost rows below its stripe
+    const size_t src = (size_t)(S.own_hi - 3 - e->m.x0) * nz, dst = (size_t)(S.own_hi - 3 - S.above.x0) * nz;
+    launch_stripe_push(e->m.height + src, static_cast<float*>(S.above.height) + dst,
+                       with_stamps ? e->d_stamp + src : nullptr,
+                       with_stamps ? static_cast<unsigned char*>(S.above.stamp) + dst : nullptr,
+                       (size_t)3 * nz, e->stream);
+  }
+  launch_stripe_signal(S.has_below ? arena_flag(S.below.arena, FLAG_READY_FROM_ABOVE) : nullptr,
+                       S.has_above ? arena_flag(S.above.arena, FLAG_READY_FROM_BELOW) : nullptr, s, e->stream);
+  launch_stripe_wait(S.has_below ? arena_flag(S.arena, FLAG_READY_FROM_BELOW) : nullptr,
+                     S.has_above ? arena_flag(S.arena, FLAG_READY_FROM_ABOVE) : nullptr, s, err, e->stream);
+  *launches += 3 + (S.has_below ? 1 : 0) + (S.has_above ? 1 : 0);
+  return s;
+}
+
+void stripe_exchange_end(swe_engine* e, unsigned s, int* launches) {
+  auto& S = e->st;
+  launch_stripe_signal(S.has_below ? arena_flag(S.below.arena, FLAG_CONSUMED_BY_ABOVE) : nullptr,
+                       S.has_above ? arena_flag(S.above.arena, FLAG_CONSUMED_BY_BELOW) : nullptr, s, e->stream);
+  *launches += 1;
+}
+
 void finish_timers(swe_engine* e) {
   float ms = 0.0f;
   if (e->erode_timed && cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->last_erode_ms = ms;
@@ -176,12 +263,18 @@ int swe_params_default(swe_params* p) {
   return SWE_OK;
 }
 
-int swe_create(swe_engine** out, int nx, int nz, const swe_params* params, int device) {
+static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_hi, bool stripe,
+                         int max_particles, const swe_params* params, int device) {
   if (!out) return fail(SWE_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (nx < 1 || nz < 1) return fail(SWE_ERR_INVALID, "map size must be >= 1x1 (got %dx%d)", nx, nz);
   if ((long long)nx * nz > (1LL << 31) - 1)
     return fail(SWE_ERR_INVALID, "map of %dx%d cells exceeds 2^31-1 cells", nx, nz);
+  if (stripe) {
+    if (own_lo < 0 || own_hi > nx || own_hi - own_lo < 8)
+      return fail(SWE_ERR_INVALID, "stripe rows [%d,%d) must lie in [0,%d) and span >= 8 rows", own_lo, own_hi, nx);
+    if (max_particles < 1) return fail(SWE_ERR_INVALID, "max_particles must be >= 1");
+  }
   swe_params p;
   if (params) p = *params; else swe_params_default(&p);
   const char* why = nullptr;
@@ -198,6 +291,15 @@ int swe_create(swe_engine** out, int nx, int nz, const swe_params* params, int d
   if (!e) return fail(SWE_ERR_OOM, "host allocation failed");
   e->device = device; e->p = p;
   e->m.nx = nx; e->m.nz = nz; e->m.x0 = 0; e->m.rows = nx;
+  if (stripe) {   // stored rows = owned + 3 ghost rows below + 5 above (clipped to the map)
+    e->st.enabled = true; e->st.own_lo = own_lo; e->st.own_hi = own_hi;
+    e->m.x0 = own_lo - 3 < 0 ? 0 : own_lo - 3;
+    const int hi = own_hi + 5 > nx ? nx : own_hi + 5;
+    e->m.rows = hi - e->m.x0;
+    e->st.max_particles = max_particles;
+    e->st.inbox_capacity = max_particles / 8 + 4096;
+    e->st.arena_bytes = arena_size(e->st.inbox_capacity);
+  }
   const size_t n = e->cells();
   cudaError_t err;
 #define TRY(call) if ((err = (call)) != cudaSuccess) goto cuda_fail
@@ -216,6 +318,18 @@ int swe_create(swe_engine** out, int nx, int nz, const swe_params* params, int d
   TRY(cudaMemsetAsync(e->m.field, 0, n * sizeof(float4), e->stream));
   TRY(cudaMemsetAsync(e->m.track, 0, n * sizeof(float4), e->stream));
   TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(DevStats), e->stream));
+  if (stripe) {
+    TRY(cudaMalloc(&e->d_stamp, n));
+    TRY(cudaMemsetAsync(e->d_stamp, 0, n, e->stream));
+    TRY(cudaMalloc(&e->st.arena, e->st.arena_bytes));
+    TRY(cudaMemsetAsync(e->st.arena, 0, e->st.arena_bytes, e->stream));
+    TRY(cudaMalloc(&e->st.d_pid, (size_t)max_particles * sizeof(uint32_t)));
+    TRY(cudaMalloc(&e->st.d_vars, 64));
+    TRY(cudaMemsetAsync(e->st.d_vars, 0, 64, e->stream));
+    TRY(cudaMalloc(&e->pbuf.a, (size_t)max_particles * sizeof(float4)));
+    TRY(cudaMalloc(&e->pbuf.b, (size_t)max_particles * sizeof(float4)));
+    e->pbuf.capacity = max_particles; e->pbuf.live = nullptr; e->pbuf.live_slots = 0;
+  }
   make_height_tensor_map(e->m, &e->tmap);   // optional: plain-load kernels are used when it fails
   launch_det_srand(e->d_rng, 1u, e->stream);
   TRY(cudaGetLastError());
@@ -235,6 +349,15 @@ cuda_fail:
   }
 }
 
+int swe_create(swe_engine** out, int nx, int nz, const swe_params* params, int device) {
+  return create_engine(out, nx, nz, 0, nx, false, 0, params, device);
+}
+
+int swe_stripe_create(swe_engine** out, int nx, int nz, int own_lo, int own_hi, int max_particles,
+                      const swe_params* params, int device) {
+  return create_engine(out, nx, nz, own_lo, own_hi, true, max_particles, params, device);
+}
+
 void swe_destroy(swe_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
@@ -242,6 +365,8 @@ void swe_destroy(swe_engine* e) {
   cudaFree(e->m.height); cudaFree(e->m.field); cudaFree(e->m.track);
   cudaFree(e->d_stats); cudaFree(e->d_rng); cudaFree(e->d_small); cudaFree(e->d_scratch);
   cudaFree(e->pbuf.a); cudaFree(e->pbuf.b); cudaFree(e->pbuf.live); cudaFree(e->d_stamp);
+  cudaFree(e->st.arena); cudaFree(e->st.d_pid); cudaFree(e->st.d_vars);
+  for (void* p : e->st.ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
   if (e->ev_b) cudaEventDestroy(e->ev_b);
@@ -288,7 +413,8 @@ int swe_upload_plane(swe_engine* e, int plane, const float* src, ptrdiff_t strid
   if (!src) return fail(SWE_ERR_INVALID, "src is NULL");
   if (plane < 0 || plane >= SWE_NUM_PLANES) return fail(SWE_ERR_INVALID, "plane %d out of range", plane);
   if (stride_bytes < 4 || stride_bytes % 4) return fail(SWE_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 4");
-  const size_t n = e->cells(), bytes = n * sizeof(float);
+  const size_t n = e->host_cells(), bytes = n * sizeof(float);
+  const MapView ov = e->owned();
   const float* packed = src;
   if (stride_bytes != 4) {  // gather the member out of the caller's AoS records
     if (int rc = need_stage(e, bytes)) return rc;
@@ -299,11 +425,11 @@ int swe_upload_plane(swe_engine* e, int plane, const float* src, ptrdiff_t strid
     packed = s;
   }
   if (plane == SWE_HEIGHT) {
-    SWE_CUDA(cudaMemcpyAsync(e->m.height, packed, bytes, cudaMemcpyHostToDevice, e->stream));
+    SWE_CUDA(cudaMemcpyAsync(ov.height, packed, bytes, cudaMemcpyHostToDevice, e->stream));
   } else {
     if (int rc = need_scratch(e, bytes)) return rc;
     SWE_CUDA(cudaMemcpyAsync(e->d_scratch, packed, bytes, cudaMemcpyHostToDevice, e->stream));
-    launch_pack_plane(e->m, plane, e->d_scratch, e->stream);
+    launch_pack_plane(ov, plane, e->d_scratch, e->stream);
     if (int rc = check_launch(e, "pack_plane")) return rc;
   }
   SWE_CUDA(cudaStreamSynchronize(e->stream));  // the caller may reuse src immediately
@@ -315,11 +441,12 @@ int swe_download_plane(swe_engine* e, int plane, float* dst, ptrdiff_t stride_by
   if (!dst) return fail(SWE_ERR_INVALID, "dst is NULL");
   if (plane < 0 || plane >= SWE_NUM_PLANES) return fail(SWE_ERR_INVALID, "plane %d out of range", plane);
   if (stride_bytes < 4 || stride_bytes % 4) return fail(SWE_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 4");
-  const size_t n = e->cells(), bytes = n * sizeof(float);
-  const float* d_src = e->m.height;
+  const size_t n = e->host_cells(), bytes = n * sizeof(float);
+  const MapView ov = e->owned();
+  const float* d_src = ov.height;
   if (plane != SWE_HEIGHT) {
     if (int rc = need_scratch(e, bytes)) return rc;
-    launch_unpack_plane(e->m, plane, e->d_scratch, e->stream);
+    launch_unpack_plane(ov, plane, e->d_scratch, e->stream);
     if (int rc = check_launch(e, "unpack_plane")) return rc;
     d_src = e->d_scratch;
   }
@@ -341,10 +468,10 @@ int swe_download_plane(swe_engine* e, int plane, float* dst, ptrdiff_t stride_by
 int swe_upload_cells(swe_engine* e, const void* cells) {
   if (int rc = bind(e)) return rc;
   if (!cells) return fail(SWE_ERR_INVALID, "cells is NULL");
-  const size_t bytes = e->cells() * 9 * sizeof(float);
+  const size_t bytes = e->host_cells() * 9 * sizeof(float);
   if (int rc = need_scratch(e, bytes)) return rc;
   SWE_CUDA(cudaMemcpyAsync(e->d_scratch, cells, bytes, cudaMemcpyHostToDevice, e->stream));
-  launch_cells_to_planes(e->m, e->d_scratch, e->stream);
+  launch_cells_to_planes(e->owned(), e->d_scratch, e->stream);
   if (int rc = check_launch(e, "cells_to_planes")) return rc;
   SWE_CUDA(cudaStreamSynchronize(e->stream));
   return SWE_OK;
@@ -353,9 +480,9 @@ int swe_upload_cells(swe_engine* e, const void* cells) {
 int swe_download_cells(swe_engine* e, void* cells) {
   if (int rc = bind(e)) return rc;
   if (!cells) return fail(SWE_ERR_INVALID, "cells is NULL");
-  const size_t bytes = e->cells() * 9 * sizeof(float);
+  const size_t bytes = e->host_cells() * 9 * sizeof(float);
   if (int rc = need_scratch(e, bytes)) return rc;
-  launch_planes_to_cells(e->m, e->d_scratch, e->stream);
+  launch_planes_to_cells(e->owned(), e->d_scratch, e->stream);
   if (int rc = check_launch(e, "planes_to_cells")) return rc;
   SWE_CUDA(cudaMemcpyAsync(cells, e->d_scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
@@ -386,7 +513,50 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
   SWE_CUDA(cudaMemsetAsync(e->m.track, 0, e->cells() * sizeof(float4), e->stream));
   // world.hpp:47-66: the particles
   SWE_CUDA(cudaEventRecord(e->ev_f0, e->stream));
-  if (mode == SWE_MODE_DETERMINISTIC) {
+  if (e->st.enabled) {
+    if (mode != SWE_MODE_PARALLEL) return fail(SWE_ERR_STATE, "a stripe engine runs parallel mode only");
+    if (!e->st.connected) return fail(SWE_ERR_STATE, "swe_stripe_connect has not been called");
+    if (cycles > e->st.max_particles)
+      return fail(SWE_ERR_INVALID, "cycles %d exceeds the stripe's max_particles %d", cycles, e->st.max_particles);
+    auto& S = e->st;
+    const int k = 1;   // particles must be handed over before they step again
+    const int rounds = e->p.max_age + 2;
+    int nl = 0;
+    if (cycles > 0) {
+      StripeRound sr{};
+      sr.own_lo = S.own_lo; sr.own_hi = S.own_hi;
+      sr.pid = S.d_pid; sr.n_used = S.d_vars + 0; sr.overflow = S.d_vars + 1;
+      launch_par_begin_stripe(e->pbuf, sr, e->m, cycles, e->seed, e->call_index, e->d_stats, e->stream);
+      nl += 3;
+      for (int r = 0; r < rounds; r++) {
+        if (++e->stamp_counter > 255u) {
+          SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
+          e->stamp_counter = 1;
+        }
+        const unsigned char now = (unsigned char)e->stamp_counter;
+        const int parity = (int)((S.seq + 1) & 1u);
+        if (S.has_below) sr.below = arena_inbox(S.below.arena, S.inbox_capacity, FROM_ABOVE, parity);
+        if (S.has_above) sr.above = arena_inbox(S.above.arena, S.inbox_capacity, FROM_BELOW, parity);
+        launch_par_round_stripe(e->pbuf, sr, e->m, e->p, k, e->seed, e->call_index, e->d_stamp, now,
+                                e->d_stats, e->stream);
+        nl += 1;
+        const unsigned s = stripe_exchange_begin(e, true, &nl);
+        for (int dir = 0; dir < 2; dir++) {
+          if ((dir == FROM_BELOW && !S.has_below) || (dir == FROM_ABOVE && !S.has_above)) continue;
+          const StripeOutbox in = arena_inbox(S.arena, S.inbox_capacity, dir, parity);
+          launch_stripe_merge(in.a, in.b, in.pid, in.count, in.capacity, e->pbuf.a, e->pbuf.b, S.d_pid,
+                              S.d_vars + 0, e->pbuf.capacity, S.d_vars + 1, S.d_vars + 3, e->stream);
+          nl += 3;
+        }
+        // rows own_lo-1 .. own_hi: the ghost row each side is recomputed here instead of exchanged
+        launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, nullptr, S.own_lo - 1, S.own_hi + 1,
+                               e->stream);
+        nl += 1;
+        stripe_exchange_end(e, s, &nl);
+      }
+    }
+    if (int rc = check_launch(e, "stripe erode", nl)) return rc;
+  } else if (mode == SWE_MODE_DETERMINISTIC) {
     launch_det_erode(e->m, e->p, cycles, e->d_rng, e->d_stats, e->stream);
     if (int rc = check_launch(e, "det_erode")) return rc;
   } else if (cycles > 0) {
@@ -413,7 +583,7 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
                        e->d_stats, e->stream);
       if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
       // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
-      launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, e->stream);
+      launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->stream);
       if (kt) { SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 2], e->stream)); e->kt_rounds = r + 1; }
       if (int rc = check_launch(e, "par_round", 2)) return rc;
     }
@@ -431,6 +601,7 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
 
 int swe_cascade(swe_engine* e, int x, int z) {
   if (int rc = bind(e)) return rc;
+  if (e->st.enabled) return fail(SWE_ERR_STATE, "not available on a stripe engine (deterministic mode is single-GPU)");
   if (e->m.oob(x, z)) return fail(SWE_ERR_OOB, "cell (%d,%d) outside %dx%d", x, z, e->m.nx, e->m.nz);
   launch_det_cascade_one(e->m, e->p, x, z, e->stream);
   return check_launch(e, "cascade_one");
@@ -439,7 +610,8 @@ int swe_cascade(swe_engine* e, int x, int z) {
 int swe_max_excess(swe_engine* e, float* out) {
   if (int rc = bind(e)) return rc;
   if (!out) return fail(SWE_ERR_INVALID, "out is NULL");
-  launch_max_excess(e->m, e->p, e->d_small, e->stream);
+  // a stripe also checks the pairs between its last owned row and the ghost row above it
+  launch_max_excess(e->owned(e->st.enabled && e->st.own_hi < e->m.nx ? 1 : 0), e->p, e->d_small, e->stream);
   if (int rc = check_launch(e, "max_excess", 2)) return rc;
   SWE_CUDA(cudaMemcpyAsync(out, e->d_small, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
@@ -452,7 +624,20 @@ int swe_cascade_sweep(swe_engine* e, int sweeps, float* max_excess_out) {
   if (sweeps < 0) return fail(SWE_ERR_INVALID, "sweeps < 0");
   finish_timers(e);
   SWE_CUDA(cudaEventRecord(e->ev_c, e->stream));
-  const int n = launch_cascade_sweep(e->m, e->p, &e->tmap, sweeps, e->d_stats, e->stream, e->opt_cascade_variant);
+  int n = 0;
+  if (e->st.enabled) {
+    // one exchange of pre-sweep boundary rows per sweep; owned rows come out bitwise equal to the
+    // single-GPU sweep (2/4-row dependency cone inside the 3/5-row ghost zone)
+    if (!e->st.connected) return fail(SWE_ERR_STATE, "swe_stripe_connect has not been called");
+    for (int s = 0; s < sweeps; s++) {
+      const unsigned q = stripe_exchange_begin(e, false, &n);
+      launch_cascade_stamped(e->m, e->p, &e->tmap, nullptr, 0, nullptr, e->st.own_lo, e->st.own_hi, e->stream);
+      n += 1;
+      stripe_exchange_end(e, q, &n);
+    }
+  } else {
+    n = launch_cascade_sweep(e->m, e->p, &e->tmap, sweeps, e->d_stats, e->stream, e->opt_cascade_variant);
+  }
   if (int rc = check_launch(e, "cascade_sweep", n)) return rc;
   SWE_CUDA(cudaEventRecord(e->ev_d, e->stream));
   e->sweep_timed = true;
@@ -481,6 +666,7 @@ int swe_cascade_converge(swe_engine* e, float tol, int max_sweeps, int* sweeps_d
 int swe_trace(swe_engine* e, float x, float z, int max_records, float* records, int* steps_out,
               swe_wind* final_out) {
   if (int rc = bind(e)) return rc;
+  if (e->st.enabled) return fail(SWE_ERR_STATE, "not available on a stripe engine (deterministic mode is single-GPU)");
   if (max_records < 0) return fail(SWE_ERR_INVALID, "max_records < 0");
   if (!records) max_records = 0;
   const size_t rec_bytes = (size_t)max_records * 8 * sizeof(float);
@@ -517,6 +703,7 @@ int swe_wind_init(swe_wind* w, float x, float z) {
 
 int swe_wind_fly(swe_engine* e, swe_wind* w, int* alive_out) {
   if (int rc = bind(e)) return rc;
+  if (e->st.enabled) return fail(SWE_ERR_STATE, "not available on a stripe engine (deterministic mode is single-GPU)");
   if (!w) return fail(SWE_ERR_INVALID, "wind is NULL");
   if (int rc = need_scratch(e, 128)) return rc;
   swe_wind* d_w = reinterpret_cast<swe_wind*>(e->d_scratch);
@@ -535,7 +722,8 @@ int swe_wind_fly(swe_engine* e, swe_wind* w, int* alive_out) {
 int swe_normal(swe_engine* e, int x, int z, float out3[3]) {
   if (int rc = bind(e)) return rc;
   if (!out3) return fail(SWE_ERR_INVALID, "out is NULL");
-  if (e->m.oob(x, z)) return fail(SWE_ERR_OOB, "cell (%d,%d) outside %dx%d", x, z, e->m.nx, e->m.nz);
+  if (e->m.oob(x, z) || x < e->own_lo() || x >= e->own_hi())
+    return fail(SWE_ERR_OOB, "cell (%d,%d) outside rows [%d,%d) of %dx%d", x, z, e->own_lo(), e->own_hi(), e->m.nx, e->m.nz);
   launch_normal_one(e->m, e->p, x, z, e->d_small, e->stream);
   if (int rc = check_launch(e, "normal_one")) return rc;
   SWE_CUDA(cudaMemcpyAsync(out3, e->d_small, 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -546,7 +734,8 @@ int swe_normal(swe_engine* e, int x, int z, float out3[3]) {
 int swe_height(swe_engine* e, int x, int z, float* out) {
   if (int rc = bind(e)) return rc;
   if (!out) return fail(SWE_ERR_INVALID, "out is NULL");
-  if (e->m.oob(x, z)) return fail(SWE_ERR_OOB, "cell (%d,%d) outside %dx%d", x, z, e->m.nx, e->m.nz);
+  if (e->m.oob(x, z) || x < e->own_lo() || x >= e->own_hi())
+    return fail(SWE_ERR_OOB, "cell (%d,%d) outside rows [%d,%d) of %dx%d", x, z, e->own_lo(), e->own_hi(), e->m.nx, e->m.nz);
   SWE_CUDA(cudaMemcpyAsync(out, e->m.height + e->m.idx(x, z), sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
   return SWE_OK;
@@ -555,9 +744,12 @@ int swe_height(swe_engine* e, int x, int z, float* out) {
 int swe_download_normals(swe_engine* e, float* dst) {
   if (int rc = bind(e)) return rc;
   if (!dst) return fail(SWE_ERR_INVALID, "dst is NULL");
-  const size_t bytes = e->cells() * 3 * sizeof(float);
+  const size_t bytes = e->host_cells() * 3 * sizeof(float);
   if (int rc = need_scratch(e, bytes)) return rc;
-  launch_normals(e->m, e->p, e->d_scratch, e->stream);
+  {
+    MapView nv = e->m;            // normals of the owned rows; neighbours may be ghost rows
+    launch_normals_rows(nv, e->p, e->own_lo(), e->own_hi(), e->d_scratch, e->stream);
+  }
   if (int rc = check_launch(e, "normals")) return rc;
   SWE_CUDA(cudaMemcpyAsync(dst, e->d_scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
@@ -586,6 +778,12 @@ int swe_get_stats(swe_engine* e, swe_stats* out) {
   out->erode_calls = e->erode_calls;
   out->last_erode_ms = e->last_erode_ms; out->last_sweep_ms = e->last_sweep_ms;
   out->kernel_launches = e->launches;
+  if (e->st.enabled) {
+    unsigned vars[4] = {0, 0, 0, 0};
+    SWE_CUDA(cudaMemcpy(vars, e->st.d_vars, sizeof vars, cudaMemcpyDeviceToHost));
+    out->stripe_overflow = vars[1];
+    if (vars[2]) return fail(SWE_ERR_STATE, "stripe neighbour exchange timed out (a rank is missing or crashed)");
+  }
   out->last_fly_ms = e->last_fly_ms;
   out->last_round_ms = e->last_round_ms;
   out->last_cascade_ms = e->last_cascade_ms;
@@ -604,7 +802,7 @@ int swe_sum_plane(swe_engine* e, int plane, double* out) {
   if (!out) return fail(SWE_ERR_INVALID, "out is NULL");
   if (plane < 0 || plane >= SWE_NUM_PLANES) return fail(SWE_ERR_INVALID, "plane %d out of range", plane);
   double* d_out = reinterpret_cast<double*>(e->d_small + 16);
-  launch_sum_plane(e->m, plane, d_out, e->stream);
+  launch_sum_plane(e->owned(), plane, d_out, e->stream);
   if (int rc = check_launch(e, "sum_plane")) return rc;
   SWE_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
@@ -614,12 +812,90 @@ int swe_sum_plane(swe_engine* e, int plane, double* out) {
 int swe_hash_height(swe_engine* e, uint64_t* out) {
   if (int rc = bind(e)) return rc;
   if (!out) return fail(SWE_ERR_INVALID, "out is NULL");
-  std::vector<uint32_t> host(e->cells());
-  SWE_CUDA(cudaMemcpyAsync(host.data(), e->m.height, host.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+  std::vector<uint32_t> host(e->host_cells());
+  SWE_CUDA(cudaMemcpyAsync(host.data(), e->owned().height, host.size() * 4, cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
   uint64_t h = 1469598103934665603ull;
   for (uint32_t w : host) { h ^= w; h *= 1099511628211ull; }
   *out = h;
+  return SWE_OK;
+}
+
+// ---- multi-GPU stripes -----------------------------------------------------------------------
+int swe_stripe_export(swe_engine* e, swe_stripe_link* out) {
+  if (!e || !out) return fail(SWE_ERR_INVALID, "NULL argument");
+  if (!e->st.enabled) return fail(SWE_ERR_STATE, "not a stripe engine");
+  out->height = e->m.height; out->stamp = e->d_stamp; out->arena = e->st.arena;
+  out->x0 = e->m.x0; out->inbox_capacity = e->st.inbox_capacity;
+  return SWE_OK;
+}
+
+int swe_stripe_export_ipc(swe_engine* e, void* buf, size_t buf_bytes) {
+  if (int rc = bind(e)) return rc;
+  if (!e->st.enabled) return fail(SWE_ERR_STATE, "not a stripe engine");
+  if (!buf || buf_bytes < SWE_STRIPE_IPC_BYTES) return fail(SWE_ERR_INVALID, "buffer must hold SWE_STRIPE_IPC_BYTES");
+  unsigned char* b = static_cast<unsigned char*>(buf);
+  std::memset(b, 0, SWE_STRIPE_IPC_BYTES);
+  cudaIpcMemHandle_t h[3];
+  SWE_CUDA(cudaIpcGetMemHandle(&h[0], e->m.height));
+  SWE_CUDA(cudaIpcGetMemHandle(&h[1], e->d_stamp));
+  SWE_CUDA(cudaIpcGetMemHandle(&h[2], e->st.arena));
+  static_assert(3 * sizeof(cudaIpcMemHandle_t) + 2 * sizeof(int) <= SWE_STRIPE_IPC_BYTES, "ipc blob size");
+  std::memcpy(b, h, sizeof h);
+  const int meta[2] = {e->m.x0, e->st.inbox_capacity};
+  std::memcpy(b + sizeof h, meta, sizeof meta);
+  return SWE_OK;
+}
+
+int swe_stripe_open_ipc(swe_engine* e, const void* buf, size_t buf_bytes, swe_stripe_link* out) {
+  if (int rc = bind(e)) return rc;
+  if (!buf || !out || buf_bytes < SWE_STRIPE_IPC_BYTES) return fail(SWE_ERR_INVALID, "bad ipc blob");
+  const unsigned char* b = static_cast<const unsigned char*>(buf);
+  cudaIpcMemHandle_t h[3];
+  std::memcpy(h, b, sizeof h);
+  int meta[2];
+  std::memcpy(meta, b + sizeof h, sizeof meta);
+  void* ptr[3] = {nullptr, nullptr, nullptr};
+  for (int i = 0; i < 3; i++) {
+    SWE_CUDA(cudaIpcOpenMemHandle(&ptr[i], h[i], cudaIpcMemLazyEnablePeerAccess));
+    e->st.ipc_opened.push_back(ptr[i]);
+  }
+  out->height = ptr[0]; out->stamp = ptr[1]; out->arena = ptr[2];
+  out->x0 = meta[0]; out->inbox_capacity = meta[1];
+  return SWE_OK;
+}
+
+int swe_stripe_connect(swe_engine* e, const swe_stripe_link* below, const swe_stripe_link* above) {
+  if (int rc = bind(e)) return rc;
+  if (!e->st.enabled) return fail(SWE_ERR_STATE, "not a stripe engine");
+  auto& S = e->st;
+  if ((below == nullptr) != (S.own_lo == 0))
+    return fail(SWE_ERR_INVALID, "a stripe needs a neighbour below exactly when it does not start at row 0");
+  if ((above == nullptr) != (S.own_hi == e->m.nx))
+    return fail(SWE_ERR_INVALID, "a stripe needs a neighbour above exactly when it does not end at the last row");
+  for (const swe_stripe_link* l : {below, above})
+    if (l && (!l->height || !l->stamp || !l->arena || l->inbox_capacity != S.inbox_capacity))
+      return fail(SWE_ERR_INVALID, "neighbour link is incomplete or was created with another max_particles");
+  S.has_below = below != nullptr; S.has_above = above != nullptr;
+  if (below) S.below = *below;
+  if (above) S.above = *above;
+  S.connected = true;
+  return SWE_OK;
+}
+
+int swe_stripe_sync_halos(swe_engine* e) {
+  if (int rc = bind(e)) return rc;
+  if (!e->st.enabled || !e->st.connected) return fail(SWE_ERR_STATE, "stripe engine is not connected");
+  int n = 0;
+  const unsigned s = stripe_exchange_begin(e, false, &n);
+  stripe_exchange_end(e, s, &n);
+  return check_launch(e, "stripe halo sync", n);
+}
+
+int swe_stripe_rows(const swe_engine* e, int* own_lo, int* own_hi) {
+  if (!e) return fail(SWE_ERR_INVALID, "engine is NULL");
+  if (own_lo) *own_lo = e->own_lo();
+  if (own_hi) *own_hi = e->own_hi();
   return SWE_OK;
 }
 

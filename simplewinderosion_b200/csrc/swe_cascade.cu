@@ -227,7 +227,7 @@ template <bool USE_STAMP, bool USE_TMA>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
                     const unsigned char* __restrict__ stamp, unsigned char stamp_now,
-                    const unsigned* __restrict__ gate) {
+                    const unsigned* __restrict__ gate, RowWindow win) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (USE_STAMP && gate && *gate == 0u) return;
   float* tile = reinterpret_cast<float*>(smem_raw);
@@ -235,7 +235,8 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   unsigned* qcount = reinterpret_cast<unsigned*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES);  // [2]
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 8);
   unsigned char* stile = smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 16;
-  const int ox0 = TILE_OX + (int)blockIdx.y * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
+  const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
+  const int sx0 = m.x0, sx1 = m.x0 + m.rows;       // rows present in local storage (a stripe + ghosts)
   const int gx0 = ox0 - 2, gz0 = oz0 - 8;          // global coords of tile[0][0]
   const int tid = threadIdx.y * TILE_BX + threadIdx.x;
   const int nx = m.nx, nz = m.nz;
@@ -263,7 +264,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       const int lx = i / TILE_PITCH, lz = i - lx * TILE_PITCH;
       const int gx = gx0 + lx, gz = gz0 + lz;
       float v = 0.0f;
-      if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) v = __ldg(m.height + m.idx(gx, gz));
+      if (gx >= sx0 && gx < sx1 && gz >= 0 && gz < nz) v = __ldg(m.height + m.idx(gx, gz));
       tile[i] = v;
     }
   }
@@ -274,7 +275,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
         const int lx = i / (TILE_PITCH / 4), q = i - lx * (TILE_PITCH / 4);
         const int gx = gx0 + lx, gz = gz0 + 4 * q;
         unsigned v = 0u;
-        if (gx >= 0 && gx < nx && gz >= 0 && gz < nz)
+        if (gx >= sx0 && gx < sx1 && gz >= 0 && gz < nz)
           v = __ldcg(reinterpret_cast<const unsigned*>(stamp + m.idx(gx, gz)));
         sw[i] = v;
       }
@@ -283,7 +284,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
         const int lx = i / TILE_PITCH, lz = i - lx * TILE_PITCH;
         const int gx = gx0 + lx, gz = gz0 + lz;
         unsigned char v = 0;
-        if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) v = __ldcg(stamp + m.idx(gx, gz));
+        if (gx >= sx0 && gx < sx1 && gz >= 0 && gz < nz) v = __ldcg(stamp + m.idx(gx, gz));
         stile[i] = v;
       }
     }
@@ -372,7 +373,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       for (int i = tid; i < TILE_TX * (TILE_TZ / 4); i += TILE_THREADS) {
         const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);
         const int gx = ox0 + ox, gz = oz0 + 4 * q;
-        if (gx >= 0 && gx < nx && gz >= 0 && gz < nz)
+        if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz)
           *reinterpret_cast<float4*>(m.height + m.idx(gx, gz)) =
               *reinterpret_cast<const float4*>(tile + (ox + 2) * TILE_PITCH + 8 + 4 * q);
       }
@@ -380,7 +381,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       for (int i = tid; i < TILE_TX * TILE_TZ; i += TILE_THREADS) {
         const int ox = i / TILE_TZ, oz = i - ox * TILE_TZ;
         const int gx = ox0 + ox, gz = oz0 + oz;
-        if (gx >= 0 && gx < nx && gz >= 0 && gz < nz)
+        if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz)
           m.height[m.idx(gx, gz)] = tile[(ox + 2) * TILE_PITCH + (oz + 8)];
       }
     }
@@ -455,39 +456,49 @@ bool make_height_tensor_map(const MapView& m, HeightTensorMap* out) {
 template <bool S, bool T>
 static void tile_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, const CUtensorMap& tm,
                         const MapView& m, float settling, CascadeThr thr, const unsigned char* stamp,
-                        unsigned char now, const unsigned* gate) {
+                        unsigned char now, const unsigned* gate, RowWindow win) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(cascade_tile_kernel<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  cascade_tile_kernel<S, T><<<grid, block, smem, st>>>(tm, m, settling, thr, stamp, now, gate);
+  cascade_tile_kernel<S, T><<<grid, block, smem, st>>>(tm, m, settling, thr, stamp, now, gate, win);
 }
 
+// rows [row_lo, row_hi) are (re)computed and stored; the tiles covering them are launched. On a
+// single GPU that is the whole map; a stripe computes its owned rows plus one ghost row each side
+// from a halo of 3 rows below / 5 above (the 2/4-row dependency cone of the nine colours).
 static void launch_tile_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                               const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                              cudaStream_t st) {
+                              int row_lo, int row_hi, cudaStream_t st) {
   CascadeThr thr;
   thr.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;      // host IEEE fp32: same values as the device helper
   thr.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
-  const dim3 grid((m.nz - TILE_OZ + TILE_TZ - 1) / TILE_TZ, (m.nx - TILE_OX + TILE_TX - 1) / TILE_TX);
+  if (row_lo < 0) row_lo = 0;
+  if (row_hi > m.nx) row_hi = m.nx;
+  if (row_hi <= row_lo) return;
+  RowWindow win;
+  win.store_lo = row_lo; win.store_hi = row_hi;
+  win.tile_y0 = (row_lo - TILE_OX) / TILE_TX;
+  const int tile_y1 = (row_hi - 1 - TILE_OX) / TILE_TX;
+  const dim3 grid((m.nz - TILE_OZ + TILE_TZ - 1) / TILE_TZ, tile_y1 - win.tile_y0 + 1);
   const dim3 block(TILE_BX, TILE_BY);
   const bool tma = tmap && tmap->valid;
   CUtensorMap tm;
   if (tma) memcpy(&tm, tmap->opaque, sizeof tm); else memset(&tm, 0, sizeof tm);
   if (stamp) {
-    if (tma) tile_launch<true, true>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate);
-    else     tile_launch<true, false>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate);
+    if (tma) tile_launch<true, true>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate, win);
+    else     tile_launch<true, false>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate, win);
   } else {
-    if (tma) tile_launch<false, true>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr);
-    else     tile_launch<false, false>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr);
+    if (tma) tile_launch<false, true>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr, win);
+    else     tile_launch<false, false>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr, win);
   }
 }
 
 void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                             const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                            cudaStream_t st) {
-  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, st);
+                            int row_lo, int row_hi, cudaStream_t st) {
+  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, row_lo, row_hi, st);
 }
 
 int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap, int sweeps,
@@ -495,7 +506,7 @@ int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTens
   int launches = 0;
   for (int s = 0; s < sweeps; s++) {
     if (variant == 0 || variant == 2) {
-      launch_tile_sweep(m, p, variant == 2 ? nullptr : tmap, nullptr, 0, nullptr, st);
+      launch_tile_sweep(m, p, variant == 2 ? nullptr : tmap, nullptr, 0, nullptr, 0, m.nx, st);
       launches++;
       continue;
     }

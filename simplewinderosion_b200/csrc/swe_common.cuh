@@ -60,11 +60,18 @@ void launch_det_fly_once(const MapView& m, const swe_params& p, swe_wind* d_wind
                          DetRand* rng, DevStats* stats, cudaStream_t st);
 void launch_det_cascade_one(const MapView& m, const swe_params& p, int x, int z, cudaStream_t st);
 void launch_det_srand(DetRand* rng, uint32_t seed, cudaStream_t st);
-void launch_normals(const MapView& m, const swe_params& p, float* d_out3, cudaStream_t st);
+void launch_normals_rows(const MapView& m, const swe_params& p, int row_lo, int row_hi, float* d_out3,
+                         cudaStream_t st);
 void launch_normal_one(const MapView& m, const swe_params& p, int x, int z, float* d_out3,
                        cudaStream_t st);
 
 // whole-map cascade: swe_cascade.cu
+// Which rows a tile sweep stores (and therefore which tiles it launches).
+struct RowWindow {
+  int store_lo, store_hi;   // global rows written back
+  int tile_y0;              // index of the first tile row launched
+};
+
 // TMA descriptor of the height plane (CUtensorMap, kept opaque here), built once per engine.
 struct alignas(64) HeightTensorMap {
   unsigned char opaque[128];
@@ -79,7 +86,7 @@ int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTens
 // (gate: device counter; the sweep is skipped when *gate == 0, i.e. no particle flew)
 void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                             const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                            cudaStream_t st);
+                            int row_lo, int row_hi, cudaStream_t st);
 void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st);
 
 // parallel flight: swe_par.cu
@@ -93,11 +100,43 @@ struct ParticleBuf {
   int live_slots;
   int capacity;
 };
+// Stripe (multi-GPU) round context. Outboxes are PEER memory: the neighbour's inbox for the
+// current round parity (device pointers valid on this GPU through CUDA IPC / peer access).
+struct StripeOutbox {
+  float4* a;
+  float4* b;
+  uint32_t* pid;
+  unsigned* count;
+  int capacity;
+};
+struct StripeRound {
+  int own_lo, own_hi;       // global rows this rank owns
+  uint32_t* pid;            // ids of the local particles
+  unsigned* n_used;         // local particle slots in use
+  unsigned* overflow;       // particles dropped for lack of space (must stay 0)
+  StripeOutbox below, above;
+};
+void launch_par_begin_stripe(const ParticleBuf& buf, const StripeRound& sr, const MapView& m, int n,
+                             uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st);
+void launch_par_round_stripe(const ParticleBuf& buf, const StripeRound& sr, const MapView& m,
+                             const swe_params& p, int steps_per_round, uint64_t seed, uint32_t call,
+                             unsigned char* stamp, unsigned char stamp_now, DevStats* stats,
+                             cudaStream_t st);
 void launch_par_begin(const ParticleBuf& buf, const MapView& m, int n, uint64_t seed, uint32_t call,
                       DevStats* stats, cudaStream_t st);
 void launch_par_round(const ParticleBuf& buf, const MapView& m, const swe_params& p, int n, int round,
                       int steps_per_round, uint64_t seed, uint32_t call, unsigned char* stamp,
                       unsigned char stamp_now, DevStats* stats, cudaStream_t st);
+
+// stripe exchange primitives: swe_stripe.cu
+void launch_stripe_push(const float* src_h, float* dst_h, const unsigned char* src_s, unsigned char* dst_s,
+                        size_t cells, cudaStream_t st);
+void launch_stripe_signal(unsigned* peer_flag_a, unsigned* peer_flag_b, unsigned value, cudaStream_t st);
+void launch_stripe_wait(const unsigned* flag_a, const unsigned* flag_b, unsigned value, unsigned* error_flag,
+                        cudaStream_t st);
+void launch_stripe_merge(const float4* in_a, const float4* in_b, const uint32_t* in_pid, unsigned* in_count,
+                         int in_capacity, float4* pa, float4* pb, uint32_t* pid, unsigned* n_used,
+                         int capacity, unsigned* overflow, unsigned* scratch_base, cudaStream_t st);
 
 // field passes and utilities: swe_fields.cu
 void launch_ema(const MapView& m, float lrate, cudaStream_t st);

@@ -205,11 +205,11 @@ __global__ void det_cascade_one_kernel(MapView m, swe_params P, int x, int z) {
 }
 
 // quad::map::normal for every cell (what the renderer's updatenode reads, cellpool.h:302-321)
-__global__ void normals_kernel(MapView m, swe_params P, float* out3) {
-  const size_t n = (size_t)m.rows * m.nz;
+__global__ void normals_kernel(MapView m, swe_params P, int row_lo, int row_hi, float* out3) {
+  const size_t n = (size_t)(row_hi - row_lo) * m.nz;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
-    const int x = m.x0 + (int)(i / m.nz), z = (int)(i % m.nz);
+    const int x = row_lo + (int)(i / m.nz), z = (int)(i % m.nz);
     const V3 nn = normal(m, P, x, z);
     out3[3 * i + 0] = nn.x; out3[3 * i + 1] = nn.y; out3[3 * i + 2] = nn.z;
   }
@@ -241,11 +241,12 @@ void launch_det_cascade_one(const MapView& m, const swe_params& p, int x, int z,
 void launch_det_srand(DetRand* rng, uint32_t seed, cudaStream_t st) {
   det_srand_kernel<<<1, 32, 0, st>>>(rng, seed);
 }
-void launch_normals(const MapView& m, const swe_params& p, float* d_out3, cudaStream_t st) {
-  const size_t n = (size_t)m.rows * m.nz;
+void launch_normals_rows(const MapView& m, const swe_params& p, int row_lo, int row_hi, float* d_out3,
+                         cudaStream_t st) {
+  const size_t n = (size_t)(row_hi - row_lo) * m.nz;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  normals_kernel<<<blocks, 256, 0, st>>>(m, p, d_out3);
+  normals_kernel<<<blocks, 256, 0, st>>>(m, p, row_lo, row_hi, d_out3);
 }
 void launch_normal_one(const MapView& m, const swe_params& p, int x, int z, float* d_out3,
                        cudaStream_t st) {

@@ -160,10 +160,8 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
 // equally likely, as in the reference, and particles adjacent in memory start adjacent on the map
 // (a warp covers ~4 rows x 32 columns at 0.25 particles/cell), so a warp's neighbourhood reads
 // and atomics fall into a handful of 32-byte sectors instead of 32 scattered ones.
-__global__ void par_spawn_kernel(float4* __restrict__ pa, float4* __restrict__ pb, int n, int nx,
-                                 int nz, uint2 key, uint32_t call) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void spawn_position(int i, int n, int nx, int nz, uint2 key, uint32_t call,
+                                               float& px, float& pz) {
   const uint4 r = philox4x32_10(make_uint4((uint32_t)i, call, 0u, 0x5u), key);
   const unsigned long long ncells = (unsigned long long)nx * (unsigned long long)nz;
   unsigned long long rank =
@@ -174,34 +172,81 @@ __global__ void par_spawn_kernel(float4* __restrict__ pa, float4* __restrict__ p
   const unsigned q = (unsigned)(rank - (unsigned long long)strip * strip_cells);
   const int rows = min(4, nx - 4 * strip);
   const int cz = (int)(q / (unsigned)rows), cx = 4 * strip + (int)(q - (unsigned)cz * (unsigned)rows);
-  const float px = (float)cx + (float)__umulhi(r.z, 1000u) / 1000.0f;
-  const float pz = (float)cz + (float)__umulhi(r.w, 1000u) / 1000.0f;
+  px = (float)cx + (float)__umulhi(r.z, 1000u) / 1000.0f;
+  pz = (float)cz + (float)__umulhi(r.w, 1000u) / 1000.0f;
+}
+
+__global__ void par_spawn_kernel(float4* __restrict__ pa, float4* __restrict__ pb, int n, int nx,
+                                 int nz, uint2 key, uint32_t call) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float px, pz;
+  spawn_position(i, n, nx, nz, key, call, px, pz);
   pa[i] = make_float4(px, 0.0f, pz, 0.0f);
   pb[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
 }
 
+// Stripe variant: the call's n particles are global; this rank materialises those of the
+// candidate id range [i0, i1) whose first cell (wind.hpp:30: round(pos)) lies in its owned rows
+// (particles spawned beyond the last row belong to the rank owning their spawn cell; they die at
+// once, wind.hpp:32-38). Survivors are compacted into the local arrays together with their id.
+__global__ void par_spawn_stripe_kernel(float4* __restrict__ pa, float4* __restrict__ pb,
+                                        uint32_t* __restrict__ pid, unsigned* __restrict__ n_used,
+                                        int capacity, unsigned* __restrict__ overflow, int i0, int i1,
+                                        int n, int nx, int nz, int own_lo, int own_hi, uint2 key,
+                                        uint32_t call) {
+  const int i = i0 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  bool mine = false;
+  float px = 0.0f, pz = 0.0f;
+  if (i < i1) {
+    spawn_position(i, n, nx, nz, key, call, px, pz);
+    int row = __float2int_rd(px + 0.5f);
+    if (row >= nx) row = nx - 1;
+    mine = row >= own_lo && row < own_hi;
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, mine);
+  if (!mask) return;
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned base = 0;
+  if (lane == (unsigned)(__ffs(mask) - 1)) base = atomicAdd(n_used, (unsigned)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+  if (!mine) return;
+  const unsigned slot = base + __popc(mask & ((1u << lane) - 1u));
+  if (slot >= (unsigned)capacity) { atomicAdd(overflow, 1u); return; }
+  pa[slot] = make_float4(px, 0.0f, pz, 0.0f);
+  pb[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
+  pid[slot] = (uint32_t)i;
+}
+
 // K steps for every live particle. live_in/live_out: device counters of particles alive
 // before/after this round (trailing rounds of a call exit at once when nothing is alive).
+// STRIPE: the particle arrays hold only this rank's particles (n = capacity, *n_used of them in
+// use, ids in pid[]); a particle whose next cell lies in a neighbour's rows is appended to that
+// neighbour's inbox through its peer-mapped pointers (NVLink stores + a system-scope atomic for
+// the slot) and retired here.
+template <bool STRIPE>
 __global__ void __launch_bounds__(256)
 par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restrict__ pb, int n,
                  int steps_per_round, uint2 key, uint32_t call, unsigned char* stamp,
                  unsigned char stamp_now, const unsigned* live_in, unsigned* live_out,
-                 DevStats* stats) {
+                 DevStats* stats, StripeRound sr) {
   if (live_in && *live_in == 0u) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned steps = 0, n_oob = 0, n_age = 0, alive = 0;
   float lost = 0.0f;
-  if (i < n) {
+  const int n_eff = STRIPE ? (int)min(*sr.n_used, (unsigned)n) : n;
+  if (i < n_eff) {
     const float4 b = pb[i];
     PState q;
     q.age = __float_as_int(b.w);
     if (q.age >= 0) {
       const float4 a = pa[i];
+      const uint32_t id = STRIPE ? sr.pid[i] : (uint32_t)i;
       q.px = a.x; q.py = a.y; q.pz = a.z; q.sed = a.w;
       q.sx = b.x; q.sy = b.y; q.sz = b.z;
       int r = 0;
       for (int s = 0; s < steps_per_round; s++) {
-        r = par_step(m, C, q, (uint32_t)i, key, call, stamp, stamp_now);
+        r = par_step(m, C, q, id, key, call, stamp, stamp_now);
         if (r != 0) break;
         steps++;
       }
@@ -211,6 +256,23 @@ par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restr
         q.age = -1;
       } else {
         alive = 1;
+        if (STRIPE) {
+          const int row = __float2int_rd(q.px + 0.5f);
+          const bool down = row < sr.own_lo && row >= 0, up = row >= sr.own_hi && row < m.nx;
+          if (down || up) {   // hand the particle to the owner of its next cell
+            const StripeOutbox& ob = down ? sr.below : sr.above;
+            const unsigned slot = atomicAdd_system(ob.count, 1u);
+            if (slot < (unsigned)ob.capacity) {
+              ob.a[slot] = make_float4(q.px, q.py, q.pz, q.sed);
+              ob.b[slot] = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
+              ob.pid[slot] = id;
+            } else {
+              atomicAdd(sr.overflow, 1u);   // dropped: reported through swe_stats
+              lost = q.sed;
+            }
+            q.age = -2;     // retired here; it stays counted as alive for the call
+          }
+        }
       }
       pa[i] = make_float4(q.px, q.py, q.pz, q.sed);
       pb[i] = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
@@ -240,7 +302,7 @@ par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restr
     if (s_cnt[0]) atomicAdd(&stats->steps, (unsigned long long)s_cnt[0]);
     if (s_cnt[1]) atomicAdd(&stats->exits_oob, (unsigned long long)s_cnt[1]);
     if (s_cnt[2]) atomicAdd(&stats->exits_age, (unsigned long long)s_cnt[2]);
-    if (s_cnt[3]) atomicAdd(live_out, s_cnt[3]);
+    if (s_cnt[3] && live_out) atomicAdd(live_out, s_cnt[3]);
     if (s_lost != 0.0f) atomicAdd(&stats->sediment_lost, (double)s_lost);
   }
 }
@@ -274,9 +336,44 @@ void launch_par_round(const ParticleBuf& buf, const MapView& m, const swe_params
                       int steps_per_round, uint64_t seed, uint32_t call, unsigned char* stamp,
                       unsigned char stamp_now, DevStats* stats, cudaStream_t st) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  par_round_kernel<<<(n + 255) / 256, 256, 0, st>>>(m, make_const(p), buf.a, buf.b, n, steps_per_round,
-                                                    key, call, stamp, stamp_now, buf.live + round,
-                                                    buf.live + round + 1, stats);
+  StripeRound none{};
+  par_round_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(m, make_const(p), buf.a, buf.b, n, steps_per_round,
+                                                           key, call, stamp, stamp_now, buf.live + round,
+                                                           buf.live + round + 1, stats, none);
+}
+
+// ---- stripe (multi-GPU) launchers ---------------------------------------------------------------
+__global__ void stripe_begin_kernel(DevStats* stats, unsigned* n_used) { *n_used = 0u; (void)stats; }
+__global__ void stripe_count_spawned_kernel(DevStats* stats, const unsigned* n_used, int capacity) {
+  stats->particles += min(*n_used, (unsigned)capacity);
+}
+
+void launch_par_begin_stripe(const ParticleBuf& buf, const StripeRound& sr, const MapView& m, int n,
+                             uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  stripe_begin_kernel<<<1, 1, 0, st>>>(stats, sr.n_used);
+  // candidate ids: strip-major rank order is monotone in the row, so the owned rows map to one
+  // id interval; +-2 strips of slack cover the jitter u and the round() of the first cell
+  const double per_cell = (double)n / ((double)m.nx * (double)m.nz);
+  long long i0 = (long long)((double)(sr.own_lo - 8) * m.nz * per_cell) - 64;
+  long long i1 = (long long)((double)(sr.own_hi + 8) * m.nz * per_cell) + 64;
+  if (i0 < 0) i0 = 0;
+  if (i1 > n) i1 = n;
+  if (i1 > i0)
+    par_spawn_stripe_kernel<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, st>>>(
+        buf.a, buf.b, sr.pid, sr.n_used, buf.capacity, sr.overflow, (int)i0, (int)i1, n, m.nx, m.nz,
+        sr.own_lo, sr.own_hi, key, call);
+  stripe_count_spawned_kernel<<<1, 1, 0, st>>>(stats, sr.n_used, buf.capacity);
+}
+
+void launch_par_round_stripe(const ParticleBuf& buf, const StripeRound& sr, const MapView& m,
+                             const swe_params& p, int steps_per_round, uint64_t seed, uint32_t call,
+                             unsigned char* stamp, unsigned char stamp_now, DevStats* stats,
+                             cudaStream_t st) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  par_round_kernel<true><<<(buf.capacity + 255) / 256, 256, 0, st>>>(
+      m, make_const(p), buf.a, buf.b, buf.capacity, steps_per_round, key, call, stamp, stamp_now, nullptr,
+      nullptr, stats, sr);
 }
 
 }  // namespace swe

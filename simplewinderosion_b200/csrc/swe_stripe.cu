@@ -1,0 +1,118 @@
+// swe_stripe.cu -- multi-GPU row stripes: halo push, particle hand-off and neighbour
+// synchronisation done by kernels over peer-mapped memory (NVLink/NVSwitch P2P through CUDA IPC),
+// with no host involvement inside a World::erode call.
+//
+// Decomposition: rank r owns the global rows [own_lo, own_hi) and stores
+// [own_lo-3, own_hi+5) (clipped to the map). Per round of the parallel pipeline:
+//   1. par_round_kernel<STRIPE>: steps the local particles (they only write their own, owned,
+//      centre cell); a particle whose next cell belongs to a neighbour is stored straight into
+//      that neighbour's inbox (peer stores + one system-scope atomic for the slot).
+//   2. wait until the neighbours have finished READING the ghosts of the previous round
+//      (consumed flags), then push the post-deposit boundary rows (heights + stamps) into their
+//      ghost rows: my first 5 owned rows go below, my last 3 owned rows go above.
+//   3. signal "round r delivered" (ready flags), wait for the neighbours' ready flags.
+//   4. merge the inbox into the local particle arrays.
+//   5. stamped cascade on rows [own_lo-1, own_hi+1): with the 3/5-row halo the nine-colour
+//      dependency cone (2 rows low, 4 high) is complete, so these rows come out bitwise equal to
+//      what the neighbour computes for them -- no second exchange for the next round's reads.
+//   6. signal "ghosts of round r consumed".
+// Flags are monotonically increasing sequence numbers written with system-scope release stores
+// after a __threadfence_system() and polled with volatile loads; every rank posts before it waits,
+// so there is no cyclic wait. Polls give up after ~10 s and raise an error flag instead of
+// hanging the GPU.
+#include "swe_common.cuh"
+
+namespace swe {
+
+__global__ void stripe_push_rows_kernel(const float* __restrict__ src_h, float* __restrict__ dst_h,
+                                        const unsigned char* __restrict__ src_s,
+                                        unsigned char* __restrict__ dst_s, size_t cells) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells;
+       i += (size_t)gridDim.x * blockDim.x) {
+    dst_h[i] = src_h[i];
+    if (src_s) dst_s[i] = src_s[i];
+  }
+}
+
+__global__ void stripe_signal_kernel(unsigned* peer_flag_a, unsigned* peer_flag_b, unsigned value) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __threadfence_system();   // everything this stream wrote to peer memory is visible first
+  if (peer_flag_a) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag_a), "r"(value) : "memory");
+  if (peer_flag_b) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag_b), "r"(value) : "memory");
+}
+
+__global__ void stripe_wait_kernel(const unsigned* flag_a, const unsigned* flag_b, unsigned value,
+                                   unsigned* error_flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (*reinterpret_cast<volatile unsigned*>(error_flag)) return;   // already failed: do not wait again
+  const long long t0 = clock64();
+  const unsigned* flags[2] = {flag_a, flag_b};
+  for (int k = 0; k < 2; k++) {
+    if (!flags[k]) continue;
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags[k]) : "memory");
+      if ((int)(v - value) >= 0) break;
+      if (clock64() - t0 > 20000000000LL) { atomicExch(error_flag, 1u); return; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+
+// append the particles neighbours handed over in this round; the inbox counter is reset for its
+// next use (two rounds later, after this rank has signalled again)
+__global__ void stripe_merge_kernel(const float4* __restrict__ in_a, const float4* __restrict__ in_b,
+                                    const uint32_t* __restrict__ in_pid, unsigned* in_count, int in_capacity,
+                                    float4* __restrict__ pa, float4* __restrict__ pb,
+                                    uint32_t* __restrict__ pid, unsigned* n_used, int capacity,
+                                    unsigned* overflow, unsigned* base_slot) {
+  const unsigned cnt = min(*in_count, (unsigned)in_capacity);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) {
+    const unsigned slot = *base_slot + i;
+    if (slot < (unsigned)capacity) {
+      pa[slot] = in_a[i]; pb[slot] = in_b[i]; pid[slot] = in_pid[i];
+    } else {
+      atomicAdd(overflow, 1u);
+    }
+  }
+}
+__global__ void stripe_merge_prepare_kernel(const unsigned* in_count, int in_capacity, const unsigned* n_used,
+                                            unsigned* base_slot, unsigned* overflow) {
+  *base_slot = *n_used;
+  if (*in_count > (unsigned)in_capacity) atomicAdd(overflow, *in_count - (unsigned)in_capacity);
+}
+__global__ void stripe_merge_finish_kernel(unsigned* in_count, int in_capacity, unsigned* n_used, int capacity) {
+  const unsigned cnt = min(*in_count, (unsigned)in_capacity);
+  const unsigned nu = *n_used + cnt;
+  *n_used = nu < (unsigned)capacity ? nu : (unsigned)capacity;
+  *in_count = 0u;
+}
+
+void launch_stripe_push(const float* src_h, float* dst_h, const unsigned char* src_s, unsigned char* dst_s,
+                        size_t cells, cudaStream_t st) {
+  if (cells == 0) return;
+  int blocks = (int)((cells + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  stripe_push_rows_kernel<<<blocks, 256, 0, st>>>(src_h, dst_h, src_s, dst_s, cells);
+}
+void launch_stripe_signal(unsigned* peer_flag_a, unsigned* peer_flag_b, unsigned value, cudaStream_t st) {
+  if (!peer_flag_a && !peer_flag_b) return;
+  stripe_signal_kernel<<<1, 32, 0, st>>>(peer_flag_a, peer_flag_b, value);
+}
+void launch_stripe_wait(const unsigned* flag_a, const unsigned* flag_b, unsigned value, unsigned* error_flag,
+                        cudaStream_t st) {
+  if (!flag_a && !flag_b) return;
+  stripe_wait_kernel<<<1, 32, 0, st>>>(flag_a, flag_b, value, error_flag);
+}
+void launch_stripe_merge(const float4* in_a, const float4* in_b, const uint32_t* in_pid, unsigned* in_count,
+                         int in_capacity, float4* pa, float4* pb, uint32_t* pid, unsigned* n_used,
+                         int capacity, unsigned* overflow, unsigned* scratch_base, cudaStream_t st) {
+  stripe_merge_prepare_kernel<<<1, 1, 0, st>>>(in_count, in_capacity, n_used, scratch_base, overflow);
+  stripe_merge_kernel<<<(in_capacity + 255) / 256, 256, 0, st>>>(in_a, in_b, in_pid, in_count, in_capacity, pa,
+                                                                  pb, pid, n_used, capacity, overflow, scratch_base);
+  stripe_merge_finish_kernel<<<1, 1, 0, st>>>(in_count, in_capacity, n_used, capacity);
+}
+
+}  // namespace swe

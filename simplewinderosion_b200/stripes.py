@@ -1,0 +1,143 @@
+"""Multi-GPU row stripes: one process and one engine per GPU, the map cut along x
+(the slow index). torch.distributed is used ONLY for set-up plumbing (exchanging CUDA IPC handles,
+reducing statistics); inside World.erode the neighbours exchange ghost rows and hand over particles
+with kernels over peer-mapped memory (NVLink P2P), see csrc/swe_stripe.cu.
+
+    bounds = stripe_bounds(nx, world_size)
+    w = StripedWorld(nx, nz, rank, world_size, max_particles, device=local_rank)
+    w.connect()                      # all ranks (collective)
+    w.upload_global(height)          # every rank passes the same global map (or only its rows)
+    w.erode(cycles)                  # cycles = GLOBAL particle count of the call
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import world as _world
+from ._capi import STRIPE_IPC_BYTES, StripeLink, check, lib
+
+MIN_ROWS = 8
+
+
+def stripe_bounds(nx: int, world_size: int, align: int = 4) -> list[tuple[int, int]]:
+    """Balanced row ranges, boundaries on multiples of `align` (the spawn order works in strips of
+    4 rows), every stripe at least MIN_ROWS rows."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    if nx < MIN_ROWS * world_size:
+        raise ValueError(f"{nx} rows cannot be cut into {world_size} stripes of >= {MIN_ROWS} rows")
+    cuts = [0]
+    for r in range(1, world_size):
+        c = int(round(nx * r / world_size / align)) * align
+        c = max(c, cuts[-1] + MIN_ROWS)
+        cuts.append(c)
+    cuts.append(nx)
+    for r in range(world_size - 1, 0, -1):          # keep the tail stripes tall enough
+        if cuts[r + 1] - cuts[r] < MIN_ROWS:
+            cuts[r] = cuts[r + 1] - MIN_ROWS
+    out = [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+    assert all(hi - lo >= MIN_ROWS for lo, hi in out) and out[0][0] == 0 and out[-1][1] == nx
+    return out
+
+
+def owner_of_row(bounds: list[tuple[int, int]], x: int) -> int:
+    for r, (lo, hi) in enumerate(bounds):
+        if lo <= x < hi:
+            return r
+    raise ValueError(f"row {x} outside the map")
+
+
+def allgather_bytes(blob: bytes, world_size: int, group=None, device=None) -> list[bytes]:
+    """Fixed-size byte blobs from every rank (torch.distributed plumbing; works with gloo or nccl)."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", device or 0) if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(blob), dtype=torch.uint8, device=dev)
+    gathered = [torch.empty(len(blob), dtype=torch.uint8, device=dev) for _ in range(world_size)]
+    dist.all_gather(gathered, mine, group=group)
+    return [bytes(g.cpu().tolist()) for g in gathered]
+
+
+def run_on_all(worlds: list, fn) -> list:
+    """In-process stripes: issue `fn(world)` for every stripe from its own host thread. The calls
+    enqueue thousands of launches whose wait kernels need the OTHER stripes' kernels to be enqueued
+    too, so a single thread would fill one stream's launch queue and stall."""
+    import threading
+    out, err = [None] * len(worlds), [None] * len(worlds)
+
+    def work(i):
+        try:
+            out[i] = fn(worlds[i])
+        except BaseException as e:   # noqa: BLE001
+            err[i] = e
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(worlds))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+class StripedWorld(_world.World):
+    """One rank's stripe of a World spread over world_size GPUs."""
+
+    def __init__(self, nx: int, nz: int, rank: int, world_size: int, max_particles: int,
+                 params=None, device: int = 0):
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.bounds = stripe_bounds(nx, world_size)
+        super().__init__(nx, nz, params=params, device=device, stripe=self.bounds[rank],
+                         max_particles=max_particles)
+
+    # -- wiring -----------------------------------------------------------------------------------
+    def export_link(self) -> StripeLink:
+        link = StripeLink()
+        check(lib.swe_stripe_export(self._h, C.byref(link)))
+        return link
+
+    def connect_links(self, below: StripeLink | None, above: StripeLink | None) -> None:
+        check(lib.swe_stripe_connect(self._h, C.byref(below) if below is not None else None,
+                                     C.byref(above) if above is not None else None))
+
+    @staticmethod
+    def connect_in_process(worlds: list["StripedWorld"]) -> None:
+        """All stripes live in this process (several logical stripes on one or more GPUs)."""
+        links = [w.export_link() for w in worlds]
+        for r, w in enumerate(worlds):
+            w.connect_links(links[r - 1] if r > 0 else None, links[r + 1] if r + 1 < len(worlds) else None)
+
+    def connect(self, group=None) -> None:
+        """One process per GPU: exchange CUDA IPC handles through torch.distributed (collective)."""
+        import torch.distributed as dist
+        blob = (C.c_ubyte * STRIPE_IPC_BYTES)()
+        check(lib.swe_stripe_export_ipc(self._h, blob, STRIPE_IPC_BYTES))
+        gathered = allgather_bytes(bytes(blob), self.world_size, group, self.device)
+        links = {}
+        for nb in (self.rank - 1, self.rank + 1):
+            if 0 <= nb < self.world_size:
+                buf = (C.c_ubyte * STRIPE_IPC_BYTES).from_buffer_copy(gathered[nb])
+                link = StripeLink()
+                check(lib.swe_stripe_open_ipc(self._h, buf, STRIPE_IPC_BYTES, C.byref(link)))
+                links[nb] = link
+        self.connect_links(links.get(self.rank - 1), links.get(self.rank + 1))
+        dist.barrier(group=group)
+
+    # -- map transfer -------------------------------------------------------------------------------
+    def upload_global(self, height: np.ndarray, plane: int = _world.HEIGHT) -> None:
+        """Take this rank's rows out of a global (nx, nz) plane. Call sync_halos() afterwards
+        (collective: every rank must)."""
+        lo, hi = self.bounds[self.rank]
+        self.upload(np.ascontiguousarray(height[lo:hi]), plane)
+
+    def sync_halos(self) -> None:
+        check(lib.swe_stripe_sync_halos(self._h))
+
+
+def gather_global(worlds: list[StripedWorld], plane: int = _world.HEIGHT) -> np.ndarray:
+    """In-process helper: stitch the owned rows of all stripes back into one (nx, nz) plane."""
+    return np.concatenate([w.download(plane) for w in worlds], axis=0)

@@ -49,7 +49,7 @@ class _Map:
 
     def oob(self, p) -> bool:
         x, z = int(p[0]), int(p[1])
-        return x < 0 or z < 0 or x >= self._w.nx or z >= self._w.nz
+        return x < 0 or z < 0 or x >= self._w.global_nx or z >= self._w.nz
 
     def height(self, p) -> float:
         """map.height(p): 0.0 for out-of-bounds, like the reference (cellpool.h:472-476)."""
@@ -68,12 +68,24 @@ class _Map:
 class World:
     """class World (world.hpp:9-32) with a run-time map size."""
 
-    def __init__(self, nx: int, nz: int | None = None, params: Params | None = None, device: int = 0):
+    def __init__(self, nx: int, nz: int | None = None, params: Params | None = None, device: int = 0,
+                 stripe: tuple[int, int] | None = None, max_particles: int = 0):
+        """stripe=(own_lo, own_hi): this engine is one row stripe of an nx-by-nz map spread over
+        several GPUs (see stripes.py); host transfers then cover the owned rows only and
+        ``self.nx`` is the number of owned rows (``self.global_nx`` the map's)."""
         nz = nx if nz is None else nz
         self._h = C.c_void_p()
         p = params if params is not None else default_params()
-        check(lib.swe_create(C.byref(self._h), int(nx), int(nz), C.byref(p), int(device)))
-        self.nx, self.nz, self.device = int(nx), int(nz), int(device)
+        self.global_nx, self.nz, self.device = int(nx), int(nz), int(device)
+        if stripe is None:
+            check(lib.swe_create(C.byref(self._h), int(nx), int(nz), C.byref(p), int(device)))
+            self.row0, self.nx = 0, int(nx)
+        else:
+            lo, hi = int(stripe[0]), int(stripe[1])
+            check(lib.swe_stripe_create(C.byref(self._h), int(nx), int(nz), lo, hi, int(max_particles),
+                                        C.byref(p), int(device)))
+            self.row0, self.nx = lo, hi - lo
+        self.stripe = stripe
         self.map = _Map(self)
         self.SEED = 0
 

@@ -1,0 +1,67 @@
+"""CPU: host-side logic of the multi-GPU stripe decomposition -- partitioning, and the
+torch.distributed plumbing (IPC-blob all_gather) under gloo with world_size 2."""
+import os
+import socket
+
+import pytest
+
+from simplewinderosion_b200 import stripes
+
+
+def test_stripe_bounds_properties():
+    for nx, w in [(16384, 8), (4096, 4), (64, 2), (100, 3), (16, 2), (4096, 1), (70, 8), (1024, 7)]:
+        b = stripes.stripe_bounds(nx, w)
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == nx
+        for (lo, hi), (lo2, _) in zip(b, b[1:]):
+            assert hi == lo2
+        assert all(hi - lo >= stripes.MIN_ROWS for lo, hi in b)
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 12
+        for x in (0, nx // 3, nx - 1):
+            r = stripes.owner_of_row(b, x)
+            assert b[r][0] <= x < b[r][1]
+    assert stripes.stripe_bounds(16384, 8)[3] == (6144, 8192)
+    with pytest.raises(ValueError):
+        stripes.stripe_bounds(15, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = stripes.stripe_bounds(4096, world)
+        blob = bytes([rank + 1]) * stripes.STRIPE_IPC_BYTES
+        got = stripes.allgather_bytes(blob, world)
+        ok = all(g == bytes([r + 1]) * stripes.STRIPE_IPC_BYTES for r, g in enumerate(got))
+        # every rank derives the same partition and knows its neighbours
+        nbrs = [r for r in (rank - 1, rank + 1) if 0 <= r < world]
+        q.put((rank, ok, b, nbrs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ipc_blob_exchange_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] and res[1][1]
+    assert res[0][2] == res[1][2] == [(0, 2048), (2048, 4096)]
+    assert res[0][3] == [1] and res[1][3] == [0]
