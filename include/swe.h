@@ -212,7 +212,8 @@ int swe_sync(swe_engine* e);
  * rows of its neighbours; inside swe_erode / swe_cascade_sweep the neighbours exchange boundary
  * rows and hand over particles by kernels writing peer memory (NVLink P2P), synchronised by
  * flags -- no host round trip per exchange. Every rank must issue the same sequence of
- * swe_erode / swe_cascade_sweep / swe_stripe_sync_halos calls with the same arguments;
+ * swe_erode / swe_cascade_sweep / swe_stripe_sync_halos calls with the same arguments
+ * (swe_max_excess on a stripe wants a swe_stripe_sync_halos first: it reads one ghost row);
  * `cycles` of swe_erode is the GLOBAL particle count of the call. Host transfers
  * (swe_upload_plane, swe_download_plane, swe_sum_plane, ...) act on the owned rows only. Parallel mode only.
  *   1. swe_stripe_create on every rank (max_particles >= the largest global `cycles`; the same

@@ -111,6 +111,12 @@ struct swe_engine {
 
 // ---- stripe arena layout (identical on every rank, so a peer base pointer is enough) ----------
 namespace {
+// Ghost rows of a stripe. A row's value after one nine-colour pass depends on at most 4 rows below
+// and 6 rows above it (each of the three x-shifts of the colouring can pull in a whole 3-row block,
+// depending on the row's alignment mod 3); erode recomputes one extra row each side instead of
+// exchanging it, hence 1+4 below and 1+6 above. The rank above therefore receives my last GHOST_LO
+// owned rows, the rank below my first GHOST_HI owned rows.
+constexpr int GHOST_LO = 5, GHOST_HI = 7;
 constexpr size_t ARENA_FLAGS = 256;   // 4 flags, 64 B apart
 enum { FLAG_READY_FROM_BELOW = 0, FLAG_READY_FROM_ABOVE = 1, FLAG_CONSUMED_BY_BELOW = 2, FLAG_CONSUMED_BY_ABOVE = 3 };
 enum { FROM_BELOW = 0, FROM_ABOVE = 1 };
@@ -195,19 +201,19 @@ unsigned stripe_exchange_begin(swe_engine* e, bool with_stamps, int* launches) {
   const int nz = e->m.nz;
   launch_stripe_wait(S.has_below ? arena_flag(S.arena, FLAG_CONSUMED_BY_BELOW) : nullptr,
                      S.has_above ? arena_flag(S.arena, FLAG_CONSUMED_BY_ABOVE) : nullptr, s - 1, err, e->stream);
-  if (S.has_below) {   // my first 5 owned rows are the below neighbour's ghost rows above its stripe
+  if (S.has_below) {   // my first GHOST_HI owned rows are the below neighbour's ghost rows above its stripe
     const size_t src = (size_t)(S.own_lo - e->m.x0) * nz, dst = (size_t)(S.own_lo - S.below.x0) * nz;
     launch_stripe_push(e->m.height + src, static_cast<float*>(S.below.height) + dst,
                        with_stamps ? e->d_stamp + src : nullptr,
                        with_stamps ? static_cast<unsigned char*>(S.below.stamp) + dst : nullptr,
-                       (size_t)5 * nz, e->stream);
+                       (size_t)GHOST_HI * nz, e->stream);
   }
-  if (S.has_above) {   // my last 3 owned rows are the above neighbour's ghost rows below its stripe
-    const size_t src = (size_t)(S.own_hi - 3 - e->m.x0) * nz, dst = (size_t)(S.own_hi - 3 - S.above.x0) * nz;
+  if (S.has_above) {   // my last GHOST_LO owned rows are the above neighbour's ghost rows below its stripe
+    const size_t src = (size_t)(S.own_hi - GHOST_LO - e->m.x0) * nz, dst = (size_t)(S.own_hi - GHOST_LO - S.above.x0) * nz;
     launch_stripe_push(e->m.height + src, static_cast<float*>(S.above.height) + dst,
                        with_stamps ? e->d_stamp + src : nullptr,
                        with_stamps ? static_cast<unsigned char*>(S.above.stamp) + dst : nullptr,
-                       (size_t)3 * nz, e->stream);
+                       (size_t)GHOST_LO * nz, e->stream);
   }
   launch_stripe_signal(S.has_below ? arena_flag(S.below.arena, FLAG_READY_FROM_ABOVE) : nullptr,
                        S.has_above ? arena_flag(S.above.arena, FLAG_READY_FROM_BELOW) : nullptr, s, e->stream);
@@ -291,10 +297,10 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
   if (!e) return fail(SWE_ERR_OOM, "host allocation failed");
   e->device = device; e->p = p;
   e->m.nx = nx; e->m.nz = nz; e->m.x0 = 0; e->m.rows = nx;
-  if (stripe) {   // stored rows = owned + 3 ghost rows below + 5 above (clipped to the map)
+  if (stripe) {   // stored rows = owned + GHOST_LO rows below + GHOST_HI above (clipped to the map)
     e->st.enabled = true; e->st.own_lo = own_lo; e->st.own_hi = own_hi;
-    e->m.x0 = own_lo - 3 < 0 ? 0 : own_lo - 3;
-    const int hi = own_hi + 5 > nx ? nx : own_hi + 5;
+    e->m.x0 = own_lo - GHOST_LO < 0 ? 0 : own_lo - GHOST_LO;
+    const int hi = own_hi + GHOST_HI > nx ? nx : own_hi + GHOST_HI;
     e->m.rows = hi - e->m.x0;
     e->st.max_particles = max_particles;
     e->st.inbox_capacity = max_particles / 8 + 4096;
@@ -610,7 +616,8 @@ int swe_cascade(swe_engine* e, int x, int z) {
 int swe_max_excess(swe_engine* e, float* out) {
   if (int rc = bind(e)) return rc;
   if (!out) return fail(SWE_ERR_INVALID, "out is NULL");
-  // a stripe also checks the pairs between its last owned row and the ghost row above it
+  // a stripe also checks the pairs between its last owned row and the ghost row above it: call
+  // swe_stripe_sync_halos first so that ghost row is current
   launch_max_excess(e->owned(e->st.enabled && e->st.own_hi < e->m.nx ? 1 : 0), e->p, e->d_small, e->stream);
   if (int rc = check_launch(e, "max_excess", 2)) return rc;
   SWE_CUDA(cudaMemcpyAsync(out, e->d_small, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -627,7 +634,7 @@ int swe_cascade_sweep(swe_engine* e, int sweeps, float* max_excess_out) {
   int n = 0;
   if (e->st.enabled) {
     // one exchange of pre-sweep boundary rows per sweep; owned rows come out bitwise equal to the
-    // single-GPU sweep (2/4-row dependency cone inside the 3/5-row ghost zone)
+    // single-GPU sweep (4/6-row dependency cone inside the 5/7-row ghost zone)
     if (!e->st.connected) return fail(SWE_ERR_STATE, "swe_stripe_connect has not been called");
     for (int s = 0; s < sweeps; s++) {
       const unsigned q = stripe_exchange_begin(e, false, &n);

@@ -467,7 +467,7 @@ static void tile_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, con
 
 // rows [row_lo, row_hi) are (re)computed and stored; the tiles covering them are launched. On a
 // single GPU that is the whole map; a stripe computes its owned rows plus one ghost row each side
-// from a halo of 3 rows below / 5 above (the 2/4-row dependency cone of the nine colours).
+// from a halo of 5 rows below / 7 above (the <= 4/6-row dependency cone of the nine colours).
 static void launch_tile_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                               const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
                               int row_lo, int row_hi, cudaStream_t st) {

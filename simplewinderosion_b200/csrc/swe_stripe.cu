@@ -3,17 +3,17 @@
 // with no host involvement inside a World::erode call.
 //
 // Decomposition: rank r owns the global rows [own_lo, own_hi) and stores
-// [own_lo-3, own_hi+5) (clipped to the map). Per round of the parallel pipeline:
+// [own_lo-5, own_hi+7) (clipped to the map). Per round of the parallel pipeline:
 //   1. par_round_kernel<STRIPE>: steps the local particles (they only write their own, owned,
 //      centre cell); a particle whose next cell belongs to a neighbour is stored straight into
 //      that neighbour's inbox (peer stores + one system-scope atomic for the slot).
 //   2. wait until the neighbours have finished READING the ghosts of the previous round
 //      (consumed flags), then push the post-deposit boundary rows (heights + stamps) into their
-//      ghost rows: my first 5 owned rows go below, my last 3 owned rows go above.
+//      ghost rows: my first 7 owned rows go below, my last 5 owned rows go above.
 //   3. signal "round r delivered" (ready flags), wait for the neighbours' ready flags.
 //   4. merge the inbox into the local particle arrays.
-//   5. stamped cascade on rows [own_lo-1, own_hi+1): with the 3/5-row halo the nine-colour
-//      dependency cone (2 rows low, 4 high) is complete, so these rows come out bitwise equal to
+//   5. stamped cascade on rows [own_lo-1, own_hi+1): with the 5/7-row halo the nine-colour
+//      dependency cone (up to 4 rows low, 6 high, depending on alignment) is complete, so these rows come out bitwise equal to
 //      what the neighbour computes for them -- no second exchange for the next round's reads.
 //   6. signal "ghosts of round r consumed".
 // Flags are monotonically increasing sequence numbers written with system-scope release stores

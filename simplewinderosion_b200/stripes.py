@@ -137,6 +137,22 @@ class StripedWorld(_world.World):
     def sync_halos(self) -> None:
         check(lib.swe_stripe_sync_halos(self._h))
 
+    def max_excess(self) -> float:
+        """Collective (one process per GPU): refresh the ghost rows, then the local maximum over
+        the owned rows and the pairs into the ghost row above. Reduce with MAX over ranks."""
+        self.sync_halos()
+        return super().max_excess()
+
+    def max_excess_local(self) -> float:
+        return super().max_excess()
+
+
+def max_excess_in_process(worlds: list[StripedWorld]) -> float:
+    """In-process stripes: enqueue the halo refresh on every stripe first (blocking reads from one
+    host thread would keep the others from enqueueing their half of the exchange)."""
+    run_on_all(worlds, lambda w: w.sync_halos())
+    return max(w.max_excess_local() for w in worlds)
+
 
 def gather_global(worlds: list[StripedWorld], plane: int = _world.HEIGHT) -> np.ndarray:
     """In-process helper: stitch the owned rows of all stripes back into one (nx, nz) plane."""

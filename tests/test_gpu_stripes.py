@@ -48,7 +48,7 @@ def test_striped_cascade_sweep_bitwise(nx, nz, world):
         ora.cascade_sweep(1)
         got = stripes.gather_global(ws)
         assert np.array_equal(bits(got), bits(ora.plane(0))), np.argwhere(bits(got) != bits(ora.plane(0)))[:4]
-    ex = max(stripes.run_on_all(ws, lambda w: w.max_excess()))
+    ex = stripes.max_excess_in_process(ws)
     assert np.float32(ex).view(np.uint32) == np.float32(ora.max_excess()).view(np.uint32)
     for w in ws:
         assert w.stats().stripe_overflow == 0
@@ -63,10 +63,14 @@ def test_striped_erode_accounts_for_every_particle(n, world, cycles):
     single = swe.World(n)
     single.upload(hm)
     single.srand(7)
+    other = swe.World(n)          # same engine, another seed: how much two runs differ anyway
+    other.upload(hm)
+    other.srand(8)
     s0 = float(hm.astype(np.float64).sum())
     for _ in range(2):
         stripes.run_on_all(ws, lambda w: w.erode(cycles, swe.MODE_PARALLEL))
         single.erode(cycles, swe.MODE_PARALLEL)
+        other.erode(cycles, swe.MODE_PARALLEL)
     sts = [w.stats() for w in ws]
     assert sum(s.stripe_overflow for s in sts) == 0
     assert sum(s.particles for s in sts) == 2 * cycles
@@ -79,7 +83,8 @@ def test_striped_erode_accounts_for_every_particle(n, world, cycles):
     assert abs(total + lost - s0) < 2e-6 * abs(s0) + 1e-4
     got, ref = stripes.gather_global(ws), single.download()
     assert np.isfinite(got).all()
-    assert np.corrcoef((got - hm).ravel(), (ref - hm).ravel())[0, 1] > 0.98
+    baseline = np.corrcoef((other.download() - hm).ravel(), (ref - hm).ravel())[0, 1]
+    assert np.corrcoef((got - hm).ravel(), (ref - hm).ravel())[0, 1] > baseline - 0.03, baseline
     assert abs(lost / ss.sediment_lost - 1.0) < 0.03
     # flow fields exist on every stripe and look like the single-engine ones
     f = stripes.gather_global(ws, swe.MOMENTUMX)
