@@ -238,6 +238,14 @@ int swe_stripe_open_ipc(swe_engine* e, const void* buf, size_t buf_bytes, swe_st
 int swe_stripe_connect(swe_engine* e, const swe_stripe_link* below, const swe_stripe_link* above);
 int swe_stripe_sync_halos(swe_engine* e);
 int swe_stripe_rows(const swe_engine* e, int* own_lo, int* own_hi);
+/* One host thread driving several stripes (logical stripes on one GPU, or a process that owns
+ * several GPUs): same effect as calling swe_erode(e, cycles, SWE_MODE_PARALLEL) /
+ * swe_cascade_sweep(e, sweeps, NULL) / swe_stripe_sync_halos(e) on every engine, with the
+ * launches interleaved exchange by exchange so no stripe's wait kernels run ahead of the
+ * neighbour launches they wait for. `engines` lists the stripes in row order. */
+int swe_stripe_group_erode(swe_engine** engines, int n, int cycles);
+int swe_stripe_group_sweep(swe_engine** engines, int n, int sweeps);
+int swe_stripe_group_sync_halos(swe_engine** engines, int n);
 
 /* ---- device-side plumbing (for a host that already lives on the GPU) ---------------- */
 /* Stream the engine launches on (a cudaStream_t); 0 = the engine's own stream. */

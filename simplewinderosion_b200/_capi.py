@@ -96,6 +96,9 @@ PROTOTYPES = {
     "swe_stripe_connect": (C.c_int, [_E, C.POINTER(StripeLink), C.POINTER(StripeLink)]),
     "swe_stripe_sync_halos": (C.c_int, [_E]),
     "swe_stripe_rows": (C.c_int, [_E, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "swe_stripe_group_erode": (C.c_int, [C.POINTER(_E), C.c_int, C.c_int]),
+    "swe_stripe_group_sweep": (C.c_int, [C.POINTER(_E), C.c_int, C.c_int]),
+    "swe_stripe_group_sync_halos": (C.c_int, [C.POINTER(_E), C.c_int]),
     "swe_srand": (C.c_int, [_E, C.c_uint32]),
     "swe_upload_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_download_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),

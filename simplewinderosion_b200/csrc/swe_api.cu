@@ -230,6 +230,82 @@ void stripe_exchange_end(swe_engine* e, unsigned s, int* launches) {
   *launches += 1;
 }
 
+void finish_timers(swe_engine* e);
+
+// ---- striped parallel erode, in phases so that a single host thread can interleave several
+// in-process stripes round by round (swe_stripe_group_erode) --------------------------------------
+int stripe_erode_check(swe_engine* e, int cycles, int mode) {
+  if (mode != SWE_MODE_PARALLEL) return fail(SWE_ERR_STATE, "a stripe engine runs parallel mode only");
+  if (!e->st.connected) return fail(SWE_ERR_STATE, "swe_stripe_connect has not been called");
+  if (cycles > e->st.max_particles)
+    return fail(SWE_ERR_INVALID, "cycles %d exceeds the stripe's max_particles %d", cycles, e->st.max_particles);
+  return SWE_OK;
+}
+
+StripeRound stripe_round_ctx(swe_engine* e) {
+  auto& S = e->st;
+  StripeRound sr{};
+  sr.own_lo = S.own_lo; sr.own_hi = S.own_hi;
+  sr.pid = S.d_pid; sr.n_used = S.d_vars + 0; sr.overflow = S.d_vars + 1;
+  return sr;
+}
+
+int stripe_erode_begin(swe_engine* e, int cycles) {
+  launch_par_begin_stripe(e->pbuf, stripe_round_ctx(e), e->m, cycles, e->seed, e->call_index, e->d_stats,
+                          e->stream);
+  return check_launch(e, "stripe begin", 3);
+}
+
+int stripe_erode_round(swe_engine* e) {
+  auto& S = e->st;
+  int nl = 0;
+  if (++e->stamp_counter > 255u) {
+    SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
+    e->stamp_counter = 1;
+  }
+  const unsigned char now = (unsigned char)e->stamp_counter;
+  const int parity = (int)((S.seq + 1) & 1u);
+  StripeRound sr = stripe_round_ctx(e);
+  if (S.has_below) sr.below = arena_inbox(S.below.arena, S.inbox_capacity, FROM_ABOVE, parity);
+  if (S.has_above) sr.above = arena_inbox(S.above.arena, S.inbox_capacity, FROM_BELOW, parity);
+  // particles must be handed over before they step again: one step per round
+  launch_par_round_stripe(e->pbuf, sr, e->m, e->p, 1, e->seed, e->call_index, e->d_stamp, now, e->d_stats,
+                          e->stream);
+  nl += 1;
+  const unsigned s = stripe_exchange_begin(e, true, &nl);
+  for (int dir = 0; dir < 2; dir++) {
+    if ((dir == FROM_BELOW && !S.has_below) || (dir == FROM_ABOVE && !S.has_above)) continue;
+    const StripeOutbox in = arena_inbox(S.arena, S.inbox_capacity, dir, parity);
+    launch_stripe_merge(in.a, in.b, in.pid, in.count, in.capacity, e->pbuf.a, e->pbuf.b, S.d_pid,
+                        S.d_vars + 0, e->pbuf.capacity, S.d_vars + 1, S.d_vars + 3, e->stream);
+    nl += 3;
+  }
+  // rows own_lo-1 .. own_hi: the ghost row each side is recomputed here instead of exchanged
+  launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, nullptr, S.own_lo - 1, S.own_hi + 1, e->stream);
+  nl += 1;
+  stripe_exchange_end(e, s, &nl);
+  return check_launch(e, "stripe round", nl);
+}
+
+int erode_prologue(swe_engine* e) {
+  finish_timers(e);
+  SWE_CUDA(cudaEventRecord(e->ev_a, e->stream));
+  SWE_CUDA(cudaMemsetAsync(e->m.track, 0, e->cells() * sizeof(float4), e->stream));   // world.hpp:38-44
+  SWE_CUDA(cudaEventRecord(e->ev_f0, e->stream));
+  return SWE_OK;
+}
+
+int erode_epilogue(swe_engine* e) {
+  SWE_CUDA(cudaEventRecord(e->ev_f1, e->stream));
+  launch_ema(e->m, e->p.lrate, e->stream);                                              // world.hpp:70-76
+  if (int rc = check_launch(e, "ema")) return rc;
+  SWE_CUDA(cudaEventRecord(e->ev_b, e->stream));
+  e->erode_timed = true;
+  e->call_index++;
+  e->erode_calls++;
+  return SWE_OK;
+}
+
 void finish_timers(swe_engine* e) {
   float ms = 0.0f;
   if (e->erode_timed && cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->last_erode_ms = ms;
@@ -337,6 +413,8 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
     e->pbuf.capacity = max_particles; e->pbuf.live = nullptr; e->pbuf.live_slots = 0;
   }
   make_height_tensor_map(e->m, &e->tmap);   // optional: plain-load kernels are used when it fails
+  preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe();
+  (void)cudaGetLastError();
   launch_det_srand(e->d_rng, 1u, e->stream);
   TRY(cudaGetLastError());
   e->launches++;
@@ -513,55 +591,17 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
   if (cycles < 0) return fail(SWE_ERR_INVALID, "cycles < 0");
   if (mode != SWE_MODE_DETERMINISTIC && mode != SWE_MODE_PARALLEL)
     return fail(SWE_ERR_INVALID, "unknown mode %d", mode);
-  finish_timers(e);
-  SWE_CUDA(cudaEventRecord(e->ev_a, e->stream));
+  if (e->st.enabled)
+    if (int rc = stripe_erode_check(e, cycles, mode)) return rc;
   // world.hpp:38-44: reset the four track members of every cell
-  SWE_CUDA(cudaMemsetAsync(e->m.track, 0, e->cells() * sizeof(float4), e->stream));
+  if (int rc = erode_prologue(e)) return rc;
   // world.hpp:47-66: the particles
-  SWE_CUDA(cudaEventRecord(e->ev_f0, e->stream));
   if (e->st.enabled) {
-    if (mode != SWE_MODE_PARALLEL) return fail(SWE_ERR_STATE, "a stripe engine runs parallel mode only");
-    if (!e->st.connected) return fail(SWE_ERR_STATE, "swe_stripe_connect has not been called");
-    if (cycles > e->st.max_particles)
-      return fail(SWE_ERR_INVALID, "cycles %d exceeds the stripe's max_particles %d", cycles, e->st.max_particles);
-    auto& S = e->st;
-    const int k = 1;   // particles must be handed over before they step again
-    const int rounds = e->p.max_age + 2;
-    int nl = 0;
     if (cycles > 0) {
-      StripeRound sr{};
-      sr.own_lo = S.own_lo; sr.own_hi = S.own_hi;
-      sr.pid = S.d_pid; sr.n_used = S.d_vars + 0; sr.overflow = S.d_vars + 1;
-      launch_par_begin_stripe(e->pbuf, sr, e->m, cycles, e->seed, e->call_index, e->d_stats, e->stream);
-      nl += 3;
-      for (int r = 0; r < rounds; r++) {
-        if (++e->stamp_counter > 255u) {
-          SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
-          e->stamp_counter = 1;
-        }
-        const unsigned char now = (unsigned char)e->stamp_counter;
-        const int parity = (int)((S.seq + 1) & 1u);
-        if (S.has_below) sr.below = arena_inbox(S.below.arena, S.inbox_capacity, FROM_ABOVE, parity);
-        if (S.has_above) sr.above = arena_inbox(S.above.arena, S.inbox_capacity, FROM_BELOW, parity);
-        launch_par_round_stripe(e->pbuf, sr, e->m, e->p, k, e->seed, e->call_index, e->d_stamp, now,
-                                e->d_stats, e->stream);
-        nl += 1;
-        const unsigned s = stripe_exchange_begin(e, true, &nl);
-        for (int dir = 0; dir < 2; dir++) {
-          if ((dir == FROM_BELOW && !S.has_below) || (dir == FROM_ABOVE && !S.has_above)) continue;
-          const StripeOutbox in = arena_inbox(S.arena, S.inbox_capacity, dir, parity);
-          launch_stripe_merge(in.a, in.b, in.pid, in.count, in.capacity, e->pbuf.a, e->pbuf.b, S.d_pid,
-                              S.d_vars + 0, e->pbuf.capacity, S.d_vars + 1, S.d_vars + 3, e->stream);
-          nl += 3;
-        }
-        // rows own_lo-1 .. own_hi: the ghost row each side is recomputed here instead of exchanged
-        launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, nullptr, S.own_lo - 1, S.own_hi + 1,
-                               e->stream);
-        nl += 1;
-        stripe_exchange_end(e, s, &nl);
-      }
+      if (int rc = stripe_erode_begin(e, cycles)) return rc;
+      for (int r = 0; r < e->p.max_age + 2; r++)
+        if (int rc = stripe_erode_round(e)) return rc;
     }
-    if (int rc = check_launch(e, "stripe erode", nl)) return rc;
   } else if (mode == SWE_MODE_DETERMINISTIC) {
     launch_det_erode(e->m, e->p, cycles, e->d_rng, e->d_stats, e->stream);
     if (int rc = check_launch(e, "det_erode")) return rc;
@@ -594,14 +634,65 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
       if (int rc = check_launch(e, "par_round", 2)) return rc;
     }
   }
-  SWE_CUDA(cudaEventRecord(e->ev_f1, e->stream));
   // world.hpp:70-76: EMA of the flow fields
-  launch_ema(e->m, e->p.lrate, e->stream);
-  if (int rc = check_launch(e, "ema")) return rc;
-  SWE_CUDA(cudaEventRecord(e->ev_b, e->stream));
-  e->erode_timed = true;
-  e->call_index++;
-  e->erode_calls++;
+  return erode_epilogue(e);
+}
+
+// Several stripes driven by ONE host thread (logical stripes on one GPU, or one process owning
+// several GPUs): the launches are interleaved round by round, so a stripe's wait kernels never
+// queue up ahead of the neighbour launches that satisfy them.
+int swe_stripe_group_erode(swe_engine** engines, int n, int cycles) {
+  if (!engines || n < 1) return fail(SWE_ERR_INVALID, "no engines");
+  if (cycles < 0) return fail(SWE_ERR_INVALID, "cycles < 0");
+  for (int i = 0; i < n; i++) {
+    if (int rc = bind(engines[i])) return rc;
+    if (!engines[i]->st.enabled) return fail(SWE_ERR_STATE, "engine %d is not a stripe engine", i);
+    if (int rc = stripe_erode_check(engines[i], cycles, SWE_MODE_PARALLEL)) return rc;
+    if (engines[i]->p.max_age != engines[0]->p.max_age) return fail(SWE_ERR_INVALID, "stripes disagree on max_age");
+  }
+  for (int i = 0; i < n; i++) {
+    if (int rc = bind(engines[i])) return rc;
+    if (int rc = erode_prologue(engines[i])) return rc;
+    if (cycles > 0)
+      if (int rc = stripe_erode_begin(engines[i], cycles)) return rc;
+  }
+  if (cycles > 0)
+    for (int r = 0; r < engines[0]->p.max_age + 2; r++)
+      for (int i = 0; i < n; i++) {
+        if (int rc = bind(engines[i])) return rc;
+        if (int rc = stripe_erode_round(engines[i])) return rc;
+      }
+  for (int i = 0; i < n; i++) {
+    if (int rc = bind(engines[i])) return rc;
+    if (int rc = erode_epilogue(engines[i])) return rc;
+  }
+  return SWE_OK;
+}
+
+int swe_stripe_group_sweep(swe_engine** engines, int n, int sweeps) {
+  if (!engines || n < 1) return fail(SWE_ERR_INVALID, "no engines");
+  if (sweeps < 0) return fail(SWE_ERR_INVALID, "sweeps < 0");
+  for (int i = 0; i < n; i++)
+    if (!engines[i] || !engines[i]->st.enabled || !engines[i]->st.connected)
+      return fail(SWE_ERR_STATE, "engine %d is not a connected stripe engine", i);
+  for (int s = 0; s < sweeps; s++)
+    for (int i = 0; i < n; i++) {
+      swe_engine* e = engines[i];
+      if (int rc = bind(e)) return rc;
+      int nl = 0;
+      const unsigned q = stripe_exchange_begin(e, false, &nl);
+      launch_cascade_stamped(e->m, e->p, &e->tmap, nullptr, 0, nullptr, e->st.own_lo, e->st.own_hi, e->stream);
+      nl += 1;
+      stripe_exchange_end(e, q, &nl);
+      if (int rc = check_launch(e, "stripe sweep", nl)) return rc;
+    }
+  return SWE_OK;
+}
+
+int swe_stripe_group_sync_halos(swe_engine** engines, int n) {
+  if (!engines || n < 1) return fail(SWE_ERR_INVALID, "no engines");
+  for (int i = 0; i < n; i++)
+    if (int rc = swe_stripe_sync_halos(engines[i])) return rc;
   return SWE_OK;
 }
 

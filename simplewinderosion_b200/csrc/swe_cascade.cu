@@ -541,4 +541,18 @@ void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cuda
   max_excess_kernel<<<blocks, 256, 0, st>>>(m, p, d_out);
 }
 
+// Force-load this translation unit's kernels (CUDA loads modules lazily on first launch, and a
+// first launch issued while another stream spins in a stripe wait kernel would stall behind it).
+void preload_cascade() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, cascade_colour_kernel);
+  cudaFuncGetAttributes(&a, cascade_tile_kernel<false, false>);
+  cudaFuncGetAttributes(&a, cascade_tile_kernel<false, true>);
+  cudaFuncGetAttributes(&a, cascade_tile_kernel<true, false>);
+  cudaFuncGetAttributes(&a, cascade_tile_kernel<true, true>);
+  cudaFuncGetAttributes(&a, max_excess_kernel);
+  cudaFuncGetAttributes(&a, set_float_kernel);
+  cudaFuncGetAttributes(&a, add_cascade_cells_kernel);
+}
+
 }  // namespace swe

@@ -146,4 +146,10 @@ void launch_cells_to_planes(const MapView& m, const float* d_cells, cudaStream_t
 void launch_planes_to_cells(const MapView& m, float* d_cells, cudaStream_t st);
 void launch_sum_plane(const MapView& m, int plane, double* d_out, cudaStream_t st);
 
+void preload_det();
+void preload_cascade();
+void preload_fields();
+void preload_par();
+void preload_stripe();
+
 }  // namespace swe

@@ -253,4 +253,17 @@ void launch_normal_one(const MapView& m, const swe_params& p, int x, int z, floa
   normal_one_kernel<<<1, 32, 0, st>>>(m, p, x, z, d_out3);
 }
 
+// Force-load this translation unit's kernels (CUDA loads modules lazily on first launch, and a
+// first launch issued while another stream spins in a stripe wait kernel would stall behind it).
+void preload_det() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, det_srand_kernel);
+  cudaFuncGetAttributes(&a, det_erode_kernel);
+  cudaFuncGetAttributes(&a, det_trace_kernel);
+  cudaFuncGetAttributes(&a, det_fly_once_kernel);
+  cudaFuncGetAttributes(&a, det_cascade_one_kernel);
+  cudaFuncGetAttributes(&a, normals_kernel);
+  cudaFuncGetAttributes(&a, normal_one_kernel);
+}
+
 }  // namespace swe

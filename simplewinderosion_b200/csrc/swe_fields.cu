@@ -115,4 +115,16 @@ void launch_sum_plane(const MapView& m, int plane, double* d_out, cudaStream_t s
   sum_plane_kernel<<<grid_for((size_t)m.rows * m.nz, 256, 4), 256, 0, st>>>(m, plane, d_out);
 }
 
+// Force-load this translation unit's kernels (CUDA loads modules lazily on first launch, and a
+// first launch issued while another stream spins in a stripe wait kernel would stall behind it).
+void preload_fields() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, ema_kernel);
+  cudaFuncGetAttributes(&a, pack_plane_kernel);
+  cudaFuncGetAttributes(&a, unpack_plane_kernel);
+  cudaFuncGetAttributes(&a, cells_to_planes_kernel);
+  cudaFuncGetAttributes(&a, planes_to_cells_kernel);
+  cudaFuncGetAttributes(&a, sum_plane_kernel);
+}
+
 }  // namespace swe

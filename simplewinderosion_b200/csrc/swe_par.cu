@@ -376,4 +376,17 @@ void launch_par_round_stripe(const ParticleBuf& buf, const StripeRound& sr, cons
       nullptr, stats, sr);
 }
 
+// Force-load this translation unit's kernels (CUDA loads modules lazily on first launch, and a
+// first launch issued while another stream spins in a stripe wait kernel would stall behind it).
+void preload_par() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, par_spawn_kernel);
+  cudaFuncGetAttributes(&a, par_spawn_stripe_kernel);
+  cudaFuncGetAttributes(&a, par_round_kernel<false>);
+  cudaFuncGetAttributes(&a, par_round_kernel<true>);
+  cudaFuncGetAttributes(&a, par_begin_kernel);
+  cudaFuncGetAttributes(&a, stripe_begin_kernel);
+  cudaFuncGetAttributes(&a, stripe_count_spawned_kernel);
+}
+
 }  // namespace swe

@@ -115,4 +115,16 @@ void launch_stripe_merge(const float4* in_a, const float4* in_b, const uint32_t*
   stripe_merge_finish_kernel<<<1, 1, 0, st>>>(in_count, in_capacity, n_used, capacity);
 }
 
+// Force-load this translation unit's kernels (CUDA loads modules lazily on first launch, and a
+// first launch issued while another stream spins in a stripe wait kernel would stall behind it).
+void preload_stripe() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, stripe_push_rows_kernel);
+  cudaFuncGetAttributes(&a, stripe_signal_kernel);
+  cudaFuncGetAttributes(&a, stripe_wait_kernel);
+  cudaFuncGetAttributes(&a, stripe_merge_kernel);
+  cudaFuncGetAttributes(&a, stripe_merge_prepare_kernel);
+  cudaFuncGetAttributes(&a, stripe_merge_finish_kernel);
+}
+
 }  // namespace swe

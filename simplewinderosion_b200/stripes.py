@@ -61,27 +61,32 @@ def allgather_bytes(blob: bytes, world_size: int, group=None, device=None) -> li
     return [bytes(g.cpu().tolist()) for g in gathered]
 
 
-def run_on_all(worlds: list, fn) -> list:
-    """In-process stripes: issue `fn(world)` for every stripe from its own host thread. The calls
-    enqueue thousands of launches whose wait kernels need the OTHER stripes' kernels to be enqueued
-    too, so a single thread would fill one stream's launch queue and stall."""
-    import threading
-    out, err = [None] * len(worlds), [None] * len(worlds)
+class StripeGroup:
+    """Several stripes of one map driven from THIS host thread (logical stripes on one GPU, or a
+    process owning several GPUs). The C library interleaves the launches exchange by exchange."""
 
-    def work(i):
-        try:
-            out[i] = fn(worlds[i])
-        except BaseException as e:   # noqa: BLE001
-            err[i] = e
-    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(worlds))]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    for e in err:
-        if e is not None:
-            raise e
-    return out
+    def __init__(self, worlds: list):
+        self.worlds = list(worlds)
+        self._arr = (C.c_void_p * len(worlds))(*[w._h for w in worlds])
+
+    def sync_halos(self) -> None:
+        check(lib.swe_stripe_group_sync_halos(self._arr, len(self.worlds)))
+
+    def erode(self, cycles: int) -> None:
+        check(lib.swe_stripe_group_erode(self._arr, len(self.worlds), int(cycles)))
+
+    def cascade_sweep(self, sweeps: int = 1) -> None:
+        check(lib.swe_stripe_group_sweep(self._arr, len(self.worlds), int(sweeps)))
+
+    def max_excess(self) -> float:
+        self.sync_halos()
+        return max(w.max_excess_local() for w in self.worlds)
+
+    def gather(self, plane: int = _world.HEIGHT) -> np.ndarray:
+        return np.concatenate([w.download(plane) for w in self.worlds], axis=0)
+
+    def stats(self):
+        return [w.stats() for w in self.worlds]
 
 
 class StripedWorld(_world.World):
@@ -145,13 +150,6 @@ class StripedWorld(_world.World):
 
     def max_excess_local(self) -> float:
         return super().max_excess()
-
-
-def max_excess_in_process(worlds: list[StripedWorld]) -> float:
-    """In-process stripes: enqueue the halo refresh on every stripe first (blocking reads from one
-    host thread would keep the others from enqueueing their half of the exchange)."""
-    run_on_all(worlds, lambda w: w.sync_halos())
-    return max(w.max_excess_local() for w in worlds)
 
 
 def gather_global(worlds: list[StripedWorld], plane: int = _world.HEIGHT) -> np.ndarray:

@@ -4,6 +4,12 @@ import sys
 
 import pytest
 
+# In-process logical stripes (tests/test_gpu_stripes.py) run several engines' streams with
+# cross-stream spin-wait kernels on ONE GPU: give every stream its own hardware queue so a waiting
+# kernel can never sit in front of the kernel it waits for (must be set before CUDA initialises;
+# irrelevant for the real one-process-per-GPU layout).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
