@@ -308,15 +308,27 @@ def run_ours(args) -> None:
     n, particles = args.size, args.particles
     hm = make_map(n)
 
-    w = swe.World(n, device=local)
+    if world == 1:
+        w = swe.World(n, device=local)
+    else:
+        # weak scaling: every GPU owns one n x n stripe of an (n*world) x n map (copies of the
+        # single-GPU map stacked along the wind axis) and the call flies particles*world particles.
+        # Neighbours exchange ghost rows and hand over particles by P2P kernels (no NCCL on the
+        # data path; torch.distributed only ships the CUDA IPC handles).
+        from simplewinderosion_b200 import stripes
+        w = stripes.StripedWorld(n * world, n, rank, world, particles * world, device=local)
+        w.connect()
     stream = torch.cuda.Stream()
     w.set_stream(stream.cuda_stream)
     w.upload(hm)
-    w.srand(1 + rank)
+    if world > 1:
+        w.sync_halos()
+    w.srand(1)
+    particles_call = particles * world     # GLOBAL particle count of one World::erode call
 
     # ---- device-resident timing ---------------------------------------------------------------
     for _ in range(args.warmup):
-        w.erode(particles, swe.MODE_PARALLEL)
+        w.erode(particles_call, swe.MODE_PARALLEL)
     w.sync()
     st0 = w.stats()
     sampler = ClockSampler(local)
@@ -328,7 +340,7 @@ def run_ours(args) -> None:
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(args.steps):
-            w.erode(particles, swe.MODE_PARALLEL)
+            w.erode(particles_call, swe.MODE_PARALLEL)
         ev1.record(stream)
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
@@ -337,6 +349,8 @@ def run_ours(args) -> None:
     steps_done = st1.steps - st0.steps
     launches = st1.kernel_launches - st0.kernel_launches
     total_steps = sum_over_ranks(float(steps_done))
+    total_particles = sum_over_ranks(float(st1.particles - st0.particles))
+    overflow_total = sum_over_ranks(float(st1.stripe_overflow))
     value = total_steps / (dev_ms * 1e-3)
 
     # per-kernel times (CUDA events on the launch stream around every round / cascade launch):
@@ -346,12 +360,14 @@ def run_ours(args) -> None:
     fly_steps = 0
     for _ in range(args.steps):
         s_before = w.stats().steps
-        w.erode(particles, swe.MODE_PARALLEL)
+        w.erode(particles_call, swe.MODE_PARALLEL)
         s = w.stats()
         round_ms += s.last_round_ms; casc_ms += s.last_cascade_ms; fly_ms += s.last_erode_ms
         fly_steps += s.steps - s_before
     w.set_option(swe.OPT_KERNEL_TIMING, 0)
     rounds_per_call = w.params.max_age + 2
+    if round_ms <= 0.0:          # stripe engines do not break the step down per kernel
+        round_ms = casc_ms = fly_ms / 2
     achieved = BYTES_PER_STEP * fly_steps / (round_ms * 1e-3) / 1e9
     pipeline = BYTES_PER_STEP * fly_steps / ((round_ms + casc_ms) * 1e-3) / 1e9
 
@@ -370,7 +386,9 @@ def run_ours(args) -> None:
 
     def e2e_step():
         w.upload(h_in)
-        w.erode(particles, swe.MODE_PARALLEL)
+        if world > 1:
+            w.sync_halos()
+        w.erode(particles_call, swe.MODE_PARALLEL)
         for i, pl in enumerate(planes):
             w.download(pl, out=h_out[i])
         h_in[...] = h_out[0]          # the host owns the canonical map between calls
@@ -402,10 +420,13 @@ def run_ours(args) -> None:
         "config": {
             "workload": WORKLOAD if (n == N_MAP and particles == PARTICLES) else
             f"{n}x{n} FBm dune field, {particles} particles per World::erode, parallel mode",
-            "map": [n, n], "particles_per_step": particles,
-            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one map per GPU)",
+            "map": [n * world, n], "particles_per_step": particles_call,
+            "parallelism": "single GPU" if world == 1 else
+            f"{world} row stripes of a {n * world}x{n} map (one {n}x{n} stripe and ~{particles} particles per GPU), "
+            f"P2P halo push + particle hand-off kernels over NVLink",
+            "stripe_overflow": int(overflow_total),
             "l2": "working set 720 MiB (height 64 + track 256 + field 256 + particles 128 + stamps 16) > 126 MB L2; no flush needed",
-            "steps_per_particle": steps_done / max(1, (st1.particles - st0.particles)),
+            "steps_per_particle": total_steps / max(1.0, total_particles),
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * n * n),
@@ -423,7 +444,7 @@ def run_ours(args) -> None:
                      "note": "104 B/step is SURVEY 8(d)'s figure for flight+cascade; `achieved` charges it "
                              "to the particle kernel alone, `pipeline_*` to particle + per-round cascade kernels"},
     }
-    if not args.skip_cascade:
+    if not args.skip_cascade and world == 1:
         line["cascade_roofline"] = cascade_roofline(swe, local, peak, peak_src, args.quick)
     if world == 1 and not args.skip_cpu:
         path = save_map_tmp(hm)

@@ -405,12 +405,24 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
     TRY(cudaMemsetAsync(e->d_stamp, 0, n, e->stream));
     TRY(cudaMalloc(&e->st.arena, e->st.arena_bytes));
     TRY(cudaMemsetAsync(e->st.arena, 0, e->st.arena_bytes, e->stream));
-    TRY(cudaMalloc(&e->st.d_pid, (size_t)max_particles * sizeof(uint32_t)));
+    {
+      // local particle slots: hand-offs append (no slot reuse within a call), so thin stripes,
+      // which every particle crosses many times, get the full budget; tall stripes twice their
+      // share of the call plus slack. swe_stats.stripe_overflow reports any shortfall.
+      const int own_rows = own_hi - own_lo;
+      long long cap = max_particles;
+      if (own_rows >= 512) {
+        cap = 2LL * (long long)((double)max_particles * own_rows / nx) + 262144;
+        if (cap > max_particles) cap = max_particles;
+      }
+      e->pbuf.capacity = (int)cap;
+    }
+    TRY(cudaMalloc(&e->st.d_pid, (size_t)e->pbuf.capacity * sizeof(uint32_t)));
     TRY(cudaMalloc(&e->st.d_vars, 64));
     TRY(cudaMemsetAsync(e->st.d_vars, 0, 64, e->stream));
-    TRY(cudaMalloc(&e->pbuf.a, (size_t)max_particles * sizeof(float4)));
-    TRY(cudaMalloc(&e->pbuf.b, (size_t)max_particles * sizeof(float4)));
-    e->pbuf.capacity = max_particles; e->pbuf.live = nullptr; e->pbuf.live_slots = 0;
+    TRY(cudaMalloc(&e->pbuf.a, (size_t)e->pbuf.capacity * sizeof(float4)));
+    TRY(cudaMalloc(&e->pbuf.b, (size_t)e->pbuf.capacity * sizeof(float4)));
+    e->pbuf.live = nullptr; e->pbuf.live_slots = 0;
   }
   make_height_tensor_map(e->m, &e->tmap);   // optional: plain-load kernels are used when it fails
   preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe();
