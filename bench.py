@@ -46,6 +46,16 @@ WORKLOAD = ("cfg3-pinned: 4096x4096 FBm dune field (seed 1), 4194304 particles p
             "parallel mode, single height layer (rock/abrasion extension off)")
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set
+    full capture (profiles/traffic.json, written by tools/make_profiles.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)["bytes_per_launch"].get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peak_gbs() -> tuple[float, str]:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -262,7 +272,8 @@ def cascade_roofline(swe, device: int, peak: float, peak_src: str, quick: bool) 
     achieved = bytes_per_sweep * sweeps / (total_ms * 1e-3) / 1e9
     return {"bound": "hbm", "workload": f"cfg5: {n}x{n} U(0,1) random-slope map relaxed until max excess < 1e-4",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": peak_src, "traffic": None, "sweeps": sweeps, "final_max_excess": ex,
+            "peak_source": peak_src, "traffic": ncu_traffic("cascade_sweep8192"), "sweeps": sweeps,
+            "final_max_excess": ex,
             "ms_per_sweep_mean": total_ms / sweeps, "ms_first_sweep": first[0],
             "ms_per_sweep_relaxed": relaxed_ms,
             "frac_relaxed": bytes_per_sweep / (relaxed_ms * 1e-3) / 1e9 / peak}
@@ -434,7 +445,7 @@ def run_ours(args) -> None:
                 "result_check_mean_height": mean_h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "par_round_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("par_round"),
                      "peak_source": peak_src, "algorithmic_bytes_per_step": BYTES_PER_STEP,
                      "launches_per_step": rounds_per_call,
                      "kernel_ms_per_launch": round_ms / args.steps / rounds_per_call,

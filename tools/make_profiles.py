@@ -1,0 +1,45 @@
+"""Turn the scratch ncu outputs in gpurun_out/ into the committed summaries under profiles/."""
+import csv, json, os, subprocess, sys
+from collections import defaultdict
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+
+def launches(path, out):
+    rows = list(csv.reader(open(path)))
+    h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    d = defaultdict(list)
+    for r in rows[h + 1:]:
+        d[r[4].split("(")[0].replace("void ", "")].append(float(r[-1]))
+    tot = sum(sum(v) for v in d.values())
+    with open(out, "w") as f:
+        f.write(f"# ncu launch list summary ({os.path.basename(path)}): `ncu --metrics gpu__time_duration.sum --clock-control none` "
+                f"over `python bench.py --steps 1 --warmup 3 --skip-cpu --skip-cascade` (first {sum(len(v) for v in d.values())} launches; "
+                f"cold-cache, serialised: compare SHARES)\n\n| kernel | launches | total ms | share | mean us |\n|---|---|---|---|---|\n")
+        for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
+            f.write(f"| {k} | {len(v)} | {sum(v)/1e6:.3f} | {100*sum(v)/tot:.1f} % | {sum(v)/len(v)/1e3:.1f} |\n")
+
+def ncu_summary(rep, out, title):
+    txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+    with open(out, "w") as f:
+        f.write(f"# {title}\n# source: ncu --set full --clock-control none --import-source on, one launch\n" + txt)
+    return txt
+
+if os.path.exists(os.path.join(G, f"launches_{tag}.csv")):
+    launches(os.path.join(G, f"launches_{tag}.csv"), os.path.join(P, f"{tag}_launches_summary.md"))
+traffic = {}
+for name, title in (("par_round", "par_round_kernel, 4096^2 FBm map, 4,194,304 particles, one round (step ~150 of a call)"),
+                    ("cascade_stamped", "cascade_tile_kernel<stamped,TMA>, same run: World::cascade at the cells touched in the round"),
+                    ("cascade_sweep8192", "cascade_tile_kernel<plain,TMA>, 8192^2 U(0,1) map, one whole-map sweep")):
+    rep = os.path.join(G, f"{name}_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        txt = ncu_summary(rep, os.path.join(P, f"{tag}_{name}_ncu.txt"), title)
+        rd = wr = None
+        for ln in txt.splitlines():
+            f = ln.split()
+            if len(f) >= 3 and f[0] == "dram__bytes_read.sum": rd = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[f[2]]
+            if len(f) >= 3 and f[0] == "dram__bytes_write.sum": wr = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[f[2]]
+        if rd is not None and wr is not None: traffic[name] = rd + wr
+json.dump({"source": f"profiles/{tag}_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)", "bytes_per_launch": traffic},
+          open(os.path.join(P, "traffic.json"), "w"), indent=1)
+print(traffic)
