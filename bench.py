@@ -327,15 +327,23 @@ def run_ours(args) -> None:
         # Neighbours exchange ghost rows and hand over particles by P2P kernels (no NCCL on the
         # data path; torch.distributed only ships the CUDA IPC handles).
         from simplewinderosion_b200 import stripes
-        w = stripes.StripedWorld(n * world, n, rank, world, particles * world, device=local)
+        if args.strong:   # cfg4-style: ONE size x size map cut into stripes, `particles` in total
+            w = stripes.StripedWorld(n, n, rank, world, particles, device=local)
+        else:
+            w = stripes.StripedWorld(n * world, n, rank, world, particles * world, device=local)
         w.connect()
     stream = torch.cuda.Stream()
     w.set_stream(stream.cuda_stream)
-    w.upload(hm)
+    if world > 1 and args.strong:
+        w.upload_global(hm)
+    else:
+        w.upload(hm)
     if world > 1:
         w.sync_halos()
     w.srand(1)
-    particles_call = particles * world     # GLOBAL particle count of one World::erode call
+    # GLOBAL particle count of one World::erode call
+    particles_call = particles if (world == 1 or args.strong) else particles * world
+    rows_local = w.nx
 
     # ---- device-resident timing ---------------------------------------------------------------
     for _ in range(args.warmup):
@@ -390,8 +398,8 @@ def run_ours(args) -> None:
         buf = (C.c_float * (nbytes // 4)).from_address(ptr.value)
         return np.frombuffer(buf, dtype=np.float32).reshape(shape), ptr
 
-    h_in, p_in = pinned((n, n))
-    h_out, p_out = pinned((5, n, n))
+    h_in, p_in = pinned((rows_local, n))
+    h_out, p_out = pinned((5, rows_local, n))
     h_in[...] = w.download()
     planes = (swe.HEIGHT, swe.MASSFLOW, swe.MOMENTUMX, swe.MOMENTUMY, swe.MOMENTUMZ)
 
@@ -427,21 +435,23 @@ def run_ours(args) -> None:
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
         "config": {
-            "workload": WORKLOAD if (n == N_MAP and particles == PARTICLES) else
+            "workload": WORKLOAD if (n == N_MAP and particles == PARTICLES and not args.strong) else
             f"{n}x{n} FBm dune field, {particles} particles per World::erode, parallel mode",
-            "map": [n * world, n], "particles_per_step": particles_call,
+            "map": [n if args.strong else n * world, n], "particles_per_step": particles_call,
             "parallelism": "single GPU" if world == 1 else
-            f"{world} row stripes of a {n * world}x{n} map (one {n}x{n} stripe and ~{particles} particles per GPU), "
+            f"{world} row stripes of a {n if args.strong else n * world}x{n} map ({rows_local} rows and "
+            f"~{particles_call // world} particles per GPU), "
             f"P2P halo push + particle hand-off kernels over NVLink",
             "stripe_overflow": int(overflow_total),
             "l2": "working set 720 MiB (height 64 + track 256 + field 256 + particles 128 + stamps 16) > 126 MB L2; no flush needed",
             "steps_per_particle": total_steps / max(1.0, total_particles),
         },
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * n * n),
-                "d2h_bytes_per_step": int(5 * 4 * n * n), "ms_per_step": 1e3 * e2e_s / args.steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * rows_local * n),
+                "d2h_bytes_per_step": int(5 * 4 * rows_local * n), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "result_check_mean_height": mean_h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "par_round_kernel", "achieved": achieved, "peak": peak,
@@ -486,6 +496,9 @@ def main() -> None:
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cascade", action="store_true")
     ap.add_argument("--quick", action="store_true", help="shorter cascade relaxation")
+    ap.add_argument("--strong", action="store_true",
+                    help="N>1: cut ONE size x size map into N stripes (cfg4: --size 16384 --particles 16777216) "
+                         "instead of the default weak scaling (one size x size stripe per GPU)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswe_b200.so")
+LIB_PATH = os.environ.get("SWE_B200_LIB") or os.path.join(_HERE, "libswe_b200.so")   # override: kernel-variant experiments
 
 ABI_VERSION = 1
 

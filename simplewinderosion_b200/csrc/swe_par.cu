@@ -224,8 +224,11 @@ __global__ void par_spawn_stripe_kernel(float4* __restrict__ pa, float4* __restr
 // use, ids in pid[]); a particle whose next cell lies in a neighbour's rows is appended to that
 // neighbour's inbox through its peer-mapped pointers (NVLink stores + a system-scope atomic for
 // the slot) and retired here.
+#ifndef SWE_ROUND_MIN_BLOCKS
+#define SWE_ROUND_MIN_BLOCKS 4   // resident CTAs of 256 threads per SM the register budget is tuned for
+#endif
 template <bool STRIPE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SWE_ROUND_MIN_BLOCKS)
 par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restrict__ pb, int n,
                  int steps_per_round, uint2 key, uint32_t call, unsigned char* stamp,
                  unsigned char stamp_now, const unsigned* live_in, unsigned* live_out,
