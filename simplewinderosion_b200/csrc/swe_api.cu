@@ -69,6 +69,7 @@ struct swe_engine {
   // parallel-mode state
   ParticleBuf pbuf{};
   HeightTensorMap tmap{};
+  TileScratch tsc{};                  // staging plane + per-tile flags of the cascade tile kernels
   unsigned char* d_stamp = nullptr;   // per-cell "touched in round" byte
   unsigned stamp_counter = 0;
   int opt_cascade_variant = 0;        // 0 fused tile kernel, 1 per-colour launches
@@ -281,8 +282,9 @@ int stripe_erode_round(swe_engine* e) {
     nl += 3;
   }
   // rows own_lo-1 .. own_hi: the ghost row each side is recomputed here instead of exchanged
-  launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, nullptr, S.own_lo - 1, S.own_hi + 1, e->stream);
-  nl += 1;
+  launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, nullptr, S.own_lo - 1, S.own_hi + 1, e->tsc,
+                         e->stream);
+  nl += 2;
   stripe_exchange_end(e, s, &nl);
   return check_launch(e, "stripe round", nl);
 }
@@ -399,6 +401,9 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
   TRY(cudaMemsetAsync(e->m.height, 0, n * sizeof(float), e->stream));
   TRY(cudaMemsetAsync(e->m.field, 0, n * sizeof(float4), e->stream));
   TRY(cudaMemsetAsync(e->m.track, 0, n * sizeof(float4), e->stream));
+  TRY(cudaMalloc(&e->tsc.stage, n * sizeof(float)));
+  TRY(cudaMalloc(&e->tsc.flags, tile_flag_count(e->m)));
+  TRY(cudaMemsetAsync(e->tsc.flags, 0, tile_flag_count(e->m), e->stream));
   TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(DevStats), e->stream));
   if (stripe) {
     TRY(cudaMalloc(&e->d_stamp, n));
@@ -462,6 +467,7 @@ void swe_destroy(swe_engine* e) {
   cudaFree(e->d_stats); cudaFree(e->d_rng); cudaFree(e->d_small); cudaFree(e->d_scratch);
   cudaFree(e->pbuf.a); cudaFree(e->pbuf.b); cudaFree(e->pbuf.live); cudaFree(e->d_stamp);
   cudaFree(e->st.arena); cudaFree(e->st.d_pid); cudaFree(e->st.d_vars);
+  cudaFree(e->tsc.stage); cudaFree(e->tsc.flags);
   for (void* p : e->st.ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
@@ -641,7 +647,7 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
                        e->d_stats, e->stream);
       if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
       // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
-      launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->stream);
+      launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->tsc, e->stream);
       if (kt) { SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 2], e->stream)); e->kt_rounds = r + 1; }
       if (int rc = check_launch(e, "par_round", 2)) return rc;
     }
@@ -693,8 +699,8 @@ int swe_stripe_group_sweep(swe_engine** engines, int n, int sweeps) {
       if (int rc = bind(e)) return rc;
       int nl = 0;
       const unsigned q = stripe_exchange_begin(e, false, &nl);
-      launch_cascade_stamped(e->m, e->p, &e->tmap, nullptr, 0, nullptr, e->st.own_lo, e->st.own_hi, e->stream);
-      nl += 1;
+      launch_cascade_stamped(e->m, e->p, &e->tmap, nullptr, 0, nullptr, e->st.own_lo, e->st.own_hi, e->tsc, e->stream);
+      nl += 2;
       stripe_exchange_end(e, q, &nl);
       if (int rc = check_launch(e, "stripe sweep", nl)) return rc;
     }
@@ -741,12 +747,12 @@ int swe_cascade_sweep(swe_engine* e, int sweeps, float* max_excess_out) {
     if (!e->st.connected) return fail(SWE_ERR_STATE, "swe_stripe_connect has not been called");
     for (int s = 0; s < sweeps; s++) {
       const unsigned q = stripe_exchange_begin(e, false, &n);
-      launch_cascade_stamped(e->m, e->p, &e->tmap, nullptr, 0, nullptr, e->st.own_lo, e->st.own_hi, e->stream);
-      n += 1;
+      launch_cascade_stamped(e->m, e->p, &e->tmap, nullptr, 0, nullptr, e->st.own_lo, e->st.own_hi, e->tsc, e->stream);
+      n += 2;
       stripe_exchange_end(e, q, &n);
     }
   } else {
-    n = launch_cascade_sweep(e->m, e->p, &e->tmap, sweeps, e->d_stats, e->stream, e->opt_cascade_variant);
+    n = launch_cascade_sweep(e->m, e->p, &e->tmap, sweeps, e->d_stats, e->stream, e->opt_cascade_variant, e->tsc);
   }
   if (int rc = check_launch(e, "cascade_sweep", n)) return rc;
   SWE_CUDA(cudaEventRecord(e->ev_d, e->stream));

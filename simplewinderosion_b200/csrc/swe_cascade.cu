@@ -16,6 +16,7 @@
 //
 // Compiled with -fmad=false; arithmetic through swe_exact.cuh.
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 
 #include "swe_exact.cuh"
@@ -215,6 +216,70 @@ __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, fl
   tc[0] = cc;
 }
 
+// ---- output ---------------------------------------------------------------------------------
+// Tiles of one launch run in waves; a tile that starts late must still read the PRE-sweep values
+// of its halo, i.e. of the border cells of its neighbours' outputs. Those border cells (the
+// first 4 / last 2 rows and first 16 / last 8 columns of O: exactly the cells some other tile's
+// R_0 covers, 20 % of the tile) are therefore written to a staging plane and copied into place
+// by cascade_commit_kernel after the sweep kernel has finished; the interior of O, which no other
+// tile reads, goes straight to the height plane.
+__device__ __forceinline__ bool tile_border(int ox, int oz) {
+  return ox < 4 || ox >= TILE_TX - 2 || oz < 16 || oz >= TILE_TZ - 8;
+}
+
+__device__ __forceinline__ void tile_store(const float* tile, const MapView& m, const RowWindow& win,
+                                           float* __restrict__ stage, int ox0, int oz0, int tid, bool vec_ok) {
+  const int nz = m.nz;
+  if (vec_ok) {
+    for (int i = tid; i < TILE_TX * (TILE_TZ / 4); i += TILE_THREADS) {
+      const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);
+      const int gx = ox0 + ox, gz = oz0 + 4 * q;
+      if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz) {
+        float* dst = tile_border(ox, 4 * q) ? stage : m.height;
+        *reinterpret_cast<float4*>(dst + m.idx(gx, gz)) =
+            *reinterpret_cast<const float4*>(tile + (ox + 2) * TILE_PITCH + 8 + 4 * q);
+      }
+    }
+  } else {
+    for (int i = tid; i < TILE_TX * TILE_TZ; i += TILE_THREADS) {
+      const int ox = i / TILE_TZ, oz = i - ox * TILE_TZ;
+      const int gx = ox0 + ox, gz = oz0 + oz;
+      if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz) {
+        float* dst = tile_border(ox, oz) ? stage : m.height;
+        dst[m.idx(gx, gz)] = tile[(ox + 2) * TILE_PITCH + (oz + 8)];
+      }
+    }
+  }
+}
+
+// copies the staged border cells of every tile that changed into the height plane
+__global__ void __launch_bounds__(256)
+cascade_commit_kernel(MapView m, RowWindow win, const float* __restrict__ stage, unsigned char* __restrict__ flags) {
+  const int tile_id = (win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x;
+  if (!flags[tile_id]) return;
+  const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
+  const int nz = m.nz;
+  const bool vec_ok = (nz & 3) == 0;
+  if (vec_ok) {
+    for (int i = threadIdx.x; i < TILE_TX * (TILE_TZ / 4); i += 256) {
+      const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);
+      if (!tile_border(ox, 4 * q)) continue;
+      const int gx = ox0 + ox, gz = oz0 + 4 * q;
+      if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz)
+        *reinterpret_cast<float4*>(m.height + m.idx(gx, gz)) = *reinterpret_cast<const float4*>(stage + m.idx(gx, gz));
+    }
+  } else {
+    for (int i = threadIdx.x; i < TILE_TX * TILE_TZ; i += 256) {
+      const int ox = i / TILE_TZ, oz = i - ox * TILE_TZ;
+      if (!tile_border(ox, oz)) continue;
+      const int gx = ox0 + ox, gz = oz0 + oz;
+      if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz) m.height[m.idx(gx, gz)] = stage[m.idx(gx, gz)];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flags[tile_id] = 0;
+}
+
 // USE_TMA: the height tile arrives by one cp.async.bulk.tensor.2d (UTMALDG) with hardware
 // zero-fill outside the map; needs nz % 4 == 0 (16-byte row pitch). Otherwise plain loads.
 //
@@ -227,7 +292,7 @@ template <bool USE_STAMP, bool USE_TMA>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
                     const unsigned char* __restrict__ stamp, unsigned char stamp_now,
-                    const unsigned* __restrict__ gate, RowWindow win) {
+                    const unsigned* __restrict__ gate, RowWindow win, TileScratch scratch) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (USE_STAMP && gate && *gate == 0u) return;
   float* tile = reinterpret_cast<float*>(smem_raw);
@@ -369,22 +434,180 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
 
   // ---- store O if anything in this tile moved -----------------------------------------------
   if (any_change) {                                  // CTA-uniform (derived from shared counters)
-    if (vec_ok) {
-      for (int i = tid; i < TILE_TX * (TILE_TZ / 4); i += TILE_THREADS) {
-        const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);
-        const int gx = ox0 + ox, gz = oz0 + 4 * q;
-        if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz)
-          *reinterpret_cast<float4*>(m.height + m.idx(gx, gz)) =
-              *reinterpret_cast<const float4*>(tile + (ox + 2) * TILE_PITCH + 8 + 4 * q);
+    tile_store(tile, m, win, scratch.stage, ox0, oz0, tid, vec_ok);
+    if (tid == 0) scratch.flags[(win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x] = 1;
+  }
+}
+
+// =============================================================================================
+// Stamped sweep (flight pipeline): World::cascade once at every cell a particle touched in the
+// round, same colour order, same tiles -- but the work is driven by the touched cells, not by
+// the map: while the stamp bytes of the tile are read, every touched cell is appended to the
+// queue of its colour (nine shared-memory queues); a tile without touched cells returns before
+// it loads any heights; otherwise each colour phase runs the early-out test densely over its
+// queue and relaxes the survivors densely. Touched cells in the halo outside R_c are processed
+// too: their blocks do not reach the cells the tile stores (they would have been in R_c), so
+// this only costs a few redundant cascades.
+// =============================================================================================
+constexpr int STAMPED_QCAP = (TILE_LX / 3) * (TILE_PITCH / 3);            // centres of one colour in the tile
+constexpr int STAMPED_SMEM = TILE_FLOAT_BYTES + 10 * STAMPED_QCAP * 2 + 96;
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
+                            const unsigned char* __restrict__ stamp, unsigned char stamp_now,
+                            const unsigned* __restrict__ gate, RowWindow win, TileScratch scratch) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (gate && *gate == 0u) return;
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  unsigned short* cq = reinterpret_cast<unsigned short*>(smem_raw + TILE_FLOAT_BYTES);   // [9][QCAP] by colour
+  unsigned short* rq = cq + 9 * STAMPED_QCAP;                                              // relax queue
+  unsigned* cnt = reinterpret_cast<unsigned*>(rq + STAMPED_QCAP);                          // [9] touched + [9] relax
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(cnt + 18);
+  const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
+  const int gx0 = ox0 - 2, gz0 = oz0 - 8;
+  const int sx0 = m.x0, sx1 = m.x0 + m.rows;
+  const int tid = threadIdx.y * TILE_BX + threadIdx.x;
+  const int nx = m.nx, nz = m.nz;
+  const float hs = fmul(settling, 0.5f);
+  const bool generic_only = !(thr.ortho >= 0.0f) || !(thr.diag >= 0.0f) || !(fabsf(settling) >= 1e-18f) ||
+                            !(fabsf(settling) <= 1e18f) || (thr.ortho != 0.0f && thr.ortho < 1e-18f);
+  const bool vec_ok = (nz & 3) == 0;
+  const bool interior = gx0 >= 0 && gz0 >= 0 && gx0 + TILE_LX <= nx && gz0 + TILE_PITCH <= nz;
+
+  if (tid < 18) cnt[tid] = 0u;
+  if (USE_TMA && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- touched cells -> per-colour queues --------------------------------------------------
+  // gx0 == 2 and gz0 == 2 (mod 3): colour of local cell (lx, lz) = ((lx+2)%3)*3 + (lz+2)%3
+  auto push = [&](int lx, int lz) {
+    if (lx < 1 || lx > TILE_LX - 2 || lz < 1 || lz > TILE_PITCH - 2) return;   // block must fit the tile
+    const int c = ((lx + 2) % 3) * 3 + (lz + 2) % 3;
+    const unsigned slot = atomicAdd(&cnt[c], 1u);
+    cq[c * STAMPED_QCAP + slot] = (unsigned short)(lx * TILE_PITCH + lz);
+  };
+  if (vec_ok) {
+    const unsigned pat = 0x01010101u * stamp_now;
+    for (int i = tid; i < TILE_LX * (TILE_PITCH / 4); i += TILE_THREADS) {
+      const int lx = i / (TILE_PITCH / 4), q = i - lx * (TILE_PITCH / 4);
+      const int gx = gx0 + lx, gz = gz0 + 4 * q;
+      if (gx < sx0 || gx >= sx1 || gx < 0 || gx >= nx || gz < 0 || gz >= nz) continue;
+      const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(stamp + m.idx(gx, gz))) ^ pat;
+      if ((v & 0x000000ffu) == 0u) push(lx, 4 * q);
+      if ((v & 0x0000ff00u) == 0u) push(lx, 4 * q + 1);
+      if ((v & 0x00ff0000u) == 0u) push(lx, 4 * q + 2);
+      if ((v & 0xff000000u) == 0u) push(lx, 4 * q + 3);
+    }
+  } else {
+    for (int i = tid; i < TILE_LX * TILE_PITCH; i += TILE_THREADS) {
+      const int lx = i / TILE_PITCH, lz = i - lx * TILE_PITCH;
+      const int gx = gx0 + lx, gz = gz0 + lz;
+      if (gx < sx0 || gx >= sx1 || gx < 0 || gx >= nx || gz < 0 || gz >= nz) continue;
+      if (__ldcg(stamp + m.idx(gx, gz)) == stamp_now) push(lx, lz);
+    }
+  }
+  __syncthreads();
+  {
+    unsigned total = 0;
+#pragma unroll
+    for (int c = 0; c < 9; c++) total += cnt[c];
+    if (total == 0u) return;                       // nothing touched here: no height traffic at all
+  }
+
+  // ---- heights -----------------------------------------------------------------------------
+  if (USE_TMA) {
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)),
+                   "r"(TILE_FLOAT_BYTES) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+          ::"r"(smem_u32(tile)), "l"(&tmap), "r"(gz0), "r"(gx0 - m.x0), "r"(smem_u32(mbar)) : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(smem_u32(mbar)) : "memory");
+    }
+  } else {
+    for (int i = tid; i < TILE_LX * TILE_PITCH; i += TILE_THREADS) {
+      const int lx = i / TILE_PITCH, lz = i - lx * TILE_PITCH;
+      const int gx = gx0 + lx, gz = gz0 + lz;
+      float v = 0.0f;
+      if (gx >= sx0 && gx < sx1 && gz >= 0 && gz < nz) v = __ldg(m.height + m.idx(gx, gz));
+      tile[i] = v;
+    }
+    __syncthreads();
+  }
+
+  bool any_change = false;
+  const unsigned lane = tid & 31;
+#pragma unroll 1
+  for (int c = 0; c < 9; c++) {
+    const unsigned nc = cnt[c];
+    if (nc == 0u) continue;                        // CTA-uniform
+    unsigned* qc = cnt + 9 + c;                    // one relax counter per colour: no reset races
+    const unsigned short* mine = cq + c * STAMPED_QCAP;
+    // ---- scan: early-out test, dense over the touched centres of this colour -----------------
+    for (unsigned base_i = 0; base_i < nc; base_i += TILE_THREADS) {
+      const unsigned i = base_i + tid;
+      bool need = i < nc;
+      int off = 0;
+      if (need) {
+        off = mine[i];
+        {   // only the colour-c centres inside R_c are part of this tile's dependency cone
+          const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
+          const int cxi3 = lx - (c / 3) - 1, czi3 = lz - c - 1;
+          need = cxi3 >= 0 && cxi3 < 3 * (TILE_TX / 3 + 2 - c / 3) && czi3 >= 0 && czi3 < 3 * (TILE_TZ / 3 + 8 - c);
+        }
+        if (need && !generic_only) {
+          const float* tc = tile + off;
+          if (interior) {
+            need = centre_needs<true, false>(tc, thr, hs, centre_valid<true>(1, 1, 3, 3));
+          } else {
+            const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
+            const int gx = gx0 + lx, gz = gz0 + lz;
+            need = gx >= 0 && gx < nx && gz >= 0 && gz < nz &&
+                   centre_needs<false, false>(tc, thr, hs, centre_valid<false>(gx, gz, nx, nz));
+          }
+        }
       }
-    } else {
-      for (int i = tid; i < TILE_TX * TILE_TZ; i += TILE_THREADS) {
-        const int ox = i / TILE_TZ, oz = i - ox * TILE_TZ;
-        const int gx = ox0 + ox, gz = oz0 + oz;
-        if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz)
-          m.height[m.idx(gx, gz)] = tile[(ox + 2) * TILE_PITCH + (oz + 8)];
+      const unsigned mask = __ballot_sync(0xffffffffu, need);
+      if (mask) {
+        unsigned b = 0;
+        if (lane == (unsigned)(__ffs(mask) - 1)) b = atomicAdd(qc, (unsigned)__popc(mask));
+        b = __shfl_sync(0xffffffffu, b, __ffs(mask) - 1);
+        if (need) rq[b + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)off;
       }
     }
+    __syncthreads();
+    // ---- relax ------------------------------------------------------------------------------
+    const unsigned nq = *qc;
+    any_change |= nq != 0u;
+    for (unsigned i = tid; i < nq; i += TILE_THREADS) {
+      const int off = rq[i];
+      float* tc = tile + off;
+      if (interior && !generic_only) {
+        centre_relax<true>(tc, thr, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
+      } else {
+        const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
+        const int gx = gx0 + lx, gz = gz0 + lz;
+        if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
+        else centre_relax<false>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
+      }
+    }
+    __syncthreads();
+  }
+
+  if (any_change) {
+    tile_store(tile, m, win, scratch.stage, ox0, oz0, tid, vec_ok);
+    if (tid == 0) scratch.flags[(win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x] = 1;
   }
 }
 
@@ -453,16 +676,18 @@ bool make_height_tensor_map(const MapView& m, HeightTensorMap* out) {
   return out->valid;
 }
 
+bool g_old_stamped = false;   // debugging switch (SWE_OLD_STAMPED=1): map-driven stamped sweep
+
 template <bool S, bool T>
 static void tile_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, const CUtensorMap& tm,
                         const MapView& m, float settling, CascadeThr thr, const unsigned char* stamp,
-                        unsigned char now, const unsigned* gate, RowWindow win) {
+                        unsigned char now, const unsigned* gate, RowWindow win, TileScratch scratch) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(cascade_tile_kernel<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  cascade_tile_kernel<S, T><<<grid, block, smem, st>>>(tm, m, settling, thr, stamp, now, gate, win);
+  cascade_tile_kernel<S, T><<<grid, block, smem, st>>>(tm, m, settling, thr, stamp, now, gate, win, scratch);
 }
 
 // rows [row_lo, row_hi) are (re)computed and stored; the tiles covering them are launched. On a
@@ -470,7 +695,9 @@ static void tile_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, con
 // from a halo of 5 rows below / 7 above (the <= 4/6-row dependency cone of the nine colours).
 static void launch_tile_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                               const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                              int row_lo, int row_hi, cudaStream_t st) {
+                              int row_lo, int row_hi, TileScratch scratch, cudaStream_t st) {
+  static bool env_read = false;
+  if (!env_read) { env_read = true; const char* v = getenv("SWE_OLD_STAMPED"); g_old_stamped = v && v[0] == '1'; }
   CascadeThr thr;
   thr.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;      // host IEEE fp32: same values as the device helper
   thr.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
@@ -486,28 +713,42 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
   const bool tma = tmap && tmap->valid;
   CUtensorMap tm;
   if (tma) memcpy(&tm, tmap->opaque, sizeof tm); else memset(&tm, 0, sizeof tm);
-  if (stamp) {
-    if (tma) tile_launch<true, true>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate, win);
-    else     tile_launch<true, false>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate, win);
+  if (stamp && g_old_stamped) {
+    if (tma) tile_launch<true, true>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
+    else     tile_launch<true, false>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
+  } else if (stamp) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(cascade_tile_stamped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAMPED_SMEM);
+      cudaFuncSetAttribute(cascade_tile_stamped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAMPED_SMEM);
+      attr = true;
+    }
+    if (tma) cascade_tile_stamped_kernel<true><<<grid, block, STAMPED_SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
+    else     cascade_tile_stamped_kernel<false><<<grid, block, STAMPED_SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
   } else {
-    if (tma) tile_launch<false, true>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr, win);
-    else     tile_launch<false, false>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr, win);
+    if (tma) tile_launch<false, true>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr, win, scratch);
+    else     tile_launch<false, false>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr, win, scratch);
   }
+  cascade_commit_kernel<<<grid, 256, 0, st>>>(m, win, scratch.stage, scratch.flags);
 }
 
 void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                             const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                            int row_lo, int row_hi, cudaStream_t st) {
-  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, row_lo, row_hi, st);
+                            int row_lo, int row_hi, TileScratch scratch, cudaStream_t st) {
+  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, row_lo, row_hi, scratch, st);
+}
+
+size_t tile_flag_count(const MapView& m) {
+  return (size_t)((m.nz - TILE_OZ + TILE_TZ - 1) / TILE_TZ) * (size_t)((m.nx - TILE_OX + TILE_TX - 1) / TILE_TX);
 }
 
 int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap, int sweeps,
-                         DevStats* stats, cudaStream_t st, int variant) {
+                         DevStats* stats, cudaStream_t st, int variant, TileScratch scratch) {
   int launches = 0;
   for (int s = 0; s < sweeps; s++) {
     if (variant == 0 || variant == 2) {
-      launch_tile_sweep(m, p, variant == 2 ? nullptr : tmap, nullptr, 0, nullptr, 0, m.nx, st);
-      launches++;
+      launch_tile_sweep(m, p, variant == 2 ? nullptr : tmap, nullptr, 0, nullptr, 0, m.nx, scratch, st);
+      launches += 2;
       continue;
     }
     for (int c = 0; c < 9; c++) {   // v1: one launch per colour straight from global memory
@@ -548,8 +789,9 @@ void preload_cascade() {
   cudaFuncGetAttributes(&a, cascade_colour_kernel);
   cudaFuncGetAttributes(&a, cascade_tile_kernel<false, false>);
   cudaFuncGetAttributes(&a, cascade_tile_kernel<false, true>);
-  cudaFuncGetAttributes(&a, cascade_tile_kernel<true, false>);
-  cudaFuncGetAttributes(&a, cascade_tile_kernel<true, true>);
+  cudaFuncGetAttributes(&a, cascade_tile_stamped_kernel<false>);
+  cudaFuncGetAttributes(&a, cascade_tile_stamped_kernel<true>);
+  cudaFuncGetAttributes(&a, cascade_commit_kernel);
   cudaFuncGetAttributes(&a, max_excess_kernel);
   cudaFuncGetAttributes(&a, set_float_kernel);
   cudaFuncGetAttributes(&a, add_cascade_cells_kernel);

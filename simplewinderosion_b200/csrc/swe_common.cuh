@@ -72,6 +72,14 @@ struct RowWindow {
   int tile_y0;              // index of the first tile row launched
 };
 
+// Scratch of the tile sweep: staging plane for the border cells of each tile's output (same
+// indexing as the height plane) and one "changed" byte per tile of the whole-map tile grid.
+struct TileScratch {
+  float* stage;
+  unsigned char* flags;
+};
+size_t tile_flag_count(const MapView& m);
+
 // TMA descriptor of the height plane (CUtensorMap, kept opaque here), built once per engine.
 struct alignas(64) HeightTensorMap {
   unsigned char opaque[128];
@@ -81,12 +89,12 @@ bool make_height_tensor_map(const MapView& m, HeightTensorMap* out);
 // variant 0 = fused 9-colour shared-memory tile kernel (TMA tile load when the descriptor is
 // valid), 1 = one global-memory launch per colour, 2 = fused tile kernel with plain loads
 int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap, int sweeps,
-                         DevStats* stats, cudaStream_t st, int variant);  // returns #kernel launches
+                         DevStats* stats, cudaStream_t st, int variant, TileScratch scratch);  // returns #launches
 // one fused sweep restricted to cells whose stamp byte equals stamp_now (flight pipeline)
 // (gate: device counter; the sweep is skipped when *gate == 0, i.e. no particle flew)
 void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                             const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                            int row_lo, int row_hi, cudaStream_t st);
+                            int row_lo, int row_hi, TileScratch scratch, cudaStream_t st);
 void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st);
 
 // parallel flight: swe_par.cu
