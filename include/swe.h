@@ -93,7 +93,8 @@ typedef struct swe_params {
   float settling;
   int32_t mapscale;
   float pspeed[3];
-  int32_t reserved[5];  /* must be zero */
+  float abrasion;       /* layered extension: fraction of unmet erosion demand ground out of rock (0 = off) */
+  int32_t reserved[4];  /* must be zero */
 } swe_params;
 
 /* struct Wind (wind.hpp:4-21) as plain data. pos = (x, altitude, z). */
@@ -152,6 +153,15 @@ int swe_download_plane(swe_engine* e, int plane, float* dst, ptrdiff_t stride_by
 /* Whole reference pool in one go: `cells` points at nx*nz 36-byte quad::cell records. */
 int swe_upload_cells(swe_engine* e, const void* cells);
 int swe_download_cells(swe_engine* e, void* cells);
+/* Layered-terrain extension (NOT in the reference snapshot, whose cell has one height; our
+ * specification): a bedrock plane under the sand, sand = height - rock >= 0.
+ * Parallel-mode erosion takes sand only and grinds rock at swe_params.abrasion efficiency;
+ * every cascade transfer is capped by the giving cell's sand. Uploading a rock plane switches
+ * the engine to layered mode (single-GPU engines, parallel mode and cascade calls);
+ * swe_clear_rock returns to the reference's single layer. */
+int swe_upload_rock(swe_engine* e, const float* src, ptrdiff_t stride_bytes);
+int swe_download_rock(swe_engine* e, float* dst, ptrdiff_t stride_bytes);
+int swe_clear_rock(swe_engine* e);
 /* Pinned host memory for fast transfers (optional; any host pointer is accepted). */
 int swe_host_alloc(void** out, size_t bytes);
 int swe_host_free(void* p);

@@ -114,7 +114,17 @@ swo_world* swo_create(int nx, int nz) {
 void swo_destroy(swo_world* w) {
   if (!w) return;
   for (int i = 0; i < 9; i++) free(w->plane[i]);
+  free(w->rock);
   free(w);
+}
+
+void swo_set_rock(swo_world* w, const float* rock) {
+  free(w->rock);
+  w->rock = NULL;
+  if (!rock) return;
+  const size_t n = (size_t)w->nx * w->nz;
+  w->rock = (float*)malloc(n * sizeof(float));
+  memcpy(w->rock, rock, n * sizeof(float));
 }
 
 /* cellpool.h:372-428 (mapsize = 1: node.pos = 0, tileres = (n,n), lodsize = 1) */
@@ -225,6 +235,13 @@ void swo_cascade(swo_world* w, int x, int z) {
     float excess = fabsf(diff) - sn[i].d * w->p.maxdiff * (float)1 /* lodsize */;
     if (excess <= 0) continue;
     float transfer = w->p.settling * excess / 2.0f;
+    if (w->rock) { /* layered extension: only sand moves */
+      const float sand = (diff > 0) ? HGT(w, x, z) - w->rock[(size_t)x * w->nz + z]
+                                    : sn[i].h - w->rock[(size_t)sn[i].x * w->nz + sn[i].z];
+      const float cap = sand > 0.0f ? sand : 0.0f;
+      if (cap < transfer) transfer = cap;
+      if (!(transfer > 0.0f)) continue;
+    }
     if (diff > 0) {
       HGT(w, x, z) -= transfer;
       HGT(w, sn[i].x, sn[i].z) += transfer;

@@ -55,6 +55,11 @@ typedef struct swo_world {
                             massflow_track, momentumx_track, momentumy_track, momentumz_track */
   swo_params p;
   swo_rand_state rng;
+  /* Layered-terrain EXTENSION (not in the reference snapshot; restates the product's own
+   * specification, parity unpinned): bedrock plane, NULL = the reference's single layer.
+   * Only swo_cascade / swo_cascade_sweep honour it: a transfer is capped by the giving
+   * cell's sand max(height - rock, 0). */
+  float* rock;
 } swo_world;
 
 typedef struct swo_particle {  /* struct Wind, wind.hpp:4-21 */
@@ -74,6 +79,7 @@ typedef struct swo_stats {
 void swo_default_params(swo_params* p);
 swo_world* swo_create(int nx, int nz);
 void swo_destroy(swo_world* w);
+void swo_set_rock(swo_world* w, const float* rock);   /* copies nx*nz values; NULL clears */
 
 void swo_srand(swo_rand_state* s, unsigned seed);
 int  swo_rand(swo_rand_state* s);

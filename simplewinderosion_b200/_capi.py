@@ -33,7 +33,8 @@ class Params(C.Structure):
         ("settling", C.c_float),
         ("mapscale", C.c_int32),
         ("pspeed", C.c_float * 3),
-        ("reserved", C.c_int32 * 5),
+        ("abrasion", C.c_float),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -104,6 +105,9 @@ PROTOTYPES = {
     "swe_download_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_upload_cells": (C.c_int, [_E, C.c_void_p]),
     "swe_download_cells": (C.c_int, [_E, C.c_void_p]),
+    "swe_upload_rock": (C.c_int, [_E, C.c_void_p, C.c_ssize_t]),
+    "swe_download_rock": (C.c_int, [_E, C.c_void_p, C.c_ssize_t]),
+    "swe_clear_rock": (C.c_int, [_E]),
     "swe_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "swe_host_free": (C.c_int, [C.c_void_p]),
     "swe_erode": (C.c_int, [_E, C.c_int, C.c_int]),

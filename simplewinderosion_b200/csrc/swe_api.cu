@@ -42,7 +42,8 @@ bool params_ok(const swe_params& p, const char** why) {
   if (p.mapscale <= 0) { *why = "mapscale must be > 0"; return false; }
   const float l2 = p.pspeed[0] * p.pspeed[0] + p.pspeed[1] * p.pspeed[1] + p.pspeed[2] * p.pspeed[2];
   if (!(l2 > 0.0f)) { *why = "pspeed must be non-zero"; return false; }
-  for (int i = 0; i < 5; i++)
+  if (!(p.abrasion >= 0.0f) || p.abrasion > 1.0f) { *why = "abrasion must be in [0, 1]"; return false; }
+  for (int i = 0; i < 4; i++)
     if (p.reserved[i] != 0) { *why = "reserved fields must be zero"; return false; }
   return true;
 }
@@ -60,6 +61,7 @@ struct swe_engine {
   DevStats* d_stats = nullptr;
   DetRand* d_rng = nullptr;
   float* d_small = nullptr;     // 64 floats of scratch for scalar results
+  float* d_rock = nullptr;      // layered extension: bedrock plane (m.rock points here when enabled)
   float* d_scratch = nullptr;   // lazily sized staging for plane/AoS conversion
   size_t scratch_bytes = 0;
   void* h_stage = nullptr;      // pinned host staging for strided host buffers
@@ -467,7 +469,7 @@ void swe_destroy(swe_engine* e) {
   cudaFree(e->d_stats); cudaFree(e->d_rng); cudaFree(e->d_small); cudaFree(e->d_scratch);
   cudaFree(e->pbuf.a); cudaFree(e->pbuf.b); cudaFree(e->pbuf.live); cudaFree(e->d_stamp);
   cudaFree(e->st.arena); cudaFree(e->st.d_pid); cudaFree(e->st.d_vars);
-  cudaFree(e->tsc.stage); cudaFree(e->tsc.flags);
+  cudaFree(e->tsc.stage); cudaFree(e->tsc.flags); cudaFree(e->d_rock);
   for (void* p : e->st.ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
@@ -567,6 +569,44 @@ int swe_download_plane(swe_engine* e, int plane, float* dst, ptrdiff_t stride_by
   return SWE_OK;
 }
 
+int swe_upload_rock(swe_engine* e, const float* src, ptrdiff_t stride_bytes) {
+  if (int rc = bind(e)) return rc;
+  if (e->st.enabled) return fail(SWE_ERR_STATE, "the layered extension is not available on stripe engines");
+  if (!src) return fail(SWE_ERR_INVALID, "src is NULL");
+  if (stride_bytes < 4 || stride_bytes % 4) return fail(SWE_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 4");
+  const size_t n = e->cells(), bytes = n * sizeof(float);
+  if (!e->d_rock) SWE_CUDA(cudaMalloc(&e->d_rock, bytes));
+  const float* packed = src;
+  if (stride_bytes != 4) {
+    if (int rc = need_stage(e, bytes)) return rc;
+    SWE_CUDA(cudaStreamSynchronize(e->stream));
+    float* s = static_cast<float*>(e->h_stage);
+    const char* b = reinterpret_cast<const char*>(src);
+    for (size_t i = 0; i < n; i++) std::memcpy(&s[i], b + i * (size_t)stride_bytes, 4);
+    packed = s;
+  }
+  SWE_CUDA(cudaMemcpyAsync(e->d_rock, packed, bytes, cudaMemcpyHostToDevice, e->stream));
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  e->m.rock = e->d_rock;
+  return SWE_OK;
+}
+
+int swe_download_rock(swe_engine* e, float* dst, ptrdiff_t stride_bytes) {
+  if (int rc = bind(e)) return rc;
+  if (!e->m.rock) return fail(SWE_ERR_STATE, "no rock plane: the engine is in single-layer mode");
+  if (!dst || stride_bytes != 4) return fail(SWE_ERR_INVALID, "dst must be a packed fp32 plane (stride 4)");
+  SWE_CUDA(cudaMemcpyAsync(dst, e->m.rock, e->cells() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  return SWE_OK;
+}
+
+int swe_clear_rock(swe_engine* e) {
+  if (int rc = bind(e)) return rc;
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  e->m.rock = nullptr;
+  return SWE_OK;
+}
+
 int swe_upload_cells(swe_engine* e, const void* cells) {
   if (int rc = bind(e)) return rc;
   if (!cells) return fail(SWE_ERR_INVALID, "cells is NULL");
@@ -621,6 +661,7 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
         if (int rc = stripe_erode_round(e)) return rc;
     }
   } else if (mode == SWE_MODE_DETERMINISTIC) {
+    if (e->m.rock) return fail(SWE_ERR_STATE, "deterministic mode reproduces the reference, which has no rock layer");
     launch_det_erode(e->m, e->p, cycles, e->d_rng, e->d_stats, e->stream);
     if (int rc = check_launch(e, "det_erode")) return rc;
   } else if (cycles > 0) {

@@ -87,20 +87,26 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) {
 }
 
 // generic exact fallback on the tile (same routine the single-cell path uses)
+// rock_c_ptr != nullptr: layered extension, rock_c_ptr points at the centre's bedrock height in
+// the global rock plane (row pitch nz); neighbours outside local storage are never gathered
+// because they are outside the map.
 __device__ __noinline__ bool tile_cascade_generic(float* tile_c, int gx, int gz, int nx, int nz,
-                                                  CascadeThr thr, float settling) {
-  float h[8]; int slot[8]; int num = 0;
+                                                  CascadeThr thr, float settling,
+                                                  const float* rock_c_ptr = nullptr) {
+  float h[8], rk[8]; int slot[8]; int num = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int dx = slot_dx(k), dz = slot_dz(k);
     const int x_ = gx + dx, z_ = gz + dz;
     if (x_ < 0 || z_ < 0 || x_ >= nx || z_ >= nz) continue;
     h[num] = tile_c[dx * TILE_PITCH + dz];
+    rk[num] = rock_c_ptr ? __ldg(rock_c_ptr + dx * nz + dz) : 0.0f;
     slot[num] = k;
     num++;
   }
   unsigned changed;
-  const float c1 = cascade_core(tile_c[0], h, slot, num, thr, settling, &changed);
+  const float c1 = cascade_core(tile_c[0], h, slot, num, thr, settling, &changed,
+                                rock_c_ptr ? __ldg(rock_c_ptr) : 0.0f, rock_c_ptr ? rk : nullptr);
   if (!changed) return false;
   tile_c[0] = c1;
   for (int i = 0; i < num; i++)
@@ -419,13 +425,15 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     for (unsigned i = tid; i < nq; i += TILE_THREADS) {
       const int off = queue[i];
       float* tc = tile + off;
-      if (interior && !generic_only) {
+      if (interior && !generic_only && !m.rock) {
         // interior: every neighbour exists; (1,1) in a 3x3 map tells the generic fallback so
         centre_relax<true>(tc, thr, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
       } else {
         const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
         const int gx = gx0 + lx, gz = gz0 + lz;
-        if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
+        if (m.rock)     // layered extension (single-GPU engines): sand-limited transfers, generic core
+          tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, m.rock + m.idx(gx, gz));
+        else if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
         else centre_relax<false>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
       }
     }
@@ -593,12 +601,14 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
     for (unsigned i = tid; i < nq; i += TILE_THREADS) {
       const int off = rq[i];
       float* tc = tile + off;
-      if (interior && !generic_only) {
+      if (interior && !generic_only && !m.rock) {
         centre_relax<true>(tc, thr, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
       } else {
         const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
         const int gx = gx0 + lx, gz = gz0 + lz;
-        if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
+        if (m.rock)     // layered extension (single-GPU engines): sand-limited transfers, generic core
+          tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, m.rock + m.idx(gx, gz));
+        else if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
         else centre_relax<false>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
       }
     }

@@ -21,6 +21,7 @@ struct MapView {
   float* height;
   float4* field;
   float4* track;
+  float* rock;  // layered-terrain extension: bedrock height (sand = height - rock >= 0); nullptr = single layer
   int nx, nz;   // GLOBAL map extent (bounds tests use these: closed boundary, cellpool.h:432-438)
   int x0;       // global x of local row 0 (0 on a single GPU)
   int rows;     // rows stored locally (== nx on a single GPU)

@@ -135,9 +135,13 @@ __device__ __forceinline__ int slot_dz(int k) {
 // `num` gathered neighbours: h[i] snapshot height, slot[i] offset-table slot (ascending).
 // Writes the new neighbour heights back into h[] (same positions as gathered, i.e. slot
 // order) and returns the new centre height. `changed` gets a bitmask over gather positions.
+// Layered extension (not in the reference snapshot; our specification): with bedrock heights
+// rock_c / rk[] given, only sand moves -- every transfer is capped by the giving cell's sand
+// max(height - rock, 0). rk == nullptr is the reference behaviour, bit for bit.
 __device__ __forceinline__ float cascade_core(float centre, float* h, const int* slot, int num,
                                               const CascadeThr thr, float settling,
-                                              unsigned* changed) {
+                                              unsigned* changed, float rock_c = 0.0f,
+                                              const float* rk = nullptr) {
   // insertion sort of indices (libstdc++ __insertion_sort semantics incl. the
   // compare-with-first shortcut, which only matters for NaN heights)
   int ord[8];
@@ -162,7 +166,12 @@ __device__ __forceinline__ float cascade_core(float centre, float* h, const int*
     const float t = slot_is_diag(slot[k]) ? thr.diag : thr.ortho;
     const float excess = fsub(fabsf(diff), t);                      // :133
     if (excess <= 0) continue;
-    const float transfer = fdiv(fmul(settling, excess), 2.0f);      // :139
+    float transfer = fdiv(fmul(settling, excess), 2.0f);            // :139
+    if (rk) {
+      const float sand = (diff > 0) ? fsub(centre, rock_c) : fsub(h[k], rk[k]);
+      transfer = fminf(transfer, fmaxf(sand, 0.0f));
+      if (!(transfer > 0.0f)) continue;
+    }
     if (diff > 0) { centre = fsub(centre, transfer); h[k] = fadd(h[k], transfer); }
     else          { centre = fadd(centre, transfer); h[k] = fsub(h[k], transfer); }
     ch |= 1u << k;
@@ -174,19 +183,21 @@ __device__ __forceinline__ float cascade_core(float centre, float* h, const int*
 // World::cascade(pos) on global memory (single cell): gather, core, scatter.
 __device__ __forceinline__ void cascade_global(const MapView& m, const swe_params& p,
                                                const CascadeThr thr, int x, int z) {
-  float h[8]; int slot[8]; int num = 0;
+  float h[8], rk[8]; int slot[8]; int num = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int nx_ = x + slot_dx(k), nz_ = z + slot_dz(k);
     if (m.oob(nx_, nz_)) continue;
     h[num] = m.height[m.idx(nx_, nz_)];
+    rk[num] = m.rock ? m.rock[m.idx(nx_, nz_)] : 0.0f;
     slot[num] = k;
     num++;
   }
   unsigned changed;
   const size_t ci = m.idx(x, z);
   const float c0 = m.height[ci];
-  const float c1 = cascade_core(c0, h, slot, num, thr, p.settling, &changed);
+  const float c1 = cascade_core(c0, h, slot, num, thr, p.settling, &changed, m.rock ? m.rock[ci] : 0.0f,
+                                m.rock ? rk : nullptr);
   if (changed) {
     m.height[ci] = c1;
     for (int i = 0; i < num; i++)

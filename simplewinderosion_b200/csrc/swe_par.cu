@@ -27,7 +27,7 @@
 namespace swe {
 
 struct ParConst {
-  float inv_boundarylayer, suspension, gravity, mapscale;
+  float inv_boundarylayer, suspension, gravity, mapscale, abrasion;
   float px, py, pz;      // pspeed
   float pnx, pny, pnz;   // normalize(pspeed)
   int max_age;
@@ -145,7 +145,16 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
     const float force = fmaxf(-(sx * nxv + sy * nyv + sz * nzv), 0.0f);           // :100-102
     const float lift = (1.0f - collision) * len;                                  // :104
     const float capacity = hfac * (force + 0.02f * lift);                         // :106
-    const float dh = C.suspension * (capacity - q.sed);                           // :110-112
+    float dh = C.suspension * (capacity - q.sed);                                 // :110-112
+    if (m.rock && dh > 0.0f) {
+      // layered extension: only the sand above the bedrock can be picked up; what the wind still
+      // demands grinds the rock at `abrasion` efficiency (rock -> suspended sediment)
+      const float rk = __ldcg(m.rock + ci);
+      const float take = fminf(dh, fmaxf(hc - rk, 0.0f));
+      const float ground = C.abrasion * (dh - take);
+      dh = take + ground;
+      if (ground > 0.0f) red_add_f32(m.rock + ci, -ground);
+    }
     q.sed += dh;
     if (dh != 0.0f) red_add_f32(hc_ptr, -dh);
   }
@@ -239,11 +248,11 @@ par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restr
   float lost = 0.0f;
   const int n_eff = STRIPE ? (int)min(*sr.n_used, (unsigned)n) : n;
   if (i < n_eff) {
-    const float4 b = pb[i];
+    const float4 b = __ldcs(pb + i);   // records stream through once per round: keep L2 for the map
     PState q;
     q.age = __float_as_int(b.w);
     if (q.age >= 0) {
-      const float4 a = pa[i];
+      const float4 a = __ldcs(pa + i);
       const uint32_t id = STRIPE ? sr.pid[i] : (uint32_t)i;
       q.px = a.x; q.py = a.y; q.pz = a.z; q.sed = a.w;
       q.sx = b.x; q.sy = b.y; q.sz = b.z;
@@ -277,8 +286,8 @@ par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restr
           }
         }
       }
-      pa[i] = make_float4(q.px, q.py, q.pz, q.sed);
-      pb[i] = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
+      __stcs(pa + i, make_float4(q.px, q.py, q.pz, q.sed));
+      __stcs(pb + i, make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age)));
     }
   }
   // block-aggregate the counters: one set of atomics per block
@@ -321,6 +330,7 @@ static ParConst make_const(const swe_params& p) {
   C.inv_boundarylayer = 1.0f / p.boundarylayer;
   C.suspension = p.suspension; C.gravity = p.gravity;
   C.mapscale = (float)p.mapscale;
+  C.abrasion = p.abrasion;
   C.px = p.pspeed[0]; C.py = p.pspeed[1]; C.pz = p.pspeed[2];
   const float pl = sqrtf(C.px * C.px + C.py * C.py + C.pz * C.pz);
   C.pnx = C.px / pl; C.pny = C.py / pl; C.pnz = C.pz / pl;

@@ -31,7 +31,7 @@ CELL_DTYPE = np.dtype([(n, np.float32) for n in (
 _PARAM_ALIASES = {  # reference spelling -> swe_params field
     "maxAge": "max_age", "boundarylayer": "boundarylayer", "suspension": "suspension",
     "gravity": "gravity", "lrate": "lrate", "maxdiff": "maxdiff", "settling": "settling",
-    "mapscale": "mapscale",
+    "mapscale": "mapscale", "abrasion": "abrasion",
 }
 
 
@@ -157,6 +157,21 @@ class World:
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.nx * self.nz
         check(lib.swe_download_plane(self._h, plane, out.ctypes.data, 4))
         return out
+
+    # layered-terrain extension (bedrock under the sand; not in the reference snapshot)
+    def upload_rock(self, rock: np.ndarray) -> None:
+        a = np.ascontiguousarray(rock, dtype=np.float32)
+        if a.size != self.nx * self.nz:
+            raise ValueError(f"expected {self.nx}x{self.nz} values, got {a.shape}")
+        check(lib.swe_upload_rock(self._h, a.ctypes.data, 4))
+
+    def download_rock(self) -> np.ndarray:
+        out = np.empty((self.nx, self.nz), dtype=np.float32)
+        check(lib.swe_download_rock(self._h, out.ctypes.data, 4))
+        return out
+
+    def clear_rock(self) -> None:
+        check(lib.swe_clear_rock(self._h))
 
     def upload_cells(self, cells: np.ndarray) -> None:
         """cells: structured array of CELL_DTYPE (the reference's cellpool memory)."""

@@ -28,7 +28,7 @@ class ORand(C.Structure):
 
 class OWorld(C.Structure):
     _fields_ = [("nx", C.c_int), ("nz", C.c_int), ("plane", C.POINTER(C.c_float) * 9),
-                ("p", OParams), ("rng", ORand)]
+                ("p", OParams), ("rng", ORand), ("rock", C.POINTER(C.c_float))]
 
 
 class OStats(C.Structure):
@@ -54,6 +54,7 @@ def port():
         L.swo_create.restype = W
         L.swo_create.argtypes = [C.c_int, C.c_int]
         L.swo_destroy.argtypes = [W]
+        L.swo_set_rock.argtypes = [W, C.c_void_p]
         L.swo_srand.argtypes = [C.POINTER(ORand), C.c_uint]
         L.swo_rand.argtypes = [C.POINTER(ORand)]
         L.swo_rand.restype = C.c_int
@@ -112,6 +113,14 @@ class PortWorld:
 
     def set_plane(self, k: int, a) -> None:
         self.plane(k)[...] = np.asarray(a, dtype=np.float32).reshape(self.nx, self.nz)
+
+    def set_rock(self, rock) -> None:
+        """Layered extension (our own specification, parity unpinned): bedrock plane or None."""
+        if rock is None:
+            self.L.swo_set_rock(self.w, None)
+        else:
+            a = np.ascontiguousarray(rock, dtype=np.float32).reshape(self.nx, self.nz)
+            self.L.swo_set_rock(self.w, a.ctypes.data)
 
     def srand(self, seed: int) -> None:
         self.L.swo_srand(C.byref(self.w.contents.rng), seed)
