@@ -148,15 +148,31 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
     float dh = C.suspension * (capacity - q.sed);                                 // :110-112
     if (m.rock && dh > 0.0f) {
       // layered extension: only the sand above the bedrock can be picked up; what the wind still
-      // demands grinds the rock at `abrasion` efficiency (rock -> suspended sediment)
+      // demands grinds the rock at `abrasion` efficiency (rock -> suspended sediment). Several
+      // particles may stand on one cell in the same round, so where the sand is thin the pick-up
+      // is a compare-and-swap loop that never takes the surface below the bedrock.
       const float rk = __ldcg(m.rock + ci);
-      const float take = fminf(dh, fmaxf(hc - rk, 0.0f));
+      float take = dh;
+      if (hc - rk < 64.0f * dh) {
+        unsigned* hp = reinterpret_cast<unsigned*>(hc_ptr);
+        unsigned old = __float_as_uint(hc), assumed;
+        do {
+          assumed = old;
+          take = fminf(dh, fmaxf(__uint_as_float(assumed) - rk, 0.0f));
+          if (!(take > 0.0f)) { take = 0.0f; break; }
+          old = atomicCAS(hp, assumed, __float_as_uint(__uint_as_float(assumed) - take));
+        } while (old != assumed);
+      } else {
+        red_add_f32(hc_ptr, -take);
+      }
       const float ground = C.abrasion * (dh - take);
+      if (ground > 0.0f) { red_add_f32(m.rock + ci, -ground); red_add_f32(hc_ptr, -ground); }
       dh = take + ground;
-      if (ground > 0.0f) red_add_f32(m.rock + ci, -ground);
+      q.sed += dh;
+    } else {
+      q.sed += dh;
+      if (dh != 0.0f) red_add_f32(hc_ptr, -dh);
     }
-    q.sed += dh;
-    if (dh != 0.0f) red_add_f32(hc_ptr, -dh);
   }
   stamp[ci] = stamp_now;                                                          // :114 (deferred)
   return 0;

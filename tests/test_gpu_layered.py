@@ -81,10 +81,10 @@ def test_layered_erosion_invariants_pyramid(abrasion):
         assert r0 - r1 > 1e-4                                  # some rock was ground
         assert r0 - r1 < 0.5 * st.sediment_lost + 1.0
     assert float((rg - hg).max()) < 2e-3                       # concurrent takes may overshoot by one grain
-    # the bare apex is eroded far less than open sand when abrasion is off
+    # the bare apex cannot be lowered when abrasion is off (sand may still settle on it)
     apex = (slice(n // 2 - 8, n // 2 + 8),) * 2
     if abrasion == 0.0:
-        assert float(np.abs(hg[apex] - height[apex]).max()) < 0.02
+        assert float((height[apex] - hg[apex]).max()) < 1e-5
 
 
 def test_layered_mode_guards():
