@@ -279,6 +279,36 @@ def cascade_roofline(swe, device: int, peak: float, peak_src: str, quick: bool) 
             "frac_relaxed": bytes_per_sweep / (relaxed_ms * 1e-3) / 1e9 / peak}
 
 
+def layered_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> dict:
+    """BASELINE.json configs[2] as named: dune field with a rock pyramid obstacle and abrasion on.
+    Rock/abrasion do not exist in the reference snapshot, so this runs the engine's layered-terrain
+    EXTENSION (parity unpinned) and is reported beside the headline, not as the headline."""
+    import numpy as np
+    import torch
+    from simplewinderosion_b200 import generate
+    rock = generate.pyramid(n, apex=0.5)
+    height = np.maximum(hm, rock).astype(np.float32)
+    w = swe.World(n, device=device)
+    w.set(abrasion=0.1)
+    w.upload(height)
+    w.upload_rock(rock)
+    w.srand(1)
+    for _ in range(2):
+        w.erode(particles, swe.MODE_PARALLEL)
+    w.sync()
+    s0 = w.stats().steps
+    ms = 0.0
+    for _ in range(steps):
+        w.erode(particles, swe.MODE_PARALLEL)
+        ms += w.stats().last_erode_ms
+    out = {"workload": f"cfg3 as named: {n}x{n} FBm dune field over a rock pyramid (base n/4, apex 0.5), abrasion 0.1, "
+                       f"{particles} particles per World::erode; layered-terrain extension, parity unpinned",
+           "value": (w.stats().steps - s0) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps}
+    w.close()
+    torch.cuda.synchronize()
+    return out
+
+
 def run_ours(args) -> None:
     import numpy as np
     import torch
@@ -465,6 +495,8 @@ def run_ours(args) -> None:
                      "note": "104 B/step is SURVEY 8(d)'s figure for flight+cascade; `achieved` charges it "
                              "to the particle kernel alone, `pipeline_*` to particle + per-round cascade kernels"},
     }
+    if world == 1 and not args.skip_layered:
+        line["layered_extension"] = layered_extra(swe, local, n, particles, hm, args.steps)
     if not args.skip_cascade and world == 1:
         line["cascade_roofline"] = cascade_roofline(swe, local, peak, peak_src, args.quick)
     if world == 1 and not args.skip_cpu:
@@ -495,6 +527,7 @@ def main() -> None:
     ap.add_argument("--ref-cycles", type=int, default=4096, help="particles per replica per step, --impl reference")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cascade", action="store_true")
+    ap.add_argument("--skip-layered", action="store_true")
     ap.add_argument("--quick", action="store_true", help="shorter cascade relaxation")
     ap.add_argument("--strong", action="store_true",
                     help="N>1: cut ONE size x size map into N stripes (cfg4: --size 16384 --particles 16777216) "
