@@ -16,8 +16,9 @@
 //
 // Compiled with -fmad=false; arithmetic through swe_exact.cuh.
 #include <cuda.h>
-#include <cstdlib>
 #include <cstring>
+#include <set>
+#include <utility>
 
 #include "swe_exact.cuh"
 
@@ -65,17 +66,8 @@ constexpr int TILE_BX = TILE_TZ / 3 + 8, TILE_BY = 6;       // 80 x 6 = 480 thre
 constexpr int TILE_THREADS = TILE_BX * TILE_BY;
 constexpr int TILE_OX = -2, TILE_OZ = -8;                   // tile grid origin: == 1 (mod 3); z also == 0 (mod 4)
 constexpr int TILE_FLOAT_BYTES = TILE_LX * TILE_PITCH * 4;  // 63,360 B   height tile
-constexpr int TILE_STAMP_BYTES = TILE_LX * TILE_PITCH;      // 15,840 B   stamp tile (stamped sweeps only)
 constexpr int TILE_QUEUE_BYTES = ((TILE_LX / 3) * (TILE_PITCH / 3) * 2 + 15) / 16 * 16;  // centres of one colour
 constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 16;   // + queue counters, mbarrier
-constexpr int TILE_SMEM_STAMPED = TILE_SMEM_PLAIN + TILE_STAMP_BYTES;
-
-#ifdef SWE_TILE_STATS
-__device__ unsigned long long g_tile_stats[4];   // [0] queued centres, [1] generic fallbacks, [2] scanned centres
-#define TILE_STAT(i, n) atomicAdd(&g_tile_stats[i], (unsigned long long)(n))
-#else
-#define TILE_STAT(i, n) ((void)0)
-#endif
 
 __device__ __forceinline__ void cswap_desc(unsigned& a, unsigned& b) {
   const unsigned hi = max(a, b), lo = min(a, b);
@@ -210,7 +202,6 @@ __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, fl
   unsigned close = min(min(k0 ^ k1, (k2 ? k1 ^ k2 : ~0u)), min((k3 ? k2 ^ k3 : ~0u), (k4 ? k3 ^ k4 : ~0u)));
   close = min(close, min(min((k5 ? k4 ^ k5 : ~0u), (k6 ? k5 ^ k6 : ~0u)), (k7 ? k6 ^ k7 : ~0u)));
   if ((INTERIOR || k1) && close < 16u) {
-    TILE_STAT(1, 1);
     tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
     return;
   }
@@ -294,18 +285,15 @@ cascade_commit_kernel(MapView m, RowWindow win, const float* __restrict__ stage,
 //           World::cascade to a shared-memory queue (warp-aggregated append);
 //   relax : the queue is processed densely, one entry per thread.
 // On a map close to the repose angle only a few per cent of the centres reach the queue.
-template <bool USE_STAMP, bool USE_TMA>
+template <bool USE_TMA>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
-                    const unsigned char* __restrict__ stamp, unsigned char stamp_now,
-                    const unsigned* __restrict__ gate, RowWindow win, TileScratch scratch) {
+                    RowWindow win, TileScratch scratch) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  if (USE_STAMP && gate && *gate == 0u) return;
   float* tile = reinterpret_cast<float*>(smem_raw);
   unsigned short* queue = reinterpret_cast<unsigned short*>(smem_raw + TILE_FLOAT_BYTES);
   unsigned* qcount = reinterpret_cast<unsigned*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES);  // [2]
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 8);
-  unsigned char* stile = smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 16;
   const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
   const int sx0 = m.x0, sx1 = m.x0 + m.rows;       // rows present in local storage (a stripe + ghosts)
   const int gx0 = ox0 - 2, gz0 = oz0 - 8;          // global coords of tile[0][0]
@@ -339,28 +327,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       tile[i] = v;
     }
   }
-  if (USE_STAMP) {
-    if (vec_ok) {   // 4 stamps per 32-bit load, whole words are inside or outside the map
-      unsigned* sw = reinterpret_cast<unsigned*>(stile);
-      for (int i = tid; i < TILE_LX * (TILE_PITCH / 4); i += TILE_THREADS) {
-        const int lx = i / (TILE_PITCH / 4), q = i - lx * (TILE_PITCH / 4);
-        const int gx = gx0 + lx, gz = gz0 + 4 * q;
-        unsigned v = 0u;
-        if (gx >= sx0 && gx < sx1 && gz >= 0 && gz < nz)
-          v = __ldcg(reinterpret_cast<const unsigned*>(stamp + m.idx(gx, gz)));
-        sw[i] = v;
-      }
-    } else {
-      for (int i = tid; i < TILE_LX * TILE_PITCH; i += TILE_THREADS) {
-        const int lx = i / TILE_PITCH, lz = i - lx * TILE_PITCH;
-        const int gx = gx0 + lx, gz = gz0 + lz;
-        unsigned char v = 0;
-        if (gx >= sx0 && gx < sx1 && gz >= 0 && gz < nz) v = __ldcg(stamp + m.idx(gx, gz));
-        stile[i] = v;
-      }
-    }
-  }
-  __syncthreads();   // mbarrier init + queue counters visible; plain loads / stamps complete
+  __syncthreads();   // mbarrier init + queue counters visible; plain loads complete
   if (USE_TMA) {
     unsigned done = 0;
     while (!done) {
@@ -376,10 +343,8 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   // which early-out test the scan uses: the refined test costs ~64 more instructions per
   // scanned centre and saves ~250 per centre it keeps out of the queue, so it pays unless more
   // than ~3/4 of the centres pass it. Colour 0 always probes with it; a tile whose refined
-  // queue fills beyond 3/4 falls back to the coarse test for its remaining colours. Stamped
-  // sweeps (flight pipeline) scan only the touched cells, few of which sit at the repose gap:
-  // measured, the coarse test is the faster filter there.
-  bool refined = !USE_STAMP;
+  // queue fills beyond 3/4 falls back to the coarse test for its remaining colours.
+  bool refined = true;
   const unsigned lane = tid & 31;
 #pragma unroll 1
   for (int c = 0; c < 9; c++) {
@@ -396,7 +361,6 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
         const int lx = cxc + 1 + 3 * cxi, gx = gx0 + lx;
         bool need = z_ok && cxi < ncx && (interior || (gx >= 0 && gx < nx));
         const int off = lx * TILE_PITCH + lz;
-        if (USE_STAMP) need = need && stile[need ? off : 0] == stamp_now;
         if (need && !generic_only) {
           const float* tc = tile + off;
           if (interior)
@@ -420,8 +384,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     const unsigned nq = *qc;
     if (tid == 0) qcount[(c + 1) & 1] = 0u;          // the other counter is idle during this phase
     any_change |= nq != 0u;                          // a queued centre always moves sand
-    if (!USE_STAMP) refined = refined && (nq * 4u < (unsigned)(ncx * ncz) * 3u);
-    if (tid == 0) { TILE_STAT(0, nq); TILE_STAT(2, ncx * ncz); }
+    refined = refined && (nq * 4u < (unsigned)(ncx * ncz) * 3u);
     for (unsigned i = tid; i < nq; i += TILE_THREADS) {
       const int off = queue[i];
       float* tc = tile + off;
@@ -686,18 +649,14 @@ bool make_height_tensor_map(const MapView& m, HeightTensorMap* out) {
   return out->valid;
 }
 
-bool g_old_stamped = false;   // debugging switch (SWE_OLD_STAMPED=1): map-driven stamped sweep
-
-template <bool S, bool T>
-static void tile_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, const CUtensorMap& tm,
-                        const MapView& m, float settling, CascadeThr thr, const unsigned char* stamp,
-                        unsigned char now, const unsigned* gate, RowWindow win, TileScratch scratch) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(cascade_tile_kernel<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
-  cascade_tile_kernel<S, T><<<grid, block, smem, st>>>(tm, m, settling, thr, stamp, now, gate, win, scratch);
+// dynamic shared memory above 48 KB needs an opt-in per function and per device
+static void allow_smem(const void* kernel, int bytes) {
+  static std::set<std::pair<int, const void*>> done;   // engines of one process share one host thread at a time
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done.count({dev, kernel})) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done.insert({dev, kernel});
 }
 
 // rows [row_lo, row_hi) are (re)computed and stored; the tiles covering them are launched. On a
@@ -706,8 +665,6 @@ static void tile_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, con
 static void launch_tile_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                               const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
                               int row_lo, int row_hi, TileScratch scratch, cudaStream_t st) {
-  static bool env_read = false;
-  if (!env_read) { env_read = true; const char* v = getenv("SWE_OLD_STAMPED"); g_old_stamped = v && v[0] == '1'; }
   CascadeThr thr;
   thr.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;      // host IEEE fp32: same values as the device helper
   thr.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
@@ -723,21 +680,22 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
   const bool tma = tmap && tmap->valid;
   CUtensorMap tm;
   if (tma) memcpy(&tm, tmap->opaque, sizeof tm); else memset(&tm, 0, sizeof tm);
-  if (stamp && g_old_stamped) {
-    if (tma) tile_launch<true, true>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
-    else     tile_launch<true, false>(grid, block, TILE_SMEM_STAMPED, st, tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
-  } else if (stamp) {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(cascade_tile_stamped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAMPED_SMEM);
-      cudaFuncSetAttribute(cascade_tile_stamped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAMPED_SMEM);
-      attr = true;
+  if (stamp) {
+    if (tma) {
+      allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<true>), STAMPED_SMEM);
+      cascade_tile_stamped_kernel<true><<<grid, block, STAMPED_SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
+    } else {
+      allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<false>), STAMPED_SMEM);
+      cascade_tile_stamped_kernel<false><<<grid, block, STAMPED_SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
     }
-    if (tma) cascade_tile_stamped_kernel<true><<<grid, block, STAMPED_SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
-    else     cascade_tile_stamped_kernel<false><<<grid, block, STAMPED_SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
   } else {
-    if (tma) tile_launch<false, true>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr, win, scratch);
-    else     tile_launch<false, false>(grid, block, TILE_SMEM_PLAIN, st, tm, m, p.settling, thr, nullptr, 0, nullptr, win, scratch);
+    if (tma) {
+      allow_smem(reinterpret_cast<const void*>(&cascade_tile_kernel<true>), TILE_SMEM_PLAIN);
+      cascade_tile_kernel<true><<<grid, block, TILE_SMEM_PLAIN, st>>>(tm, m, p.settling, thr, win, scratch);
+    } else {
+      allow_smem(reinterpret_cast<const void*>(&cascade_tile_kernel<false>), TILE_SMEM_PLAIN);
+      cascade_tile_kernel<false><<<grid, block, TILE_SMEM_PLAIN, st>>>(tm, m, p.settling, thr, win, scratch);
+    }
   }
   cascade_commit_kernel<<<grid, 256, 0, st>>>(m, win, scratch.stage, scratch.flags);
 }
@@ -776,14 +734,6 @@ int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTens
   return launches + 1;
 }
 
-#ifdef SWE_TILE_STATS
-extern "C" void swe_debug_tile_stats(unsigned long long* out4, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(unsigned long long) * 4);
-  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_tile_stats, z, sizeof z); }
-}
-#endif
-
 void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st) {
   set_float_kernel<<<1, 1, 0, st>>>(d_out, -INFINITY);
   const size_t n = (size_t)m.rows * m.nz;
@@ -797,8 +747,8 @@ void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cuda
 void preload_cascade() {
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, cascade_colour_kernel);
-  cudaFuncGetAttributes(&a, cascade_tile_kernel<false, false>);
-  cudaFuncGetAttributes(&a, cascade_tile_kernel<false, true>);
+  cudaFuncGetAttributes(&a, cascade_tile_kernel<false>);
+  cudaFuncGetAttributes(&a, cascade_tile_kernel<true>);
   cudaFuncGetAttributes(&a, cascade_tile_stamped_kernel<false>);
   cudaFuncGetAttributes(&a, cascade_tile_stamped_kernel<true>);
   cudaFuncGetAttributes(&a, cascade_commit_kernel);

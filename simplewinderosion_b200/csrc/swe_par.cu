@@ -139,9 +139,7 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
   q.px += sx; q.py += sy; q.pz += sz;                                             // :91
   q.sx = sx; q.sy = sy; q.sz = sz;
 
-#ifndef SWE_EXP_NO_TRACK
   red_add_v4(m.track + ci, q.sed, sx, sy, sz);                                    // :93-96
-#endif
   {
     const float len = sqrtf(sx * sx + sy * sy + sz * sz);
     const float force = fmaxf(-(sx * nxv + sy * nyv + sz * nzv), 0.0f);           // :100-102
@@ -176,9 +174,7 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
       if (dh != 0.0f) red_add_f32(hc_ptr, -dh);
     }
   }
-#ifndef SWE_EXP_NO_STAMP
   stamp[ci] = stamp_now;                                                          // :114 (deferred)
-#endif
   return 0;
 }
 
