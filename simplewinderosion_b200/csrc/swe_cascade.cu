@@ -220,29 +220,31 @@ __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, fl
 // R_0 covers, 20 % of the tile) are therefore written to a staging plane and copied into place
 // by cascade_commit_kernel after the sweep kernel has finished; the interior of O, which no other
 // tile reads, goes straight to the height plane.
+template <int TX>
 __device__ __forceinline__ bool tile_border(int ox, int oz) {
-  return ox < 4 || ox >= TILE_TX - 2 || oz < 16 || oz >= TILE_TZ - 8;
+  return ox < 4 || ox >= TX - 2 || oz < 16 || oz >= TILE_TZ - 8;
 }
 
+template <int TX, int NTHREADS>
 __device__ __forceinline__ void tile_store(const float* tile, const MapView& m, const RowWindow& win,
                                            float* __restrict__ stage, int ox0, int oz0, int tid, bool vec_ok) {
   const int nz = m.nz;
   if (vec_ok) {
-    for (int i = tid; i < TILE_TX * (TILE_TZ / 4); i += TILE_THREADS) {
+    for (int i = tid; i < TX * (TILE_TZ / 4); i += NTHREADS) {
       const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);
       const int gx = ox0 + ox, gz = oz0 + 4 * q;
       if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz) {
-        float* dst = tile_border(ox, 4 * q) ? stage : m.height;
+        float* dst = tile_border<TX>(ox, 4 * q) ? stage : m.height;
         *reinterpret_cast<float4*>(dst + m.idx(gx, gz)) =
             *reinterpret_cast<const float4*>(tile + (ox + 2) * TILE_PITCH + 8 + 4 * q);
       }
     }
   } else {
-    for (int i = tid; i < TILE_TX * TILE_TZ; i += TILE_THREADS) {
+    for (int i = tid; i < TX * TILE_TZ; i += NTHREADS) {
       const int ox = i / TILE_TZ, oz = i - ox * TILE_TZ;
       const int gx = ox0 + ox, gz = oz0 + oz;
       if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz) {
-        float* dst = tile_border(ox, oz) ? stage : m.height;
+        float* dst = tile_border<TX>(ox, oz) ? stage : m.height;
         dst[m.idx(gx, gz)] = tile[(ox + 2) * TILE_PITCH + (oz + 8)];
       }
     }
@@ -250,25 +252,26 @@ __device__ __forceinline__ void tile_store(const float* tile, const MapView& m, 
 }
 
 // copies the staged border cells of every tile that changed into the height plane
+template <int TX>
 __global__ void __launch_bounds__(256)
 cascade_commit_kernel(MapView m, RowWindow win, const float* __restrict__ stage, unsigned char* __restrict__ flags) {
   const int tile_id = (win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x;
   if (!flags[tile_id]) return;
-  const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
+  const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
   const int nz = m.nz;
   const bool vec_ok = (nz & 3) == 0;
   if (vec_ok) {
-    for (int i = threadIdx.x; i < TILE_TX * (TILE_TZ / 4); i += 256) {
+    for (int i = threadIdx.x; i < TX * (TILE_TZ / 4); i += 256) {
       const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);
-      if (!tile_border(ox, 4 * q)) continue;
+      if (!tile_border<TX>(ox, 4 * q)) continue;
       const int gx = ox0 + ox, gz = oz0 + 4 * q;
       if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz)
         *reinterpret_cast<float4*>(m.height + m.idx(gx, gz)) = *reinterpret_cast<const float4*>(stage + m.idx(gx, gz));
     }
   } else {
-    for (int i = threadIdx.x; i < TILE_TX * TILE_TZ; i += 256) {
+    for (int i = threadIdx.x; i < TX * TILE_TZ; i += 256) {
       const int ox = i / TILE_TZ, oz = i - ox * TILE_TZ;
-      if (!tile_border(ox, oz)) continue;
+      if (!tile_border<TX>(ox, oz)) continue;
       const int gx = ox0 + ox, gz = oz0 + oz;
       if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz) m.height[m.idx(gx, gz)] = stage[m.idx(gx, gz)];
     }
@@ -405,7 +408,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
 
   // ---- store O if anything in this tile moved -----------------------------------------------
   if (any_change) {                                  // CTA-uniform (derived from shared counters)
-    tile_store(tile, m, win, scratch.stage, ox0, oz0, tid, vec_ok);
+    tile_store<TILE_TX, TILE_THREADS>(tile, m, win, scratch.stage, ox0, oz0, tid, vec_ok);
     if (tid == 0) scratch.flags[(win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x] = 1;
   }
 }
@@ -420,16 +423,29 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
 // too: their blocks do not reach the cells the tile stores (they would have been in R_c), so
 // this only costs a few redundant cascades.
 // =============================================================================================
-constexpr int STAMPED_QCAP = (TILE_LX / 3) * (TILE_PITCH / 3);            // centres of one colour in the tile
-constexpr int STAMPED_SMEM = TILE_FLOAT_BYTES + 10 * STAMPED_QCAP * 2 + 96;
+// The stamped sweep spends most of its time waiting at the 18 barriers of a tile with only a few
+// warps busy (relax of a few hundred centres), so it uses HALF-HEIGHT tiles (30 x 216 outputs,
+// 256 threads, 53 KB): four CTAs per SM instead of two hide each other's barrier phases. The
+// extra halo (1.33x instead of 1.22x) only costs redundant work where particles were.
+constexpr int STAMPED_TX = 30;
+template <int TX> struct StampedGeo {
+  static constexpr int LX = TX + 6;
+  static constexpr int THREADS = (TX <= 30) ? 256 : 480;               // queue-driven: a flat block, whole warps
+  static constexpr int FLOAT_BYTES = LX * TILE_PITCH * 4;
+  static constexpr int QCAP = ((LX + 2) / 3) * (TILE_PITCH / 3);          // centres of one colour in the tile
+  static constexpr int SMEM = FLOAT_BYTES + 10 * QCAP * 2 + 96;
+};
 
-template <bool USE_TMA>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+template <int TX, bool USE_TMA>
+__global__ void __launch_bounds__(StampedGeo<TX>::THREADS, (TX <= 30) ? 4 : 2)
 cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
                             const unsigned char* __restrict__ stamp, unsigned char stamp_now,
                             const unsigned* __restrict__ gate, RowWindow win, TileScratch scratch) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (gate && *gate == 0u) return;
+  constexpr int TILE_LX = StampedGeo<TX>::LX, TILE_THREADS = StampedGeo<TX>::THREADS;     // shadow the 60-row geometry
+  constexpr int TILE_FLOAT_BYTES = StampedGeo<TX>::FLOAT_BYTES, STAMPED_QCAP = StampedGeo<TX>::QCAP;
+  constexpr int TILE_TX = TX;
   float* tile = reinterpret_cast<float*>(smem_raw);
   unsigned short* cq = reinterpret_cast<unsigned short*>(smem_raw + TILE_FLOAT_BYTES);   // [9][QCAP] by colour
   unsigned short* rq = cq + 9 * STAMPED_QCAP;                                              // relax queue
@@ -579,7 +595,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
   }
 
   if (any_change) {
-    tile_store(tile, m, win, scratch.stage, ox0, oz0, tid, vec_ok);
+    tile_store<TX, TILE_THREADS>(tile, m, win, scratch.stage, ox0, oz0, tid, vec_ok);
     if (tid == 0) scratch.flags[(win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x] = 1;
   }
 }
@@ -639,13 +655,18 @@ bool make_height_tensor_map(const MapView& m, HeightTensorMap* out) {
   static_assert(sizeof(CUtensorMap) == sizeof(out->opaque), "tensor map size");
   const cuuint64_t dims[2] = {(cuuint64_t)m.nz, (cuuint64_t)m.rows};
   const cuuint64_t strides[1] = {(cuuint64_t)m.nz * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)TILE_PITCH, (cuuint32_t)TILE_LX};
   const cuuint32_t estr[2] = {1, 1};
+  const cuuint32_t box[2] = {(cuuint32_t)TILE_PITCH, (cuuint32_t)TILE_LX};                       // whole-map sweeps
+  const cuuint32_t box_s[2] = {(cuuint32_t)TILE_PITCH, (cuuint32_t)StampedGeo<STAMPED_TX>::LX};  // stamped sweeps
   const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out->opaque), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                             m.height, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  out->valid = (r == CUDA_SUCCESS);
+  const CUresult r2 = encode(reinterpret_cast<CUtensorMap*>(out->opaque_small), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                             m.height, dims, strides, box_s, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  out->valid = (r == CUDA_SUCCESS && r2 == CUDA_SUCCESS);
   return out->valid;
 }
 
@@ -671,24 +692,28 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
   if (row_lo < 0) row_lo = 0;
   if (row_hi > m.nx) row_hi = m.nx;
   if (row_hi <= row_lo) return;
+  const int tx = stamp ? STAMPED_TX : TILE_TX;     // output rows per tile of the kernel used
   RowWindow win;
   win.store_lo = row_lo; win.store_hi = row_hi;
-  win.tile_y0 = (row_lo - TILE_OX) / TILE_TX;
-  const int tile_y1 = (row_hi - 1 - TILE_OX) / TILE_TX;
+  win.tile_y0 = (row_lo - TILE_OX) / tx;
+  const int tile_y1 = (row_hi - 1 - TILE_OX) / tx;
   const dim3 grid((m.nz - TILE_OZ + TILE_TZ - 1) / TILE_TZ, tile_y1 - win.tile_y0 + 1);
-  const dim3 block(TILE_BX, TILE_BY);
   const bool tma = tmap && tmap->valid;
   CUtensorMap tm;
-  if (tma) memcpy(&tm, tmap->opaque, sizeof tm); else memset(&tm, 0, sizeof tm);
+  if (tma) memcpy(&tm, stamp ? tmap->opaque_small : tmap->opaque, sizeof tm); else memset(&tm, 0, sizeof tm);
   if (stamp) {
+    using G = StampedGeo<STAMPED_TX>;
+    const dim3 block(G::THREADS, 1);
     if (tma) {
-      allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<true>), STAMPED_SMEM);
-      cascade_tile_stamped_kernel<true><<<grid, block, STAMPED_SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
+      allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<STAMPED_TX, true>), G::SMEM);
+      cascade_tile_stamped_kernel<STAMPED_TX, true><<<grid, block, G::SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
     } else {
-      allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<false>), STAMPED_SMEM);
-      cascade_tile_stamped_kernel<false><<<grid, block, STAMPED_SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
+      allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<STAMPED_TX, false>), G::SMEM);
+      cascade_tile_stamped_kernel<STAMPED_TX, false><<<grid, block, G::SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
     }
+    cascade_commit_kernel<STAMPED_TX><<<grid, 256, 0, st>>>(m, win, scratch.stage, scratch.flags);
   } else {
+    const dim3 block(TILE_BX, TILE_BY);
     if (tma) {
       allow_smem(reinterpret_cast<const void*>(&cascade_tile_kernel<true>), TILE_SMEM_PLAIN);
       cascade_tile_kernel<true><<<grid, block, TILE_SMEM_PLAIN, st>>>(tm, m, p.settling, thr, win, scratch);
@@ -696,8 +721,8 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
       allow_smem(reinterpret_cast<const void*>(&cascade_tile_kernel<false>), TILE_SMEM_PLAIN);
       cascade_tile_kernel<false><<<grid, block, TILE_SMEM_PLAIN, st>>>(tm, m, p.settling, thr, win, scratch);
     }
+    cascade_commit_kernel<TILE_TX><<<grid, 256, 0, st>>>(m, win, scratch.stage, scratch.flags);
   }
-  cascade_commit_kernel<<<grid, 256, 0, st>>>(m, win, scratch.stage, scratch.flags);
 }
 
 void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
@@ -707,7 +732,8 @@ void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightT
 }
 
 size_t tile_flag_count(const MapView& m) {
-  return (size_t)((m.nz - TILE_OZ + TILE_TZ - 1) / TILE_TZ) * (size_t)((m.nx - TILE_OX + TILE_TX - 1) / TILE_TX);
+  // sized for the finer of the two tile grids (stamped sweeps use half-height tiles)
+  return (size_t)((m.nz - TILE_OZ + TILE_TZ - 1) / TILE_TZ) * (size_t)((m.nx - TILE_OX + STAMPED_TX - 1) / STAMPED_TX);
 }
 
 int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap, int sweeps,
@@ -749,9 +775,10 @@ void preload_cascade() {
   cudaFuncGetAttributes(&a, cascade_colour_kernel);
   cudaFuncGetAttributes(&a, cascade_tile_kernel<false>);
   cudaFuncGetAttributes(&a, cascade_tile_kernel<true>);
-  cudaFuncGetAttributes(&a, cascade_tile_stamped_kernel<false>);
-  cudaFuncGetAttributes(&a, cascade_tile_stamped_kernel<true>);
-  cudaFuncGetAttributes(&a, cascade_commit_kernel);
+  cudaFuncGetAttributes(&a, cascade_tile_stamped_kernel<STAMPED_TX, false>);
+  cudaFuncGetAttributes(&a, cascade_tile_stamped_kernel<STAMPED_TX, true>);
+  cudaFuncGetAttributes(&a, cascade_commit_kernel<TILE_TX>);
+  cudaFuncGetAttributes(&a, cascade_commit_kernel<STAMPED_TX>);
   cudaFuncGetAttributes(&a, max_excess_kernel);
   cudaFuncGetAttributes(&a, set_float_kernel);
   cudaFuncGetAttributes(&a, add_cascade_cells_kernel);

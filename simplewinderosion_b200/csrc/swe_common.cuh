@@ -83,7 +83,8 @@ size_t tile_flag_count(const MapView& m);
 
 // TMA descriptor of the height plane (CUtensorMap, kept opaque here), built once per engine.
 struct alignas(64) HeightTensorMap {
-  unsigned char opaque[128];
+  alignas(64) unsigned char opaque[128];        // box of the whole-map sweep tiles
+  alignas(64) unsigned char opaque_small[128];  // box of the half-height stamped-sweep tiles
   bool valid;
 };
 bool make_height_tensor_map(const MapView& m, HeightTensorMap* out);
