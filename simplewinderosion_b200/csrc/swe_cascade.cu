@@ -477,7 +477,41 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
     const unsigned slot = atomicAdd(&cnt[c], 1u);
     cq[c * STAMPED_QCAP + slot] = (unsigned short)(lx * TILE_PITCH + lz);
   };
-  if (vec_ok) {
+  if ((nz & 7) == 0) {
+    // 8 stamps per 64-bit load (rows are 8-byte aligned and every tile's z origin, -16 + 216 j, is
+    // == 0 mod 8); all loads of a thread are issued before any is inspected, and a word is only
+    // taken apart if the "has a zero byte" test says one of its stamps matches
+    const unsigned pat = 0x01010101u * stamp_now;
+    constexpr int QPR = TILE_PITCH / 8;                       // 30 uint2 per tile row
+    constexpr int NV = TILE_LX * QPR;
+    constexpr int PER = (NV + TILE_THREADS - 1) / TILE_THREADS;
+    uint2 v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int i = tid + k * TILE_THREADS;
+      const int lx = i / QPR, q = i - lx * QPR;
+      const int gx = gx0 + lx, gz = gz0 + 8 * q;
+      v[k] = make_uint2(~pat, ~pat);
+      if (i < NV && gx >= sx0 && gx < sx1 && gx >= 0 && gx < nx && gz >= 0 && gz < nz)
+        v[k] = __ldcg(reinterpret_cast<const uint2*>(stamp + m.idx(gx, gz)));
+    }
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int i = tid + k * TILE_THREADS;
+      const int lx = i / QPR, q = i - lx * QPR;
+      const unsigned w2[2] = {v[k].x ^ pat, v[k].y ^ pat};
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const unsigned x = w2[j];
+        if (((x - 0x01010101u) & ~x & 0x80808080u) == 0u) continue;   // no byte of x is zero
+        const int lz = 8 * q + 4 * j;
+        if ((x & 0x000000ffu) == 0u) push(lx, lz);
+        if ((x & 0x0000ff00u) == 0u) push(lx, lz + 1);
+        if ((x & 0x00ff0000u) == 0u) push(lx, lz + 2);
+        if ((x & 0xff000000u) == 0u) push(lx, lz + 3);
+      }
+    }
+  } else if (vec_ok) {
     const unsigned pat = 0x01010101u * stamp_now;
     for (int i = tid; i < TILE_LX * (TILE_PITCH / 4); i += TILE_THREADS) {
       const int lx = i / (TILE_PITCH / 4), q = i - lx * (TILE_PITCH / 4);
