@@ -575,6 +575,38 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
     if (nc == 0u) continue;                        // CTA-uniform
     unsigned* qc = cnt + 9 + c;                    // one relax counter per colour: no reset races
     const unsigned short* mine = cq + c * STAMPED_QCAP;
+    if (nc <= 64u) {
+      // sparse tile (few particles per tile, e.g. 16384^2 with 0.06 particles/cell): test and
+      // relax in one pass on at most two warps -- one barrier per colour instead of two, no queue
+      if ((unsigned)tid < nc) {
+        const int off = mine[tid];
+        const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
+        const int cxi3 = lx - (c / 3) - 1, czi3 = lz - c - 1;
+        const int gx = gx0 + lx, gz = gz0 + lz;
+        if (cxi3 >= 0 && cxi3 < 3 * (TILE_TX / 3 + 2 - c / 3) && czi3 >= 0 && czi3 < 3 * (TILE_TZ / 3 + 8 - c) &&
+            gx >= 0 && gx < nx && gz >= 0 && gz < nz) {
+          float* tc = tile + off;
+          if (m.rock) {
+            any_change |= tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, m.rock + m.idx(gx, gz));
+          } else if (generic_only) {
+            any_change |= tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
+          } else if (interior) {
+            if (centre_needs<true, false>(tc, thr, hs, centre_valid<true>(1, 1, 3, 3))) {
+              centre_relax<true>(tc, thr, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
+              any_change = true;
+            }
+          } else {
+            const Valid8 v = centre_valid<false>(gx, gz, nx, nz);
+            if (centre_needs<false, false>(tc, thr, hs, v)) {
+              centre_relax<false>(tc, thr, settling, hs, v, gx, gz, nx, nz);
+              any_change = true;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      continue;
+    }
     // ---- scan: early-out test, dense over the touched centres of this colour -----------------
     for (unsigned base_i = 0; base_i < nc; base_i += TILE_THREADS) {
       const unsigned i = base_i + tid;
@@ -628,7 +660,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
     __syncthreads();
   }
 
-  if (any_change) {
+  if (__syncthreads_or(any_change ? 1 : 0)) {        // per-thread flags in the sparse path
     tile_store<TX, TILE_THREADS>(tile, m, win, scratch.stage, ox0, oz0, tid, vec_ok);
     if (tid == 0) scratch.flags[(win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x] = 1;
   }
