@@ -166,26 +166,36 @@ __device__ __forceinline__ unsigned height_key(float h, bool valid, unsigned cod
 
 // one element of the transfer chain (world.hpp:122-151), branch-free; thresholds >= 0 so that
 // diff == 0 implies excess <= 0 and the reference's explicit diff == 0 test is subsumed.
+// LAYERED (extension): the transfer is capped by the giving cell's sand, height - rock.
+template <bool LAYERED>
 __device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, const CascadeThr thr,
-                                           float settling) {
+                                           float settling, const float* rock_c_ptr, int nz, float rock_c) {
   const unsigned code = 15u - (k & 15u);
-  float* hp = tc + ((int)(code >> 2) - 1) * TILE_PITCH + ((int)(code & 3u) - 1);
+  const int dxm = (int)(code >> 2) - 1, dzm = (int)(code & 3u) - 1;
+  float* hp = tc + dxm * TILE_PITCH + dzm;
   const float hv = *hp;
   const float t = (code & 5u) ? thr.ortho : thr.diag;
   const float diff = fsub(cc, hv);
   const float excess = fsub(fabsf(diff), t);
-  const bool go = (k != 0u) && !(excess <= 0.0f);
+  bool go = (k != 0u) && !(excess <= 0.0f);
   // (settling*excess)/2.0f == excess*(settling/2): halving is exact and commutes with the
   // rounding of the product (sub-normal products excluded: tiny thresholds use the generic core)
-  const float transfer = fmul(excess, settling);                 // settling: already halved
+  float transfer = fmul(excess, settling);                       // settling: already halved
+  if (LAYERED) {
+    const float rk = (k != 0u) ? __ldg(rock_c_ptr + dxm * nz + dzm) : 0.0f;
+    const float sand = (diff > 0.0f) ? fsub(cc, rock_c) : fsub(hv, rk);
+    transfer = fminf(transfer, fmaxf(sand, 0.0f));
+    go = go && (transfer > 0.0f);
+  }
   const float sgn = (diff > 0.0f) ? transfer : -transfer;        // diff > 0: centre gives, else takes
   if (go) { cc = fsub(cc, sgn); *hp = fadd(hv, sgn); }
 }
 
 // World::cascade at one centre of the tile whose early-out test failed.
-template <bool INTERIOR>
+template <bool INTERIOR, bool LAYERED = false>
 __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, float settling, float hs,
-                                             const Valid8 v, int gx, int gz, int nx, int nz) {
+                                             const Valid8 v, int gx, int gz, int nx, int nz,
+                                             const float* rock_c_ptr = nullptr) {
   unsigned k0 = height_key(tc[-TILE_PITCH - 1], v.v0, 0), k1 = height_key(tc[-TILE_PITCH], v.v1, 1),
            k2 = height_key(tc[-TILE_PITCH + 1], v.v2, 2), k3 = height_key(tc[-1], v.v3, 4),
            k4 = height_key(tc[1], v.v4, 6), k5 = height_key(tc[TILE_PITCH - 1], v.v5, 8),
@@ -202,14 +212,16 @@ __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, fl
   unsigned close = min(min(k0 ^ k1, (k2 ? k1 ^ k2 : ~0u)), min((k3 ? k2 ^ k3 : ~0u), (k4 ? k3 ^ k4 : ~0u)));
   close = min(close, min(min((k5 ? k4 ^ k5 : ~0u), (k6 ? k5 ^ k6 : ~0u)), (k7 ? k6 ^ k7 : ~0u)));
   if ((INTERIOR || k1) && close < 16u) {
-    tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
+    tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, LAYERED ? rock_c_ptr : nullptr);
     return;
   }
   float cc = tc[0];
-  chain_step(tc, k0, cc, thr, hs); chain_step(tc, k1, cc, thr, hs);
-  chain_step(tc, k2, cc, thr, hs); chain_step(tc, k3, cc, thr, hs);
-  chain_step(tc, k4, cc, thr, hs); chain_step(tc, k5, cc, thr, hs);
-  chain_step(tc, k6, cc, thr, hs); chain_step(tc, k7, cc, thr, hs);
+  const float rock_c = LAYERED ? __ldg(rock_c_ptr) : 0.0f;
+  const int rnz = nz;
+  chain_step<LAYERED>(tc, k0, cc, thr, hs, rock_c_ptr, rnz, rock_c); chain_step<LAYERED>(tc, k1, cc, thr, hs, rock_c_ptr, rnz, rock_c);
+  chain_step<LAYERED>(tc, k2, cc, thr, hs, rock_c_ptr, rnz, rock_c); chain_step<LAYERED>(tc, k3, cc, thr, hs, rock_c_ptr, rnz, rock_c);
+  chain_step<LAYERED>(tc, k4, cc, thr, hs, rock_c_ptr, rnz, rock_c); chain_step<LAYERED>(tc, k5, cc, thr, hs, rock_c_ptr, rnz, rock_c);
+  chain_step<LAYERED>(tc, k6, cc, thr, hs, rock_c_ptr, rnz, rock_c); chain_step<LAYERED>(tc, k7, cc, thr, hs, rock_c_ptr, rnz, rock_c);
   tc[0] = cc;
 }
 
@@ -397,8 +409,11 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       } else {
         const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
         const int gx = gx0 + lx, gz = gz0 + lz;
-        if (m.rock)     // layered extension (single-GPU engines): sand-limited transfers, generic core
-          tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, m.rock + m.idx(gx, gz));
+        if (m.rock) {   // layered extension (single-GPU engines): sand-limited transfers
+          const float* rp = m.rock + m.idx(gx, gz);
+          if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, rp);
+          else centre_relax<false, true>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz, rp);
+        }
         else if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
         else centre_relax<false>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
       }
@@ -586,7 +601,13 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
         if (cxi3 >= 0 && cxi3 < 3 * (TILE_TX / 3 + 2 - c / 3) && czi3 >= 0 && czi3 < 3 * (TILE_TZ / 3 + 8 - c) &&
             gx >= 0 && gx < nx && gz >= 0 && gz < nz) {
           float* tc = tile + off;
-          if (m.rock) {
+          if (m.rock && !generic_only) {
+            const Valid8 v = centre_valid<false>(gx, gz, nx, nz);
+            if (centre_needs<false, false>(tc, thr, hs, v)) {
+              centre_relax<false, true>(tc, thr, settling, hs, v, gx, gz, nx, nz, m.rock + m.idx(gx, gz));
+              any_change = true;
+            }
+          } else if (m.rock) {
             any_change |= tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, m.rock + m.idx(gx, gz));
           } else if (generic_only) {
             any_change |= tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
@@ -651,8 +672,11 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
       } else {
         const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
         const int gx = gx0 + lx, gz = gz0 + lz;
-        if (m.rock)     // layered extension (single-GPU engines): sand-limited transfers, generic core
-          tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, m.rock + m.idx(gx, gz));
+        if (m.rock) {   // layered extension (single-GPU engines): sand-limited transfers
+          const float* rp = m.rock + m.idx(gx, gz);
+          if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, rp);
+          else centre_relax<false, true>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz, rp);
+        }
         else if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
         else centre_relax<false>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
       }
