@@ -415,7 +415,7 @@ def run_ours(args) -> None:
         fly_steps += s.steps - s_before
     w.set_option(swe.OPT_KERNEL_TIMING, 0)
     rounds_per_call = w.params.max_age + 2
-    if round_ms <= 0.0:          # stripe engines do not break the step down per kernel
+    if round_ms <= 0.0:
         round_ms = casc_ms = fly_ms / 2
     achieved = BYTES_PER_STEP * fly_steps / (round_ms * 1e-3) / 1e9
     pipeline = BYTES_PER_STEP * fly_steps / ((round_ms + casc_ms) * 1e-3) / 1e9
@@ -490,7 +490,8 @@ def run_ours(args) -> None:
                      "launches_per_step": rounds_per_call,
                      "kernel_ms_per_launch": round_ms / args.steps / rounds_per_call,
                      "share_of_step": {"par_round_kernel": round_ms / fly_ms,
-                                       "cascade_tile_kernel(stamped)": casc_ms / fly_ms},
+                                       ("cascade_tile_stamped_kernel+commit" if world == 1 else
+                                        "halo exchange+hand-off+cascade"): casc_ms / fly_ms},
                      "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
                      "note": "104 B/step is SURVEY 8(d)'s figure for flight+cascade; `achieved` charges it "
                              "to the particle kernel alone, `pipeline_*` to particle + per-round cascade kernels"},

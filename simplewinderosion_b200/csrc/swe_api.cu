@@ -79,6 +79,7 @@ struct swe_engine {
   int opt_kernel_timing = 0;          // record an event pair around every round / cascade launch
   std::vector<cudaEvent_t> kt_events; // [3*r] before round, [3*r+1] between, [3*r+2] after cascade
   int kt_rounds = 0;
+  int kt_rounds_pending = 0;          // stripe rounds recorded so far in the current call
   double last_round_ms = 0.0, last_cascade_ms = 0.0;
   uint64_t launches = 0, erode_calls = 0;
   double last_erode_ms = 0.0, last_sweep_ms = 0.0, last_fly_ms = 0.0;
@@ -254,6 +255,7 @@ StripeRound stripe_round_ctx(swe_engine* e) {
 }
 
 int stripe_erode_begin(swe_engine* e, int cycles) {
+  e->kt_rounds_pending = 0;
   launch_par_begin_stripe(e->pbuf, stripe_round_ctx(e), e->m, cycles, e->seed, e->call_index, e->d_stats,
                           e->stream);
   return check_launch(e, "stripe begin", 3);
@@ -271,10 +273,19 @@ int stripe_erode_round(swe_engine* e) {
   StripeRound sr = stripe_round_ctx(e);
   if (S.has_below) sr.below = arena_inbox(S.below.arena, S.inbox_capacity, FROM_ABOVE, parity);
   if (S.has_above) sr.above = arena_inbox(S.above.arena, S.inbox_capacity, FROM_BELOW, parity);
+  const bool kt = e->opt_kernel_timing != 0;
+  const int r = e->kt_rounds_pending;
+  if (kt) {
+    while ((int)e->kt_events.size() < 3 * (r + 1)) {
+      cudaEvent_t ev; SWE_CUDA(cudaEventCreate(&ev)); e->kt_events.push_back(ev);
+    }
+    SWE_CUDA(cudaEventRecord(e->kt_events[3 * r], e->stream));
+  }
   // particles must be handed over before they step again: one step per round
   launch_par_round_stripe(e->pbuf, sr, e->m, e->p, 1, e->seed, e->call_index, e->d_stamp, now, e->d_stats,
                           e->stream);
   nl += 1;
+  if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
   const unsigned s = stripe_exchange_begin(e, true, &nl);
   for (int dir = 0; dir < 2; dir++) {
     if ((dir == FROM_BELOW && !S.has_below) || (dir == FROM_ABOVE && !S.has_above)) continue;
@@ -288,6 +299,10 @@ int stripe_erode_round(swe_engine* e) {
                          e->stream);
   nl += 2;
   stripe_exchange_end(e, s, &nl);
+  if (kt) {   // "cascade" share of a stripe round = exchange + merge + cascade
+    SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 2], e->stream));
+    e->kt_rounds_pending = r + 1; e->kt_rounds = r + 1;
+  }
   return check_launch(e, "stripe round", nl);
 }
 

@@ -23,3 +23,6 @@ elif what == "cascade8192relaxed":
 elif what == "cascade4096conv":
     w = swe.World(4096); w.upload(generate.random_slopes(4096))
     w.cascade_sweep(164); w.sync(); print(w.stats().last_sweep_ms / 164)
+elif what == "cascade8192long":
+    w = swe.World(8192); w.upload(generate.random_slopes(8192))
+    w.cascade_sweep(44); w.sync(); print(w.stats().last_sweep_ms / 44)
