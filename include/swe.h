@@ -76,7 +76,10 @@ typedef enum swe_option {
   SWE_OPT_CASCADE_INTERVAL = 2,
   /* 1 = record CUDA events around every particle-round and cascade launch of swe_erode so that
    * swe_stats.last_round_ms / last_cascade_ms report each kernel's share (default 0). */
-  SWE_OPT_KERNEL_TIMING = 3
+  SWE_OPT_KERNEL_TIMING = 3,
+  /* 1 (default) = a parallel swe_erode on a single-GPU engine is captured once per (cycles, params,
+   * options) as a CUDA graph of ~1550 nodes and replayed; 0 = launch kernel by kernel. */
+  SWE_OPT_CUDA_GRAPH = 4
 } swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:

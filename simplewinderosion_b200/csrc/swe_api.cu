@@ -77,6 +77,10 @@ struct swe_engine {
   int opt_cascade_variant = 0;        // 0 fused tile kernel, 1 per-colour launches
   int opt_cascade_interval = 1;       // Wind::fly steps per particle between cascade passes
   int opt_kernel_timing = 0;          // record an event pair around every round / cascade launch
+  int opt_cuda_graph = 1;             // replay the parallel erode of a single-GPU engine as one CUDA graph
+  CallCtl* d_ctl = nullptr;           // seed / call index of the current call (read by graph-replayed kernels)
+  struct CachedGraph { uint64_t key; cudaGraphExec_t exec; };
+  std::vector<CachedGraph> graphs;
   std::vector<cudaEvent_t> kt_events; // [3*r] before round, [3*r+1] between, [3*r+2] after cascade
   int kt_rounds = 0;
   int kt_rounds_pending = 0;          // stripe rounds recorded so far in the current call
@@ -306,6 +310,97 @@ int stripe_erode_round(swe_engine* e) {
   return check_launch(e, "stripe round", nl);
 }
 
+// The particle phase of a single-GPU parallel World::erode: spawn, then R rounds of
+// [particle step kernel, stamped cascade, commit]. Stamp values are per call: round r uses
+// 1 + r % 255 and the plane is cleared whenever the value wraps, so the launch sequence depends only
+// on (cycles, params, options) and can be captured once and replayed (ctl != nullptr).
+int parallel_rounds(swe_engine* e, int cycles, const CallCtl* ctl) {
+  const int k = e->opt_cascade_interval;
+  const int rounds = (e->p.max_age + 2 + k - 1) / k;   // every particle is dead after maxAge+2 calls
+  launch_par_begin(e->pbuf, e->m, cycles, e->seed, e->call_index, ctl, e->d_stats, e->stream);
+  if (int rc = check_launch(e, "par_begin", 2)) return rc;
+  const bool kt = e->opt_kernel_timing != 0 && ctl == nullptr;
+  for (int r = 0; r < rounds; r++) {
+    if (r % 255 == 0) SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
+    const unsigned char now = (unsigned char)(1 + r % 255);
+    if (kt) {
+      while ((int)e->kt_events.size() < 3 * (r + 1)) {
+        cudaEvent_t ev; SWE_CUDA(cudaEventCreate(&ev)); e->kt_events.push_back(ev);
+      }
+      SWE_CUDA(cudaEventRecord(e->kt_events[3 * r], e->stream));
+    }
+    launch_par_round(e->pbuf, e->m, e->p, cycles, r, k, e->seed, e->call_index, ctl, e->d_stamp, now,
+                     e->d_stats, e->stream);
+    if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
+    // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
+    launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->tsc, e->stream);
+    if (kt) { SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 2], e->stream)); e->kt_rounds = r + 1; }
+    if (int rc = check_launch(e, "par_round", 3)) return rc;
+  }
+  return SWE_OK;
+}
+
+// Whole parallel World::erode (track reset, particle phase, EMA) as ONE graph launch: ~1550 kernel
+// and memset nodes captured once per (cycles, params, options) and replayed; the seed and the call
+// index travel through CallCtl in device memory.
+uint64_t graph_key(const swe_engine* e, int cycles) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&h](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  };
+  mix(&cycles, sizeof cycles);
+  mix(&e->p, sizeof e->p);
+  mix(&e->opt_cascade_interval, sizeof(int));
+  mix(&e->stream, sizeof e->stream);
+  mix(&e->m.rock, sizeof e->m.rock);
+  mix(&e->pbuf.a, sizeof e->pbuf.a);
+  return h;
+}
+
+int erode_parallel_graph(swe_engine* e, int cycles) {
+  if (int rc = need_particles(e, cycles)) return rc;
+  if (int rc = need_stamp(e)) return rc;
+  const uint64_t key = graph_key(e, cycles);
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : e->graphs) if (g.key == key) exec = g.exec;
+  finish_timers(e);
+  const CallCtl ctl_host{(uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->call_index, 0u};
+  SWE_CUDA(cudaMemcpyAsync(e->d_ctl, &ctl_host, sizeof ctl_host, cudaMemcpyHostToDevice, e->stream));
+  if (!exec) {
+    cudaGraph_t graph = nullptr;
+    SWE_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = SWE_OK;
+    if (cudaMemsetAsync(e->m.track, 0, e->cells() * sizeof(float4), e->stream) != cudaSuccess) rc = SWE_ERR_CUDA;
+    if (rc == SWE_OK) rc = parallel_rounds(e, cycles, e->d_ctl);
+    if (rc == SWE_OK) { launch_ema(e->m, e->p.lrate, e->stream); rc = check_launch(e, "ema"); }
+    const cudaError_t end = cudaStreamEndCapture(e->stream, &graph);
+    if (rc != SWE_OK || end != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      return rc != SWE_OK ? rc : fail(SWE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(end));
+    }
+    const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) return fail(SWE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(inst));
+    if (e->graphs.size() >= 4) { cudaGraphExecDestroy(e->graphs.front().exec); e->graphs.erase(e->graphs.begin()); }
+    e->graphs.push_back({key, exec});
+    e->launches -= (uint64_t)0;   // the capture pass already counted one call's worth of launches
+  } else {
+    const int k = e->opt_cascade_interval;
+    e->launches += 3ull + 3ull * (uint64_t)((e->p.max_age + 2 + k - 1) / k);   // kernels inside the replayed graph
+  }
+  SWE_CUDA(cudaEventRecord(e->ev_a, e->stream));
+  SWE_CUDA(cudaEventRecord(e->ev_f0, e->stream));
+  SWE_CUDA(cudaGraphLaunch(exec, e->stream));
+  SWE_CUDA(cudaEventRecord(e->ev_f1, e->stream));
+  SWE_CUDA(cudaEventRecord(e->ev_b, e->stream));
+  e->erode_timed = true;
+  e->call_index++;
+  e->erode_calls++;
+  return SWE_OK;
+}
+
 int erode_prologue(swe_engine* e) {
   finish_timers(e);
   SWE_CUDA(cudaEventRecord(e->ev_a, e->stream));
@@ -415,6 +510,7 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
   TRY(cudaMalloc(&e->d_stats, sizeof(DevStats)));
   TRY(cudaMalloc(&e->d_rng, sizeof(DetRand)));
   TRY(cudaMalloc(&e->d_small, 64 * sizeof(float)));
+  TRY(cudaMalloc(&e->d_ctl, sizeof(CallCtl)));
   TRY(cudaMemsetAsync(e->m.height, 0, n * sizeof(float), e->stream));
   TRY(cudaMemsetAsync(e->m.field, 0, n * sizeof(float4), e->stream));
   TRY(cudaMemsetAsync(e->m.track, 0, n * sizeof(float4), e->stream));
@@ -484,7 +580,8 @@ void swe_destroy(swe_engine* e) {
   cudaFree(e->d_stats); cudaFree(e->d_rng); cudaFree(e->d_small); cudaFree(e->d_scratch);
   cudaFree(e->pbuf.a); cudaFree(e->pbuf.b); cudaFree(e->pbuf.live); cudaFree(e->d_stamp);
   cudaFree(e->st.arena); cudaFree(e->st.d_pid); cudaFree(e->st.d_vars);
-  cudaFree(e->tsc.stage); cudaFree(e->tsc.flags); cudaFree(e->d_rock);
+  cudaFree(e->tsc.stage); cudaFree(e->tsc.flags); cudaFree(e->d_rock); cudaFree(e->d_ctl);
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : e->st.ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
@@ -666,6 +763,8 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
     return fail(SWE_ERR_INVALID, "unknown mode %d", mode);
   if (e->st.enabled)
     if (int rc = stripe_erode_check(e, cycles, mode)) return rc;
+  if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_cuda_graph && !e->opt_kernel_timing)
+    return erode_parallel_graph(e, cycles);
   // world.hpp:38-44: reset the four track members of every cell
   if (int rc = erode_prologue(e)) return rc;
   // world.hpp:47-66: the particles
@@ -682,31 +781,7 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
   } else if (cycles > 0) {
     if (int rc = need_particles(e, cycles)) return rc;
     if (int rc = need_stamp(e)) return rc;
-    const int k = e->opt_cascade_interval;
-    const int rounds = (e->p.max_age + 2 + k - 1) / k;   // every particle is dead after maxAge+2 calls
-    launch_par_begin(e->pbuf, e->m, cycles, e->seed, e->call_index, e->d_stats, e->stream);
-    if (int rc = check_launch(e, "par_begin", 2)) return rc;
-    for (int r = 0; r < rounds; r++) {
-      if (++e->stamp_counter > 255u) {   // stamp values 1..255; recycle with a clean plane
-        SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
-        e->stamp_counter = 1;
-      }
-      const unsigned char now = (unsigned char)e->stamp_counter;
-      const bool kt = e->opt_kernel_timing != 0;
-      if (kt) {
-        while ((int)e->kt_events.size() < 3 * (r + 1)) {
-          cudaEvent_t ev; SWE_CUDA(cudaEventCreate(&ev)); e->kt_events.push_back(ev);
-        }
-        SWE_CUDA(cudaEventRecord(e->kt_events[3 * r], e->stream));
-      }
-      launch_par_round(e->pbuf, e->m, e->p, cycles, r, k, e->seed, e->call_index, e->d_stamp, now,
-                       e->d_stats, e->stream);
-      if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
-      // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
-      launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->tsc, e->stream);
-      if (kt) { SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 2], e->stream)); e->kt_rounds = r + 1; }
-      if (int rc = check_launch(e, "par_round", 2)) return rc;
-    }
+    if (int rc = parallel_rounds(e, cycles, nullptr)) return rc;
   }
   // world.hpp:70-76: EMA of the flow fields
   return erode_epilogue(e);
@@ -1082,6 +1157,8 @@ int swe_set_option(swe_engine* e, int option, int value) {
       e->opt_cascade_interval = value; return SWE_OK;
     case SWE_OPT_KERNEL_TIMING:
       e->opt_kernel_timing = value ? 1 : 0; return SWE_OK;
+    case SWE_OPT_CUDA_GRAPH:
+      e->opt_cuda_graph = value ? 1 : 0; return SWE_OK;
     default:
       return fail(SWE_ERR_INVALID, "unknown option %d", option);
   }

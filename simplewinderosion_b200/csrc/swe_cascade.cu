@@ -862,6 +862,10 @@ void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cuda
 // first launch issued while another stream spins in a stripe wait kernel would stall behind it).
 void preload_cascade() {
   cudaFuncAttributes a;
+  allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<STAMPED_TX, true>), StampedGeo<STAMPED_TX>::SMEM);
+  allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<STAMPED_TX, false>), StampedGeo<STAMPED_TX>::SMEM);
+  allow_smem(reinterpret_cast<const void*>(&cascade_tile_kernel<true>), TILE_SMEM_PLAIN);
+  allow_smem(reinterpret_cast<const void*>(&cascade_tile_kernel<false>), TILE_SMEM_PLAIN);
   cudaFuncGetAttributes(&a, cascade_colour_kernel);
   cudaFuncGetAttributes(&a, cascade_tile_kernel<false>);
   cudaFuncGetAttributes(&a, cascade_tile_kernel<true>);

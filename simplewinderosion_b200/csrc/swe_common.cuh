@@ -99,6 +99,14 @@ void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightT
                             int row_lo, int row_hi, TileScratch scratch, cudaStream_t st);
 void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st);
 
+// Per-call values the particle kernels read from device memory instead of their parameter list, so
+// that a captured CUDA graph of a whole World::erode call can be replayed for the next call.
+struct CallCtl {
+  uint32_t key_x, key_y;   // Philox key = seed
+  uint32_t call;           // World::erode call index (Philox counter word)
+  uint32_t pad;
+};
+
 // parallel flight: swe_par.cu
 // Particle records of one World::erode call, 32 B each, SoA of two float4:
 //   a = {pos.x, pos.y, pos.z, sediment}   b = {speed.x, speed.y, speed.z, age (int bits; <0 = dead)}
@@ -132,11 +140,12 @@ void launch_par_round_stripe(const ParticleBuf& buf, const StripeRound& sr, cons
                              const swe_params& p, int steps_per_round, uint64_t seed, uint32_t call,
                              unsigned char* stamp, unsigned char stamp_now, DevStats* stats,
                              cudaStream_t st);
+// ctl != nullptr: seed and call index come from device memory (graph replay), else from the arguments
 void launch_par_begin(const ParticleBuf& buf, const MapView& m, int n, uint64_t seed, uint32_t call,
-                      DevStats* stats, cudaStream_t st);
+                      const CallCtl* ctl, DevStats* stats, cudaStream_t st);
 void launch_par_round(const ParticleBuf& buf, const MapView& m, const swe_params& p, int n, int round,
-                      int steps_per_round, uint64_t seed, uint32_t call, unsigned char* stamp,
-                      unsigned char stamp_now, DevStats* stats, cudaStream_t st);
+                      int steps_per_round, uint64_t seed, uint32_t call, const CallCtl* ctl,
+                      unsigned char* stamp, unsigned char stamp_now, DevStats* stats, cudaStream_t st);
 
 // stripe exchange primitives: swe_stripe.cu
 void launch_stripe_push(const float* src_h, float* dst_h, const unsigned char* src_s, unsigned char* dst_s,

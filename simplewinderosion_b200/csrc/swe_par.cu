@@ -202,9 +202,10 @@ __device__ __forceinline__ void spawn_position(int i, int n, int nx, int nz, uin
 }
 
 __global__ void par_spawn_kernel(float4* __restrict__ pa, float4* __restrict__ pb, int n, int nx,
-                                 int nz, uint2 key, uint32_t call) {
+                                 int nz, uint2 key, uint32_t call, const CallCtl* __restrict__ ctl) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (ctl) { key = make_uint2(ctl->key_x, ctl->key_y); call = ctl->call; }
   float px, pz;
   spawn_position(i, n, nx, nz, key, call, px, pz);
   pa[i] = make_float4(px, 0.0f, pz, 0.0f);
@@ -257,8 +258,9 @@ __global__ void __launch_bounds__(256, SWE_ROUND_MIN_BLOCKS)
 par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restrict__ pb, int n,
                  int steps_per_round, uint2 key, uint32_t call, unsigned char* stamp,
                  unsigned char stamp_now, const unsigned* live_in, unsigned* live_out,
-                 DevStats* stats, StripeRound sr) {
+                 DevStats* stats, StripeRound sr, const CallCtl* __restrict__ ctl) {
   if (live_in && *live_in == 0u) return;
+  if (ctl) { key = make_uint2(ctl->key_x, ctl->key_y); call = ctl->call; }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned steps = 0, n_oob = 0, n_age = 0, alive = 0;
   float lost = 0.0f;
@@ -355,20 +357,20 @@ static ParConst make_const(const swe_params& p) {
 }
 
 void launch_par_begin(const ParticleBuf& buf, const MapView& m, int n, uint64_t seed, uint32_t call,
-                      DevStats* stats, cudaStream_t st) {
+                      const CallCtl* ctl, DevStats* stats, cudaStream_t st) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   par_begin_kernel<<<(buf.live_slots + 255) / 256, 256, 0, st>>>(stats, buf.live, buf.live_slots, (unsigned)n);
-  par_spawn_kernel<<<(n + 255) / 256, 256, 0, st>>>(buf.a, buf.b, n, m.nx, m.nz, key, call);
+  par_spawn_kernel<<<(n + 255) / 256, 256, 0, st>>>(buf.a, buf.b, n, m.nx, m.nz, key, call, ctl);
 }
 
 void launch_par_round(const ParticleBuf& buf, const MapView& m, const swe_params& p, int n, int round,
-                      int steps_per_round, uint64_t seed, uint32_t call, unsigned char* stamp,
-                      unsigned char stamp_now, DevStats* stats, cudaStream_t st) {
+                      int steps_per_round, uint64_t seed, uint32_t call, const CallCtl* ctl,
+                      unsigned char* stamp, unsigned char stamp_now, DevStats* stats, cudaStream_t st) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   StripeRound none{};
   par_round_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(m, make_const(p), buf.a, buf.b, n, steps_per_round,
                                                            key, call, stamp, stamp_now, buf.live + round,
-                                                           buf.live + round + 1, stats, none);
+                                                           buf.live + round + 1, stats, none, ctl);
 }
 
 // ---- stripe (multi-GPU) launchers ---------------------------------------------------------------
@@ -402,7 +404,7 @@ void launch_par_round_stripe(const ParticleBuf& buf, const StripeRound& sr, cons
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   par_round_kernel<true><<<(buf.capacity + 255) / 256, 256, 0, st>>>(
       m, make_const(p), buf.a, buf.b, buf.capacity, steps_per_round, key, call, stamp, stamp_now, nullptr,
-      nullptr, stats, sr);
+      nullptr, stats, sr, nullptr);
 }
 
 // Force-load this translation unit's kernels (CUDA loads modules lazily on first launch, and a

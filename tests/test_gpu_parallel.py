@@ -136,3 +136,36 @@ def test_ragged_and_tiny_maps(nx, nz, cycles):
     assert st.particles == 2 * cycles == st.exits_oob + st.exits_age
     assert np.isfinite(w.download()).all()
     assert abs(w.sum_plane() + st.sediment_lost - s0) < 2e-5 * max(1.0, abs(s0))
+
+
+def test_cuda_graph_replay_equals_kernel_by_kernel():
+    """A parallel erode is captured once as a CUDA graph and replayed; seed and call index reach
+    the kernels through device memory, so replays must behave like fresh launches: same particle
+    accounting, different random streams per call, re-capture when parameters change."""
+    n, cycles = 256, 8192
+    hm = generate.gaussian_hill(n)
+    runs = {}
+    for graph in (1, 0):
+        w = swe.World(n)
+        w.set_option(swe.OPT_CUDA_GRAPH, graph)
+        w.upload(hm)
+        w.srand(21)
+        s0 = w.sum_plane()
+        per_call = []
+        for _ in range(4):
+            before = w.stats().steps
+            w.erode(cycles, swe.MODE_PARALLEL)
+            per_call.append(w.stats().steps - before)
+        st = w.stats()
+        assert st.particles == 4 * cycles == st.exits_oob + st.exits_age
+        assert abs(w.sum_plane() + st.sediment_lost - s0) < 2e-5 * s0
+        assert len(set(per_call)) == 4            # every call drew a new random stream
+        w.set(maxAge=100)                          # parameters are baked into the graph: must re-capture
+        w.erode(cycles, swe.MODE_PARALLEL)
+        st2 = w.stats()
+        assert st2.exits_oob + st2.exits_age == 5 * cycles
+        assert st2.steps - st.steps <= cycles * 101
+        runs[graph] = (per_call, w.download())
+    a, b = runs[1], runs[0]
+    assert abs(sum(a[0]) / sum(b[0]) - 1.0) < 0.01
+    assert np.corrcoef((a[1] - hm).ravel(), (b[1] - hm).ravel())[0, 1] > 0.97
