@@ -202,32 +202,43 @@ int check_launch(swe_engine* e, const char* what, int n = 1) {
 // One neighbour exchange of a stripe engine (all on the engine's stream, no host sync):
 // wait until the neighbours consumed the previous ghosts, push my boundary rows, signal, wait.
 // Returns the sequence number; the caller signals "consumed" with it after using the ghosts.
-unsigned stripe_exchange_begin(swe_engine* e, bool with_stamps, int* launches) {
+unsigned stripe_exchange_begin(swe_engine* e, bool with_stamps, int* launches, bool merge_inboxes = false,
+                               int parity = 0) {
   auto& S = e->st;
   const unsigned s = ++S.seq;
   unsigned* err = S.d_vars + 2;
   const int nz = e->m.nz;
-  launch_stripe_wait(S.has_below ? arena_flag(S.arena, FLAG_CONSUMED_BY_BELOW) : nullptr,
-                     S.has_above ? arena_flag(S.arena, FLAG_CONSUMED_BY_ABOVE) : nullptr, s - 1, err, e->stream);
+  StripePush down{}, up{};
   if (S.has_below) {   // my first GHOST_HI owned rows are the below neighbour's ghost rows above its stripe
     const size_t src = (size_t)(S.own_lo - e->m.x0) * nz, dst = (size_t)(S.own_lo - S.below.x0) * nz;
-    launch_stripe_push(e->m.height + src, static_cast<float*>(S.below.height) + dst,
-                       with_stamps ? e->d_stamp + src : nullptr,
-                       with_stamps ? static_cast<unsigned char*>(S.below.stamp) + dst : nullptr,
-                       (size_t)GHOST_HI * nz, e->stream);
+    down.src_h = e->m.height + src; down.dst_h = static_cast<float*>(S.below.height) + dst;
+    down.src_s = with_stamps ? e->d_stamp + src : nullptr;
+    down.dst_s = with_stamps ? static_cast<unsigned char*>(S.below.stamp) + dst : nullptr;
+    down.cells = (size_t)GHOST_HI * nz;
   }
   if (S.has_above) {   // my last GHOST_LO owned rows are the above neighbour's ghost rows below its stripe
     const size_t src = (size_t)(S.own_hi - GHOST_LO - e->m.x0) * nz, dst = (size_t)(S.own_hi - GHOST_LO - S.above.x0) * nz;
-    launch_stripe_push(e->m.height + src, static_cast<float*>(S.above.height) + dst,
-                       with_stamps ? e->d_stamp + src : nullptr,
-                       with_stamps ? static_cast<unsigned char*>(S.above.stamp) + dst : nullptr,
-                       (size_t)GHOST_LO * nz, e->stream);
+    up.src_h = e->m.height + src; up.dst_h = static_cast<float*>(S.above.height) + dst;
+    up.src_s = with_stamps ? e->d_stamp + src : nullptr;
+    up.dst_s = with_stamps ? static_cast<unsigned char*>(S.above.stamp) + dst : nullptr;
+    up.cells = (size_t)GHOST_LO * nz;
   }
-  launch_stripe_signal(S.has_below ? arena_flag(S.below.arena, FLAG_READY_FROM_ABOVE) : nullptr,
-                       S.has_above ? arena_flag(S.above.arena, FLAG_READY_FROM_BELOW) : nullptr, s, e->stream);
-  launch_stripe_wait(S.has_below ? arena_flag(S.arena, FLAG_READY_FROM_BELOW) : nullptr,
-                     S.has_above ? arena_flag(S.arena, FLAG_READY_FROM_ABOVE) : nullptr, s, err, e->stream);
-  *launches += 3 + (S.has_below ? 1 : 0) + (S.has_above ? 1 : 0);
+  // one kernel: wait until the neighbours consumed the previous ghosts, push, signal "delivered"
+  launch_stripe_push_signal(down, up,
+                            S.has_below ? arena_flag(S.arena, FLAG_CONSUMED_BY_BELOW) : nullptr,
+                            S.has_above ? arena_flag(S.arena, FLAG_CONSUMED_BY_ABOVE) : nullptr,
+                            S.has_below ? arena_flag(S.below.arena, FLAG_READY_FROM_ABOVE) : nullptr,
+                            S.has_above ? arena_flag(S.above.arena, FLAG_READY_FROM_BELOW) : nullptr,
+                            s, S.d_vars + 4, err, e->stream);
+  // one kernel: wait for the neighbours' deliveries, merge the particles they handed over
+  StripeOutbox in_a{}, in_b{};
+  if (merge_inboxes && S.has_below) in_a = arena_inbox(S.arena, S.inbox_capacity, FROM_BELOW, parity);
+  if (merge_inboxes && S.has_above) in_b = arena_inbox(S.arena, S.inbox_capacity, FROM_ABOVE, parity);
+  launch_stripe_wait_merge(in_a, in_b, S.has_below ? arena_flag(S.arena, FLAG_READY_FROM_BELOW) : nullptr,
+                           S.has_above ? arena_flag(S.arena, FLAG_READY_FROM_ABOVE) : nullptr, s, e->pbuf.a,
+                           e->pbuf.b, S.d_pid, S.d_vars + 0, e->pbuf.capacity, S.d_vars + 1, S.d_vars + 5, err,
+                           e->stream);
+  *launches += 2;
   return s;
 }
 
@@ -290,14 +301,7 @@ int stripe_erode_round(swe_engine* e) {
                           e->stream);
   nl += 1;
   if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
-  const unsigned s = stripe_exchange_begin(e, true, &nl);
-  for (int dir = 0; dir < 2; dir++) {
-    if ((dir == FROM_BELOW && !S.has_below) || (dir == FROM_ABOVE && !S.has_above)) continue;
-    const StripeOutbox in = arena_inbox(S.arena, S.inbox_capacity, dir, parity);
-    launch_stripe_merge(in.a, in.b, in.pid, in.count, in.capacity, e->pbuf.a, e->pbuf.b, S.d_pid,
-                        S.d_vars + 0, e->pbuf.capacity, S.d_vars + 1, S.d_vars + 3, e->stream);
-    nl += 3;
-  }
+  const unsigned s = stripe_exchange_begin(e, true, &nl, true, parity);
   // rows own_lo-1 .. own_hi: the ghost row each side is recomputed here instead of exchanged
   launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, nullptr, S.own_lo - 1, S.own_hi + 1, e->tsc,
                          e->stream);

@@ -157,6 +157,20 @@ void launch_stripe_merge(const float4* in_a, const float4* in_b, const uint32_t*
                          int in_capacity, float4* pa, float4* pb, uint32_t* pid, unsigned* n_used,
                          int capacity, unsigned* overflow, unsigned* scratch_base, cudaStream_t st);
 
+// fused exchange: [wait consumed, push both strips, signal ready] and [wait ready, merge both inboxes]
+struct StripePush {
+  const float* src_h; float* dst_h;
+  const unsigned char* src_s; unsigned char* dst_s;
+  size_t cells;
+};
+void launch_stripe_push_signal(const StripePush& down, const StripePush& up, const unsigned* consumed_a,
+                               const unsigned* consumed_b, unsigned* ready_a, unsigned* ready_b, unsigned seq,
+                               unsigned* done_counter, unsigned* error_flag, cudaStream_t st);
+void launch_stripe_wait_merge(const StripeOutbox& in_a, const StripeOutbox& in_b, const unsigned* ready_a,
+                              const unsigned* ready_b, unsigned seq, float4* pa, float4* pb, uint32_t* pid,
+                              unsigned* n_used, int capacity, unsigned* overflow, unsigned* done_counter,
+                              unsigned* error_flag, cudaStream_t st);
+
 // field passes and utilities: swe_fields.cu
 void launch_ema(const MapView& m, float lrate, cudaStream_t st);
 void launch_pack_plane(const MapView& m, int plane, const float* d_src, cudaStream_t st);

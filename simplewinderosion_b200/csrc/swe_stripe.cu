@@ -115,6 +115,115 @@ void launch_stripe_merge(const float4* in_a, const float4* in_b, const uint32_t*
   stripe_merge_finish_kernel<<<1, 1, 0, st>>>(in_count, in_capacity, n_used, capacity);
 }
 
+// ---- fused exchange kernels (one launch each instead of 4 + 7) -----------------------------------
+// poll helper: thread 0 of the calling block spins until both flags reached `value`
+__device__ __forceinline__ bool spin_until(const unsigned* flag_a, const unsigned* flag_b, unsigned value,
+                                           unsigned* error_flag) {
+  if (*reinterpret_cast<volatile unsigned*>(error_flag)) return false;
+  const long long t0 = clock64();
+  const unsigned* flags[2] = {flag_a, flag_b};
+  for (int k = 0; k < 2; k++) {
+    if (!flags[k]) continue;
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags[k]) : "memory");
+      if ((int)(v - value) >= 0) break;
+      if (clock64() - t0 > 20000000000LL) { atomicExch(error_flag, 1u); return false; }
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+  return true;
+}
+
+// wait(consumed >= seq-1) -> push both boundary strips into the neighbours' ghost rows -> the last
+// block to finish signals ready = seq to both neighbours.
+__global__ void __launch_bounds__(256)
+stripe_push_signal_kernel(StripePush down, StripePush up, const unsigned* consumed_a, const unsigned* consumed_b,
+                          unsigned* ready_a, unsigned* ready_b, unsigned seq, unsigned* done_counter,
+                          unsigned* error_flag) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = spin_until(consumed_a, consumed_b, seq - 1u, error_flag) ? 1 : 0;
+  __syncthreads();
+  if (ok) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = t; i < down.cells; i += stride) {
+      down.dst_h[i] = down.src_h[i];
+      if (down.src_s) down.dst_s[i] = down.src_s[i];
+    }
+    for (size_t i = t; i < up.cells; i += stride) {
+      up.dst_h[i] = up.src_h[i];
+      if (up.src_s) up.dst_s[i] = up.src_s[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) {               // every block has pushed (and fenced) its share
+      *done_counter = 0u;
+      __threadfence_system();
+      if (ready_a) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ready_a), "r"(seq) : "memory");
+      if (ready_b) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ready_b), "r"(seq) : "memory");
+    }
+  }
+}
+
+// wait(ready >= seq) -> append both inboxes to the local particle arrays -> the last block bumps
+// n_used and clears the inbox counters.
+__global__ void __launch_bounds__(256)
+stripe_wait_merge_kernel(StripeOutbox in_a, StripeOutbox in_b, const unsigned* ready_a, const unsigned* ready_b,
+                         unsigned seq, float4* __restrict__ pa, float4* __restrict__ pb,
+                         uint32_t* __restrict__ pid, unsigned* n_used, int capacity, unsigned* overflow,
+                         unsigned* done_counter, unsigned* error_flag) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = spin_until(ready_a, ready_b, seq, error_flag) ? 1 : 0;
+  __syncthreads();
+  const unsigned base = *n_used;               // constant until the last block updates it
+  unsigned ca = 0, cb = 0;
+  if (ok) {
+    ca = in_a.count ? min(*in_a.count, (unsigned)in_a.capacity) : 0u;
+    cb = in_b.count ? min(*in_b.count, (unsigned)in_b.capacity) : 0u;
+    const unsigned stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned i = t; i < ca + cb; i += stride) {
+      const unsigned slot = base + i;
+      if (slot >= (unsigned)capacity) { atomicAdd(overflow, 1u); continue; }
+      if (i < ca) { pa[slot] = in_a.a[i]; pb[slot] = in_a.b[i]; pid[slot] = in_a.pid[i]; }
+      else { const unsigned j = i - ca; pa[slot] = in_b.a[j]; pb[slot] = in_b.b[j]; pid[slot] = in_b.pid[j]; }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *done_counter = 0u;
+      if (ok) {
+        if (in_a.count && *in_a.count > (unsigned)in_a.capacity) atomicAdd(overflow, *in_a.count - (unsigned)in_a.capacity);
+        if (in_b.count && *in_b.count > (unsigned)in_b.capacity) atomicAdd(overflow, *in_b.count - (unsigned)in_b.capacity);
+        const unsigned nu = base + ca + cb;
+        *n_used = nu < (unsigned)capacity ? nu : (unsigned)capacity;
+        if (in_a.count) *in_a.count = 0u;
+        if (in_b.count) *in_b.count = 0u;
+      }
+    }
+  }
+}
+
+void launch_stripe_push_signal(const StripePush& down, const StripePush& up, const unsigned* consumed_a,
+                               const unsigned* consumed_b, unsigned* ready_a, unsigned* ready_b, unsigned seq,
+                               unsigned* done_counter, unsigned* error_flag, cudaStream_t st) {
+  stripe_push_signal_kernel<<<64, 256, 0, st>>>(down, up, consumed_a, consumed_b, ready_a, ready_b, seq,
+                                                done_counter, error_flag);
+}
+void launch_stripe_wait_merge(const StripeOutbox& in_a, const StripeOutbox& in_b, const unsigned* ready_a,
+                              const unsigned* ready_b, unsigned seq, float4* pa, float4* pb, uint32_t* pid,
+                              unsigned* n_used, int capacity, unsigned* overflow, unsigned* done_counter,
+                              unsigned* error_flag, cudaStream_t st) {
+  stripe_wait_merge_kernel<<<32, 256, 0, st>>>(in_a, in_b, ready_a, ready_b, seq, pa, pb, pid, n_used, capacity,
+                                               overflow, done_counter, error_flag);
+}
+
 // Force-load this translation unit's kernels (CUDA loads modules lazily on first launch, and a
 // first launch issued while another stream spins in a stripe wait kernel would stall behind it).
 void preload_stripe() {
@@ -125,6 +234,8 @@ void preload_stripe() {
   cudaFuncGetAttributes(&a, stripe_merge_kernel);
   cudaFuncGetAttributes(&a, stripe_merge_prepare_kernel);
   cudaFuncGetAttributes(&a, stripe_merge_finish_kernel);
+  cudaFuncGetAttributes(&a, stripe_push_signal_kernel);
+  cudaFuncGetAttributes(&a, stripe_wait_merge_kernel);
 }
 
 }  // namespace swe
