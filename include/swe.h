@@ -211,6 +211,21 @@ int swe_height(swe_engine* e, int x, int z, float* out);
  * dst = nx*nz*3 floats. */
 int swe_download_normals(swe_engine* e, float* dst);
 
+/* ---- generate (host generate of the reference, run on the device) ------------------- */
+/* The noise layers of quad::map::init (cellpool.h:388-411; a comment in the mounted snapshot):
+ *   for o in 0..layers-1: height += scale_o * noise.GetNoise(x/tile, z/tile, (float)(seed % 10000))
+ * with frequency 2^o, scale_0 = 0.6, scale *= 0.6, and `noise` the FastNoiseLite object as map::init
+ * configures it (OpenSimplex2, FBm of 3 octaves, seed 1337; cellpool.h:366-368). Bitwise identical
+ * to the host library (fp32 + wrapping int arithmetic only). ADDS to the current heights, like the
+ * reference adds to its Gaussian hill; tile = coordinate divisor (quad::tilesize), 0 = nz;
+ * layers <= 16. Works on stripe engines (global coordinates; ghost rows are generated too). */
+int swe_generate_noise(swe_engine* e, int seed, int layers, int tile);
+/* The normalisation that ends map::init (cellpool.h:416-428): min and max are folded from 0.0f,
+ * then height = 0.5*((height - min)/(max - min)). Split in two calls so that stripes can reduce
+ * min/max across ranks in between; a single GPU passes the range straight through. */
+int swe_height_range(swe_engine* e, float* min_out, float* max_out);
+int swe_normalize_height(swe_engine* e, float min, float max);
+
 /* ---- diagnostics ------------------------------------------------------------------- */
 int swe_get_stats(swe_engine* e, swe_stats* out);
 int swe_reset_stats(swe_engine* e);

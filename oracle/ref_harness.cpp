@@ -218,4 +218,58 @@ double ref_sum_height() {
   return s;
 }
 
+// ---- host generate, noise stack -------------------------------------
+// The UNMODIFIED FastNoiseLite class (source/include/FastNoiseLite.h, pulled in by
+// cellpool.h) configured exactly as map::init configures it (cellpool.h:366-368).
+static FastNoiseLite& ref_noise_object() {
+  static FastNoiseLite noise;
+  static bool set = false;
+  if (!set) {
+    noise.SetNoiseType(FastNoiseLite::NoiseType_OpenSimplex2);
+    noise.SetFractalType(FastNoiseLite::FractalType_FBm);
+    set = true;
+  }
+  return noise;
+}
+
+// noise.SetFrequency(frequency); noise.GetNoise(x, y, z)
+float ref_get_noise(float frequency, float x, float y, float z) {
+  FastNoiseLite& noise = ref_noise_object();
+  noise.SetFrequency(frequency);
+  return noise.GetNoise(x, y, z);
+}
+
+// The layer loop map::init carries as a comment (cellpool.h:392-409), restated around the
+// reference's own noise object: height += scale*GetNoise(p.x, p.y, SEED%10000) for `layers`
+// layers of doubling frequency, scale 0.6 *= 0.6.
+void ref_noise_stack(int SEED, int layers) {
+  FastNoiseLite& noise = ref_noise_object();
+  for (auto& node : World::map.nodes) {
+    float frequency = 1.0f;
+    float scale = 0.6f;
+    for (int o = 0; o < layers; o++) {
+      noise.SetFrequency(frequency);
+      for (auto [cell, pos] : node.s) {
+        vec2 p = vec2(node.pos + quad::lodsize * pos) / vec2(quad::tileres);
+        cell.height += scale * noise.GetNoise(p.x, p.y, (float)(SEED % 10000));
+      }
+      frequency *= 2;
+      scale *= 0.6;
+    }
+  }
+}
+
+// cellpool.h:416-428 (the tail of map::init), verbatim semantics on the current heights.
+void ref_normalize() {
+  float min = 0.0f;
+  float max = 0.0f;
+  for (auto& node : World::map.nodes)
+    for (auto [cell, pos] : node.s) {
+      min = (min < cell.height) ? min : cell.height;
+      max = (max > cell.height) ? max : cell.height;
+    }
+  for (auto& node : World::map.nodes)
+    for (auto [cell, pos] : node.s) cell.height = 0.5 * ((cell.height - min) / (max - min));
+}
+
 }  // extern "C"

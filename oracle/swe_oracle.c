@@ -411,3 +411,120 @@ uint64_t swo_hash_height(const swo_world* w) {
   }
   return h;
 }
+
+/* ------------------------------------------------------------------------------------
+ * Host generate, noise stack: quad::map::init's eight layers of
+ * FastNoiseLite OpenSimplex2 FBm, cellpool.h:388-411 (commented out in the snapshot, so the
+ * layer loop is restated from the comment; the noise itself is source/include/FastNoiseLite.h).
+ * FastNoiseLite object state as map::init leaves it: default ctor (FastNoiseLite.h:114-129:
+ * seed 1337, 3 octaves, lacunarity 2, gain 0.5, weighted strength 0, fractal bounding
+ * 1/1.75f), SetNoiseType(OpenSimplex2), SetFractalType(FBm) (cellpool.h:366-368).
+ * ---------------------------------------------------------------------------------- */
+/* Lookup<float>::Gradients3D (FastNoiseLite.h:2529-2547) has a closed form: entries 0..59 are
+ * five repeats of the twelve cube-edge directions (family = which coordinate is zero, two sign
+ * bits), entries 60..63 repeat directions 8, 1, 9, 3. */
+static void swo_fnl_gradient(int g, float out[3]) {
+  static const int tail[4] = {8, 1, 9, 3};
+  const int e = (g >= 60) ? tail[g - 60] : g % 12;
+  const int family = e / 4;
+  const float s0 = (e & 1) ? -1.0f : 1.0f, s1 = (e & 2) ? -1.0f : 1.0f;
+  if (family == 0) { out[0] = 0.0f; out[1] = s0; out[2] = s1; }
+  else if (family == 1) { out[0] = s0; out[1] = 0.0f; out[2] = s1; }
+  else { out[0] = s0; out[1] = s1; out[2] = 0.0f; }
+}
+
+/* GradCoord 3D (FastNoiseLite.h:542-553) on top of Hash (:500-506); int arithmetic wraps. */
+static float swo_fnl_gradcoord(int32_t seed, int32_t xp, int32_t yp, int32_t zp, float xd, float yd, float zd) {
+  int32_t h = (int32_t)((uint32_t)(seed ^ xp ^ yp ^ zp) * 0x27d4eb2du);
+  h ^= h >> 15;                           /* arithmetic shift, as on the reference's int */
+  float g[3];
+  swo_fnl_gradient((h >> 2) & 63, g);
+  return xd * g[0] + yd * g[1] + zd * g[2];
+}
+
+#define FNL_PX 501125321
+#define FNL_PY 1136930381
+#define FNL_PZ 1720413743
+static inline int32_t wrap_mul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+static inline int32_t wrap_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+static inline int32_t fnl_round(float f) { return f >= 0 ? (int32_t)(f + 0.5f) : (int32_t)(f - 0.5f); }
+
+/* SingleOpenSimplex2 3D (FastNoiseLite.h:1054-1147): two offset cubic lattices; on each, the
+ * nearest lattice point and its neighbour along the axis of largest offset contribute
+ * falloff^4 * gradient. */
+float swo_fnl_single3(int seed, float x, float y, float z) {
+  int32_t li = fnl_round(x), lj = fnl_round(y), lk = fnl_round(z);
+  float dx = x - (float)li, dy = y - (float)lj, dz = z - (float)lk;
+  int32_t sx = (int32_t)(-1.0f - dx) | 1, sy = (int32_t)(-1.0f - dy) | 1, sz = (int32_t)(-1.0f - dz) | 1;
+  float ax = (float)sx * -dx, ay = (float)sy * -dy, az = (float)sz * -dz;
+  li = wrap_mul(li, FNL_PX); lj = wrap_mul(lj, FNL_PY); lk = wrap_mul(lk, FNL_PZ);
+  float value = 0;
+  float fall = (0.6f - dx * dx) - (dy * dy + dz * dz);
+  int32_t sd = seed;
+  for (int lattice = 0; lattice < 2; lattice++) {
+    if (fall > 0) value += (fall * fall) * (fall * fall) * swo_fnl_gradcoord(sd, li, lj, lk, dx, dy, dz);
+    /* second vertex: step along the dominant axis (ties: x before y before z, :1100,1106) */
+    float fall2 = fall + 1;
+    int32_t i2 = li, j2 = lj, k2 = lk;
+    float ex = dx, ey = dy, ez = dz;
+    if (ax >= ay && ax >= az)      { ex += (float)sx; fall2 -= (float)(sx * 2) * ex; i2 = wrap_add(i2, -wrap_mul(sx, FNL_PX)); }
+    else if (ay > ax && ay >= az)  { ey += (float)sy; fall2 -= (float)(sy * 2) * ey; j2 = wrap_add(j2, -wrap_mul(sy, FNL_PY)); }
+    else                           { ez += (float)sz; fall2 -= (float)(sz * 2) * ez; k2 = wrap_add(k2, -wrap_mul(sz, FNL_PZ)); }
+    if (fall2 > 0) value += (fall2 * fall2) * (fall2 * fall2) * swo_fnl_gradcoord(sd, i2, j2, k2, ex, ey, ez);
+    if (lattice == 1) break;
+    /* move to the second lattice (:1126-1143) */
+    ax = 0.5f - ax; ay = 0.5f - ay; az = 0.5f - az;
+    dx = (float)sx * ax; dy = (float)sy * ay; dz = (float)sz * az;
+    fall += (0.75f - ax) - (ay + az);
+    li = wrap_add(li, (sx >> 1) & FNL_PX); lj = wrap_add(lj, (sy >> 1) & FNL_PY); lk = wrap_add(lk, (sz >> 1) & FNL_PZ);
+    sx = -sx; sy = -sy; sz = -sz;
+    sd = ~sd;
+  }
+  return value * 32.69428253173828125f;
+}
+
+/* GetNoise(x,y,z) (FastNoiseLite.h:322-340) in the state described above:
+ * TransformNoiseCoordinate (:687-721, DefaultOpenSimplex2 rotation) then GenFractalFBm (:866-887). */
+float swo_fnl_getnoise(float frequency, float x, float y, float z) {
+  x *= frequency; y *= frequency; z *= frequency;
+  const float R3 = (float)(2.0 / 3.0);
+  const float r = (x + y + z) * R3;
+  x = r - x; y = r - y; z = r - z;
+  int seed = 1337;
+  float sum = 0;
+  float amp = 1 / 1.75f;
+  for (int o = 0; o < 3; o++) {
+    const float noise = swo_fnl_single3(seed++, x, y, z);
+    sum += noise * amp;
+    amp *= 1.0f + 0.0f * ((noise + 1) * 0.5f - 1.0f);   /* Lerp(1, (noise+1)/2, weightedStrength = 0) */
+    x *= 2.0f; y *= 2.0f; z *= 2.0f;
+    amp *= 0.5f;
+  }
+  return sum;
+}
+
+/* The layer loop of cellpool.h:392-409: frequency 1,2,4,...; scale 0.6, *= 0.6 (double product
+ * rounded to float); p = cell / tile; third coordinate (float)(SEED % 10000). Adds to height. */
+void swo_noise_stack(swo_world* w, int seed, int layers, int tile) {
+  float* H = w->plane[0];
+  float frequency = 1.0f, scale = 0.6f;
+  const float zc = (float)(seed % 10000);
+  for (int o = 0; o < layers; o++) {
+    for (int x = 0; x < w->nx; x++)
+      for (int z = 0; z < w->nz; z++) {
+        const float px = (float)x / (float)tile, pz = (float)z / (float)tile;
+        H[(size_t)x * w->nz + z] += scale * swo_fnl_getnoise(frequency, px, pz, zc);
+      }
+    frequency *= 2;
+    scale = (float)((double)scale * 0.6);
+  }
+}
+
+/* cellpool.h:416-428: min and max start at 0.0f; height = 0.5*((h-min)/(max-min)). */
+void swo_normalize(swo_world* w) {
+  float* H = w->plane[0];
+  float mn = 0.0f, mx = 0.0f;
+  const size_t n = (size_t)w->nx * w->nz;
+  for (size_t i = 0; i < n; i++) { mn = (mn < H[i]) ? mn : H[i]; mx = (mx > H[i]) ? mx : H[i]; }
+  for (size_t i = 0; i < n; i++) H[i] = (float)(0.5 * (double)((H[i] - mn) / (mx - mn)));
+}

@@ -121,6 +121,9 @@ PROTOTYPES = {
     "swe_normal": (C.c_int, [_E, C.c_int, C.c_int, _F]),
     "swe_height": (C.c_int, [_E, C.c_int, C.c_int, _F]),
     "swe_download_normals": (C.c_int, [_E, C.c_void_p]),
+    "swe_generate_noise": (C.c_int, [_E, C.c_int, C.c_int, C.c_int]),
+    "swe_height_range": (C.c_int, [_E, _F, _F]),
+    "swe_normalize_height": (C.c_int, [_E, C.c_float, C.c_float]),
     "swe_get_stats": (C.c_int, [_E, C.POINTER(Stats)]),
     "swe_reset_stats": (C.c_int, [_E]),
     "swe_sum_plane": (C.c_int, [_E, C.c_int, C.POINTER(C.c_double)]),

@@ -547,7 +547,7 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
     e->pbuf.live = nullptr; e->pbuf.live_slots = 0;
   }
   make_height_tensor_map(e->m, &e->tmap);   // optional: plain-load kernels are used when it fails
-  preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe();
+  preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe(); preload_noise();
   (void)cudaGetLastError();
   launch_det_srand(e->d_rng, 1u, e->stream);
   TRY(cudaGetLastError());
@@ -1005,6 +1005,36 @@ int swe_download_normals(swe_engine* e, float* dst) {
   SWE_CUDA(cudaMemcpyAsync(dst, e->d_scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
   return SWE_OK;
+}
+
+// ---- generate --------------------------------------------------------------
+int swe_generate_noise(swe_engine* e, int seed, int layers, int tile) {
+  if (int rc = bind(e)) return rc;
+  if (layers < 0 || layers > noise_max_layers()) return fail(SWE_ERR_INVALID, "layers must be in [0, %d]", noise_max_layers());
+  if (tile < 0) return fail(SWE_ERR_INVALID, "tile must be >= 0");
+  if (layers == 0) return SWE_OK;
+  launch_noise_stack(e->m, seed, layers, tile ? tile : e->m.nz, e->stream);   // ghost rows included
+  return check_launch(e, "noise_stack");
+}
+
+int swe_height_range(swe_engine* e, float* min_out, float* max_out) {
+  if (int rc = bind(e)) return rc;
+  if (!min_out || !max_out) return fail(SWE_ERR_INVALID, "output pointer is NULL");
+  int* d_out = reinterpret_cast<int*>(e->d_small + 24);
+  launch_height_range(e->owned().height, e->host_cells(), d_out, e->stream);
+  if (int rc = check_launch(e, "height_range")) return rc;
+  float both[2];
+  SWE_CUDA(cudaMemcpyAsync(both, d_out, sizeof both, cudaMemcpyDeviceToHost, e->stream));
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  *min_out = both[0]; *max_out = both[1];
+  return SWE_OK;
+}
+
+int swe_normalize_height(swe_engine* e, float min, float max) {
+  if (int rc = bind(e)) return rc;
+  if (!(max > min)) return fail(SWE_ERR_INVALID, "normalisation needs max > min (a flat map divides by zero, cellpool.h:427)");
+  launch_normalize(e->m.height, e->cells(), min, max, e->stream);              // ghost rows included
+  return check_launch(e, "normalize");
 }
 
 // ---- diagnostics ----------------------------------------------------------------------------

@@ -179,10 +179,17 @@ void launch_cells_to_planes(const MapView& m, const float* d_cells, cudaStream_t
 void launch_planes_to_cells(const MapView& m, float* d_cells, cudaStream_t st);
 void launch_sum_plane(const MapView& m, int plane, double* d_out, cudaStream_t st);
 
+// generate: swe_noise.cu
+int noise_max_layers();
+void launch_noise_stack(const MapView& m, int seed, int layers, int tile, cudaStream_t st);
+void launch_height_range(const float* d_height, size_t n, int* d_out2, cudaStream_t st);
+void launch_normalize(float* d_height, size_t n, float mn, float mx, cudaStream_t st);
+
 void preload_det();
 void preload_cascade();
 void preload_fields();
 void preload_par();
 void preload_stripe();
+void preload_noise();
 
 }  // namespace swe

@@ -196,6 +196,24 @@ class World:
         check(lib.swe_download_normals(self._h, out.ctypes.data))
         return out
 
+    # -- generate (quad::map::init on the device) -------------------------------------------------
+    def generate_noise(self, seed: int, layers: int = 8, tile: int = 0) -> None:
+        """height += the FastNoiseLite OpenSimplex2-FBm layers of map::init (cellpool.h:388-411);
+        bitwise identical to the host library. tile = coordinate divisor (quad::tilesize), 0 = nz."""
+        check(lib.swe_generate_noise(self._h, int(seed), int(layers), int(tile)))
+
+    def height_range(self) -> tuple[float, float]:
+        """(min, max) folded from 0.0f like cellpool.h:416-423."""
+        lo, hi = C.c_float(), C.c_float()
+        check(lib.swe_height_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def normalize(self, lo: float | None = None, hi: float | None = None) -> None:
+        """height = 0.5*((height - min)/(max - min)) (cellpool.h:424-428)."""
+        if lo is None or hi is None:
+            lo, hi = self.height_range()
+        check(lib.swe_normalize_height(self._h, float(lo), float(hi)))
+
     # -- hot path --------------------------------------------------------------------------------
     def erode(self, cycles: int, mode: int = MODE_PARALLEL) -> None:
         """World::erode(cycles) (world.hpp:36-77)."""

@@ -74,6 +74,12 @@ def port():
         L.swo_trace.restype = C.c_int
         L.swo_hash_height.argtypes = [W]
         L.swo_hash_height.restype = C.c_uint64
+        L.swo_fnl_single3.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+        L.swo_fnl_single3.restype = C.c_float
+        L.swo_fnl_getnoise.argtypes = [C.c_float] * 4
+        L.swo_fnl_getnoise.restype = C.c_float
+        L.swo_noise_stack.argtypes = [W, C.c_int, C.c_int, C.c_int]
+        L.swo_normalize.argtypes = [W]
         _port = L
     return _port
 
@@ -158,6 +164,16 @@ class PortWorld:
     def hash_height(self) -> int:
         return self.L.swo_hash_height(self.w)
 
+    def noise_stack(self, seed: int, layers: int = 8, tile: int | None = None) -> None:
+        """height += the FastNoiseLite layer stack of cellpool.h:392-409."""
+        self.L.swo_noise_stack(self.w, seed, layers, self.nz if tile is None else tile)
+
+    def normalize(self) -> None:
+        self.L.swo_normalize(self.w)
+
+    def get_noise(self, frequency: float, x: float, y: float, z: float) -> float:
+        return self.L.swo_fnl_getnoise(frequency, x, y, z)
+
 
 def ref_available(n: int) -> bool:
     return os.path.exists(os.path.join(REF_DIR, f"libswe_ref_{n}.so"))
@@ -181,6 +197,10 @@ class RefWorld:
             L.ref_cascade.argtypes = [C.c_float, C.c_float]
             L.ref_normal.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
             L.ref_set_params.argtypes = [C.c_int] + [C.c_float] * 6
+            if hasattr(L, "ref_get_noise"):
+                L.ref_get_noise.argtypes = [C.c_float] * 4
+                L.ref_get_noise.restype = C.c_float
+                L.ref_noise_stack.argtypes = [C.c_int, C.c_int]
             RefWorld._libs[n] = L
         self.L = RefWorld._libs[n]
         assert self.L.ref_size() == n
@@ -237,6 +257,15 @@ class RefWorld:
 
     def sum_height(self) -> float:
         return self.L.ref_sum_height()
+
+    def noise_stack(self, seed: int, layers: int = 8) -> None:
+        self.L.ref_noise_stack(seed, layers)
+
+    def normalize(self) -> None:
+        self.L.ref_normalize()
+
+    def get_noise(self, frequency: float, x: float, y: float, z: float) -> float:
+        return self.L.ref_get_noise(frequency, x, y, z)
 
 
 def fnv1a64_f32(a: np.ndarray) -> int:
