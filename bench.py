@@ -42,8 +42,9 @@ BYTES_PER_STEP = 104.0          # 9x4 read + 9x4 write + 4 track
 BYTES_PER_CELL_SWEEP = 8.0      # read h + write h
 METRIC = "wind particle-steps/sec @4096^2 map"
 UNIT = "particle-steps/s"
-WORKLOAD = ("cfg3-pinned: 4096x4096 FBm dune field (seed 1), 4194304 particles per World::erode, "
-            "parallel mode, single height layer (rock/abrasion extension off)")
+WORKLOAD = ("cfg3-pinned: 4096x4096 dune field = map::init's eight FastNoiseLite OpenSimplex2-FBm layers (seed 1, "
+            "cellpool.h:388-428), 4194304 particles per World::erode, parallel mode, single height layer "
+            "(rock/abrasion extension off)")
 
 
 def ncu_traffic(kernel: str):
@@ -200,9 +201,25 @@ def host_threads_for_reference(n: int) -> int:
     return max(1, min(ncpu, by_mem, 64))
 
 
-def make_map(n: int):
-    from simplewinderosion_b200 import generate
-    return generate.fbm(n, seed=1)
+def make_map(n: int, device: int | None = None):
+    """The dune-field input of SURVEY 8(d) cfg3/cfg4: quad::map::init's eight layers of FastNoiseLite
+    OpenSimplex2 FBm (cellpool.h:388-411, seed 1) normalised to [0, 0.5] (cellpool.h:416-428).
+    Our arm generates it on its GPU (swe_generate_noise, bitwise identical to the host library);
+    the reference arm computes the same map with the oracle port on the host cores."""
+    if device is not None:
+        import simplewinderosion_b200 as swe
+        w = swe.World(n, device=device)
+        w.generate_noise(1, 8)
+        w.normalize()
+        hm = w.download()
+        w.close()
+        return hm
+    from tests.oracle_lib import noise_map
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        ncpu = os.cpu_count() or 1
+    return noise_map(n, seed=1, layers=8, workers=max(1, min(ncpu, 64)))
 
 
 def save_map_tmp(hm) -> str:
@@ -347,7 +364,7 @@ def run_ours(args) -> None:
 
     peak, peak_src = measured_peak_gbs()
     n, particles = args.size, args.particles
-    hm = make_map(n)
+    hm = make_map(n, device=local)
 
     if world == 1:
         w = swe.World(n, device=local)

@@ -4,7 +4,7 @@
 //
 //   g++ -std=c++17 -O2 -Iinclude examples/headless_main.cpp -Lsimplewinderosion_b200 -lswe_b200
 //       -Wl,-rpath,$PWD/simplewinderosion_b200 -o headless
-//   ./headless <size> <seed> <frames> <cycles> <mode: 0 deterministic | 1 parallel>
+//   ./headless <size> <seed> <frames> <cycles> <mode: 0 deterministic | 1 parallel> [noise layers]
 #include <cstdio>
 #include <cstdlib>
 
@@ -16,11 +16,12 @@ int main(int argc, char* args[]) {
   const int frames = argc > 3 ? std::atoi(args[3]) : 5;
   const int cycles = argc > 4 ? std::atoi(args[4]) : 8 * size;    // world.erode(8*quad::tilesize), :217
   World::mode = argc > 5 ? std::atoi(args[5]) : SWE_MODE_PARALLEL;
+  const int noise_layers = argc > 6 ? std::atoi(args[6]) : 0;     // cellpool.h:388-411 (commented out there)
   try {
     World::SEED = seed;
     World::init(size, size);          // cellpool.reserve(quad::area)            :36
     World::seed(seed);                // srand(SEED)                             :27-34
-    World::map.init(World::SEED);     // World::map.init(vertexpool, cellpool, SEED) :38
+    World::map.init(World::SEED, noise_layers);   // World::map.init(vertexpool, cellpool, SEED) :38
     for (int n = 0; n < frames; n++) {
       World::erode(cycles);           // :217
       World::map.sync_render_fields_from_device();   // what updatenode / windmap read, :219-230

@@ -100,9 +100,12 @@ struct map {
       swe::check(swe_download_plane(engine, pl, &cells[0].height + pl, sizeof(cell)));
   }
 
-  // quad::map::init (cellpool.h:339-430), host-side like the reference: zero the cells, add
-  // the Gaussian hill, normalise to [0, 0.5]; then hand the pool to the device.
-  void init(int /*SEED*/) {
+  // quad::map::init (cellpool.h:339-430): zero the cells, add the Gaussian hill (host: it needs
+  // libm's double exp), optionally the `noise_layers` layers of FastNoiseLite OpenSimplex2 FBm
+  // that the reference carries as a comment (cellpool.h:388-411; generated on the device,
+  // bitwise identical to the host library), normalise to [0, 0.5] (cellpool.h:416-428).
+  // The reference's active code is noise_layers = 0.
+  void init(int SEED, int noise_layers = 0) {
     for (cell& c : cells) c = cell{};
     const int n = nx;
     const float cx = (float)(n / 4) / (float)n, cz = (float)(n / 2) / (float)n;
@@ -112,10 +115,12 @@ struct map {
         const float d = std::sqrt(dx * dx + dz * dz);
         cells[(size_t)x * nz + z].height = (float)std::exp((double)(-d * d * (float)n) * 0.2);
       }
-    float mn = 0.0f, mx = 0.0f;
-    for (const cell& c : cells) { mn = (mn < c.height) ? mn : c.height; mx = (mx > c.height) ? mx : c.height; }
-    for (cell& c : cells) c.height = (float)(0.5 * (double)((c.height - mn) / (mx - mn)));
     sync_to_device();
+    if (noise_layers > 0) swe::check(swe_generate_noise(engine, SEED, noise_layers, n));
+    float mn = 0.0f, mx = 0.0f;
+    swe::check(swe_height_range(engine, &mn, &mx));
+    swe::check(swe_normalize_height(engine, mn, mx));
+    swe::check(swe_download_plane(engine, SWE_HEIGHT, &cells[0].height, sizeof(cell)));
   }
 };
 

@@ -128,7 +128,7 @@ void swo_set_rock(swo_world* w, const float* rock) {
 }
 
 /* cellpool.h:372-428 (mapsize = 1: node.pos = 0, tileres = (n,n), lodsize = 1) */
-void swo_init_gaussian(swo_world* w) {
+void swo_hill_raw(swo_world* w) {
   const int n = w->nx;
   float* H = w->plane[0];
   for (int i = 1; i < 9; i++) memset(w->plane[i], 0, sizeof(float) * (size_t)w->nx * w->nz);
@@ -142,14 +142,11 @@ void swo_init_gaussian(swo_world* w) {
       /* exp(-d*d*quad::tilesize*0.2): float*float, *int -> float, *0.2 -> double exp */
       H[(size_t)x * w->nz + z] = (float)exp((double)(-d * d * (float)n) * 0.2);
     }
-  /* :416-428 min/max start at 0.0f; height = 0.5*((h-min)/(max-min)) (0.5 is double) */
-  float mn = 0.0f, mx = 0.0f;
-  for (size_t i = 0; i < (size_t)w->nx * w->nz; i++) {
-    mn = (mn < H[i]) ? mn : H[i];
-    mx = (mx > H[i]) ? mx : H[i];
-  }
-  for (size_t i = 0; i < (size_t)w->nx * w->nz; i++)
-    H[i] = (float)(0.5 * (double)((H[i] - mn) / (mx - mn)));
+}
+
+void swo_init_gaussian(swo_world* w) {
+  swo_hill_raw(w);
+  swo_normalize(w);   /* :416-428 */
 }
 
 /* ---- glm scalar semantics (see header) ---- */
@@ -505,19 +502,23 @@ float swo_fnl_getnoise(float frequency, float x, float y, float z) {
 
 /* The layer loop of cellpool.h:392-409: frequency 1,2,4,...; scale 0.6, *= 0.6 (double product
  * rounded to float); p = cell / tile; third coordinate (float)(SEED % 10000). Adds to height. */
-void swo_noise_stack(swo_world* w, int seed, int layers, int tile) {
-  float* H = w->plane[0];
+void swo_noise_rows(float* H, int x_lo, int x_hi, int nz, int seed, int layers, int tile) {
+  /* H = rows [x_lo, x_hi) of the map (a band, so that callers can split the work) */
   float frequency = 1.0f, scale = 0.6f;
   const float zc = (float)(seed % 10000);
   for (int o = 0; o < layers; o++) {
-    for (int x = 0; x < w->nx; x++)
-      for (int z = 0; z < w->nz; z++) {
+    for (int x = x_lo; x < x_hi; x++)
+      for (int z = 0; z < nz; z++) {
         const float px = (float)x / (float)tile, pz = (float)z / (float)tile;
-        H[(size_t)x * w->nz + z] += scale * swo_fnl_getnoise(frequency, px, pz, zc);
+        H[(size_t)(x - x_lo) * nz + z] += scale * swo_fnl_getnoise(frequency, px, pz, zc);
       }
     frequency *= 2;
     scale = (float)((double)scale * 0.6);
   }
+}
+
+void swo_noise_stack(swo_world* w, int seed, int layers, int tile) {
+  swo_noise_rows(w->plane[0], 0, w->nx, w->nz, seed, layers, tile);
 }
 
 /* cellpool.h:416-428: min and max start at 0.0f; height = 0.5*((h-min)/(max-min)). */

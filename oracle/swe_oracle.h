@@ -87,6 +87,7 @@ float swo_expf(float x);
 
 /* cellpool.h:372-428 for a single tile of edge nx==nz (Gaussian hill, normalised to [0,0.5]) */
 void swo_init_gaussian(swo_world* w);
+void swo_hill_raw(swo_world* w);   /* the Gaussian hill of cellpool.h:378-385 before normalisation */
 
 void swo_normal(const swo_world* w, int x, int z, float out[3]);
 void swo_spawn(swo_world* w, swo_particle* q);            /* world.hpp:52-54 + Wind ctor */
@@ -102,6 +103,7 @@ uint64_t swo_hash_height(const swo_world* w);             /* FNV-1a-64 over fp32
 float swo_fnl_single3(int seed, float x, float y, float z);            /* SingleOpenSimplex2 3D */
 float swo_fnl_getnoise(float frequency, float x, float y, float z);    /* GetNoise, FBm of 3 octaves */
 void swo_noise_stack(swo_world* w, int seed, int layers, int tile);    /* height += layers of noise */
+void swo_noise_rows(float* rows, int x_lo, int x_hi, int nz, int seed, int layers, int tile);  /* same, one band */
 void swo_normalize(swo_world* w);                                      /* cellpool.h:416-428 */
 
 #ifdef __cplusplus

@@ -61,6 +61,7 @@ def port():
         L.swo_expf.argtypes = [C.c_float]
         L.swo_expf.restype = C.c_float
         L.swo_init_gaussian.argtypes = [W]
+        L.swo_hill_raw.argtypes = [W]
         L.swo_normal.argtypes = [W, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.swo_fly.argtypes = [W, C.POINTER(OParticle)]
         L.swo_fly.restype = C.c_int
@@ -80,6 +81,7 @@ def port():
         L.swo_fnl_getnoise.restype = C.c_float
         L.swo_noise_stack.argtypes = [W, C.c_int, C.c_int, C.c_int]
         L.swo_normalize.argtypes = [W]
+        L.swo_noise_rows.argtypes = [C.c_void_p] + [C.c_int] * 6
         _port = L
     return _port
 
@@ -136,6 +138,10 @@ class PortWorld:
 
     def init_gaussian(self) -> None:
         self.L.swo_init_gaussian(self.w)
+
+    def hill_raw(self) -> None:
+        """the Gaussian hill before normalisation (cellpool.h:378-385)"""
+        self.L.swo_hill_raw(self.w)
 
     def erode(self, cycles: int) -> OStats:
         st = OStats()
@@ -266,6 +272,31 @@ class RefWorld:
 
     def get_noise(self, frequency: float, x: float, y: float, z: float) -> float:
         return self.L.ref_get_noise(frequency, x, y, z)
+
+
+def _noise_band(args):
+    x_lo, x_hi, nz, seed, layers, tile = args
+    band = np.zeros((x_hi - x_lo, nz), dtype=np.float32)
+    port().swo_noise_rows(band.ctypes.data, x_lo, x_hi, nz, seed, layers, tile)
+    return band
+
+
+def noise_map(nx: int, nz: int | None = None, seed: int = 1, layers: int = 8, workers: int = 1) -> np.ndarray:
+    """The map::init noise layers on a zero map, normalised (cellpool.h:388-428), computed by the
+    oracle port on `workers` host threads (row bands are independent)."""
+    nz = nx if nz is None else nz
+    edges = np.linspace(0, nx, max(1, min(workers, nx)) * 4 + 1).astype(int)
+    jobs = [(int(a), int(b), nz, seed, layers, nz) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    if workers <= 1:
+        bands = [_noise_band(j) for j in jobs]
+    else:
+        from concurrent.futures import ThreadPoolExecutor   # ctypes drops the GIL inside the C call
+        port()
+        with ThreadPoolExecutor(workers) as pool:
+            bands = list(pool.map(_noise_band, jobs))
+    h = np.concatenate(bands, axis=0)
+    mn, mx = np.float32(min(0.0, h.min())), np.float32(max(0.0, h.max()))
+    return (np.float32(0.5) * ((h - mn) / (mx - mn))).astype(np.float32)
 
 
 def fnv1a64_f32(a: np.ndarray) -> int:

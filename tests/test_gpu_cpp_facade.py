@@ -52,3 +52,20 @@ def test_cpp_main_loop_parallel_mode_runs(tmp_path):
     out = subprocess.check_output([exe, "256", "3", "2", "2048", "1"], text=True)
     got = dict(kv.split("=") for kv in out.split())
     assert int(got["steps"]) > 100000 and int(got["oob"]) + int(got["age"]) == 4096
+
+
+@pytest.mark.gpu
+def test_cpp_init_with_noise_layers_matches_oracle(tmp_path):
+    """map::init with the reference's commented noise layers enabled: Gaussian hill on the host,
+    eight FastNoiseLite layers and the normalisation on the device, then a deterministic erode."""
+    exe = _build(tmp_path)
+    out = subprocess.check_output([exe, "64", "7", "1", "256", "0", "8"], text=True)
+    got = dict(kv.split("=") for kv in out.split())
+    raw = PortWorld(64)
+    raw.hill_raw()
+    raw.noise_stack(7, 8)
+    raw.normalize()
+    raw.srand(7)
+    steps = raw.erode(256).steps
+    assert int(got["steps"]) == steps
+    assert got["hash"] == f"{raw.hash_height():016x}"
