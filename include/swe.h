@@ -148,6 +148,15 @@ int swe_set_option(swe_engine* e, int option, int value);
  * replica and the parallel mode's counter-based generator. */
 int swe_srand(swe_engine* e, uint32_t seed);
 
+/* Run state for checkpoint / resume: the libc-rand replica of the deterministic mode (the
+ * reference's stream is process-global and continues across World::erode calls), the seed and the
+ * World::erode call index of the parallel mode's counter-based generator. Together with the nine
+ * planes (swe_download_cells) this is everything a run needs to continue: a deterministic run
+ * resumed from it is bitwise identical to the uninterrupted one. */
+#define SWE_STATE_BYTES 256
+int swe_export_state(swe_engine* e, void* buf, size_t bytes);
+int swe_import_state(swe_engine* e, const void* buf, size_t bytes);
+
 /* ---- map transfer (host buffers) --------------------------------------------------- */
 /* Write / read one quad::cell member for every cell. `stride_bytes` is the distance
  * between consecutive cells in the host buffer (4 = packed plane, 36 = reference AoS). */
@@ -210,6 +219,18 @@ int swe_height(swe_engine* e, int x, int z, float* out);
 /* normals for every cell (what updatenode reads each frame, cellpool.h:302-321):
  * dst = nx*nz*3 floats. */
 int swe_download_normals(swe_engine* e, float* dst);
+
+/* The Vertex records updatenode writes for every cell each frame (cellpool.h:302-321,
+ * vertexpool.hpp:6-26): 12 floats = 48 bytes per cell, index x*nz + z (math::flatten):
+ *   position = (x, mapscale*height, z), normal = map.normal(p),
+ *   tangent = T - P, bitangent = B - P   (T, B: the surface at (x+1, z), (x, z+1); outside the map
+ *   the height is 0, cellpool.h:257-261).
+ * swe_download_vertices fills a host buffer of nx*nz*48 bytes; swe_write_vertices_device writes the
+ * same records to DEVICE memory on the engine's stream without a host round trip -- e.g. the
+ * CUDA-mapped pointer of the renderer's persistently mapped vertex buffer (vertexpool.hpp:155-172);
+ * 16-byte aligned, not synchronised: use swe_sync or the stream. */
+int swe_download_vertices(swe_engine* e, void* dst);
+int swe_write_vertices_device(swe_engine* e, void* device_dst);
 
 /* ---- generate (host generate of the reference, run on the device) ------------------- */
 /* The noise layers of quad::map::init (cellpool.h:388-411; a comment in the mounted snapshot):

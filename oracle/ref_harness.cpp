@@ -27,15 +27,23 @@ using namespace std;
 typedef unsigned int uint;
 
 // ---- render-memory stub (source/vertexpool.hpp is OpenGL; out of scope) -----------------
+// The stub keeps what updatenode hands to fill() (cellpool.h:312-317: position, normal, tangent,
+// bitangent for vertex k) so that ref_updatenode can return the reference's own vertex records.
 struct Vertex {};
+static std::vector<float> g_vertices;   // 12 floats per vertex once ref_updatenode ran
 template <typename T> struct Vertexpool {
   std::vector<unsigned int> indices;
   uint dummy = 0;
+  void fill(uint*, int k, glm::vec3 p, glm::vec3 n, glm::vec3 t, glm::vec3 b) {
+    if ((size_t)(k + 1) * 12 > g_vertices.size()) return;
+    float* v = &g_vertices[(size_t)k * 12];
+    v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = n.x; v[4] = n.y; v[5] = n.z;
+    v[6] = t.x; v[7] = t.y; v[8] = t.z; v[9] = b.x; v[10] = b.y; v[11] = b.z;
+  }
   uint* section(int, int, glm::vec3, size_t) { return &dummy; }
   void resize(const uint*, size_t) {}
   void index() { indices.clear(); indices.shrink_to_fit(); }  // keep the harness small in RAM
   void update() {}
-  template <typename... A> void fill(uint*, int, A&&...) {}
   void reserve(int, int) {}
 };
 
@@ -216,6 +224,15 @@ double ref_sum_height() {
   double s = 0;
   for (int i = 0; i < quad::area; i++) s += cellpool.root.start[i].height;
   return s;
+}
+
+// quad::updatenode (cellpool.h:302-321), the reference's own per-frame vertex update, for every
+// node; out = quad::area records of 12 floats (Vertex layout, vertexpool.hpp:6-26).
+void ref_updatenode(float* out) {
+  g_vertices.assign((size_t)quad::area * 12, 0.0f);
+  for (auto& node : World::map.nodes) quad::updatenode(vertexpool, node);
+  std::memcpy(out, g_vertices.data(), g_vertices.size() * sizeof(float));
+  g_vertices.clear(); g_vertices.shrink_to_fit();
 }
 
 // ---- host generate, noise stack -------------------------------------

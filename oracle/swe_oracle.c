@@ -529,3 +529,23 @@ void swo_normalize(swo_world* w) {
   for (size_t i = 0; i < n; i++) { mn = (mn < H[i]) ? mn : H[i]; mx = (mx > H[i]) ? mx : H[i]; }
   for (size_t i = 0; i < n; i++) H[i] = (float)(0.5 * (double)((H[i] - mn) / (mx - mn)));
 }
+
+/* quad::updatenode, cellpool.h:302-321: the 12-float Vertex (vertexpool.hpp:6-26) of every cell --
+ * P = (x, mapscale*h, z), normal, T - P, B - P with T/B the surface at (x+1,z)/(x,z+1); a
+ * neighbour outside the map has height 0 (node::height, cellpool.h:257-261). */
+void swo_vertices(const swo_world* w, float* out) {
+  const float ms = (float)w->p.mapscale;
+  for (int x = 0; x < w->nx; x++)
+    for (int z = 0; z < w->nz; z++) {
+      float* v = out + ((size_t)x * w->nz + z) * 12;
+      const float px = (float)x, pz = (float)z;
+      const float py = ms * HGT(w, x, z);
+      const float ty = ms * (oob(w, x + 1, z) ? 0.0f : HGT(w, x + 1, z));
+      const float by = ms * (oob(w, x, z + 1) ? 0.0f : HGT(w, x, z + 1));
+      v3 n = normal_v3(w, x, z);
+      v[0] = px; v[1] = py; v[2] = pz;
+      v[3] = n.x; v[4] = n.y; v[5] = n.z;
+      v[6] = (float)(x + 1) - px; v[7] = ty - py; v[8] = pz - pz;
+      v[9] = px - px; v[10] = by - py; v[11] = (float)(z + 1) - pz;
+    }
+}

@@ -99,6 +99,7 @@ void swo_cascade_sweep(swo_world* w, int sweeps);         /* 9-colour order, c=0
 float swo_max_excess(const swo_world* w);                 /* max over pairs of |dh| - d*maxdiff (<=0: relaxed) */
 int  swo_trace(swo_world* w, float x, float z, int max_records, float* out8);
 uint64_t swo_hash_height(const swo_world* w);             /* FNV-1a-64 over fp32 words */
+void swo_vertices(const swo_world* w, float* out12);       /* updatenode, cellpool.h:302-321: 12 floats per cell */
 /* host generate, noise stack (cellpool.h:366-368,388-411 + FastNoiseLite.h; see swe_oracle.c) */
 float swo_fnl_single3(int seed, float x, float y, float z);            /* SingleOpenSimplex2 3D */
 float swo_fnl_getnoise(float frequency, float x, float y, float z);    /* GetNoise, FBm of 3 octaves */

@@ -75,6 +75,7 @@ class StripeLink(C.Structure):
 
 
 STRIPE_IPC_BYTES = 256
+STATE_BYTES = 256
 
 # name -> (restype, argtypes); must list every symbol include/swe.h declares
 _E = C.c_void_p
@@ -101,6 +102,8 @@ PROTOTYPES = {
     "swe_stripe_group_sweep": (C.c_int, [C.POINTER(_E), C.c_int, C.c_int]),
     "swe_stripe_group_sync_halos": (C.c_int, [C.POINTER(_E), C.c_int]),
     "swe_srand": (C.c_int, [_E, C.c_uint32]),
+    "swe_export_state": (C.c_int, [_E, C.c_void_p, C.c_size_t]),
+    "swe_import_state": (C.c_int, [_E, C.c_void_p, C.c_size_t]),
     "swe_upload_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_download_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_upload_cells": (C.c_int, [_E, C.c_void_p]),
@@ -121,6 +124,8 @@ PROTOTYPES = {
     "swe_normal": (C.c_int, [_E, C.c_int, C.c_int, _F]),
     "swe_height": (C.c_int, [_E, C.c_int, C.c_int, _F]),
     "swe_download_normals": (C.c_int, [_E, C.c_void_p]),
+    "swe_download_vertices": (C.c_int, [_E, C.c_void_p]),
+    "swe_write_vertices_device": (C.c_int, [_E, C.c_void_p]),
     "swe_generate_noise": (C.c_int, [_E, C.c_int, C.c_int, C.c_int]),
     "swe_height_range": (C.c_int, [_E, _F, _F]),
     "swe_normalize_height": (C.c_int, [_E, C.c_float, C.c_float]),

@@ -627,6 +627,45 @@ int swe_srand(swe_engine* e, uint32_t seed) {
   return check_launch(e, "srand");
 }
 
+// ---- run state (checkpoint / resume) ----------------------------------------------------------
+namespace {
+struct RunState {                 // the SWE_STATE_BYTES blob
+  char magic[8];                  // "SWESTAT1"
+  uint64_t seed;
+  uint32_t call_index;
+  uint32_t pad;
+  DetRand rng;                    // glibc TYPE_3 ring of the deterministic mode
+};
+static_assert(sizeof(RunState) <= SWE_STATE_BYTES, "state blob too small");
+}  // namespace
+
+int swe_export_state(swe_engine* e, void* buf, size_t bytes) {
+  if (int rc = bind(e)) return rc;
+  if (!buf || bytes < SWE_STATE_BYTES) return fail(SWE_ERR_INVALID, "state buffer must hold SWE_STATE_BYTES");
+  RunState st{};
+  memcpy(st.magic, "SWESTAT1", 8);
+  st.seed = e->seed; st.call_index = e->call_index;
+  SWE_CUDA(cudaMemcpyAsync(&st.rng, e->d_rng, sizeof(DetRand), cudaMemcpyDeviceToHost, e->stream));
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  memset(buf, 0, SWE_STATE_BYTES);
+  memcpy(buf, &st, sizeof st);
+  return SWE_OK;
+}
+
+int swe_import_state(swe_engine* e, const void* buf, size_t bytes) {
+  if (int rc = bind(e)) return rc;
+  if (!buf || bytes < SWE_STATE_BYTES) return fail(SWE_ERR_INVALID, "state buffer must hold SWE_STATE_BYTES");
+  RunState st;
+  memcpy(&st, buf, sizeof st);
+  if (memcmp(st.magic, "SWESTAT1", 8) != 0) return fail(SWE_ERR_INVALID, "not a swe state blob");
+  if (st.rng.f < 0 || st.rng.f >= 31 || st.rng.b < 0 || st.rng.b >= 31) return fail(SWE_ERR_INVALID, "corrupt state blob");
+  e->seed = st.seed; e->call_index = st.call_index;
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  SWE_CUDA(cudaMemcpyAsync(e->d_rng, &st.rng, sizeof(DetRand), cudaMemcpyHostToDevice, e->stream));
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  return SWE_OK;
+}
+
 // ---- transfers ----------------------------------------------------------------------------
 int swe_upload_plane(swe_engine* e, int plane, const float* src, ptrdiff_t stride_bytes) {
   if (int rc = bind(e)) return rc;
@@ -1005,6 +1044,28 @@ int swe_download_normals(swe_engine* e, float* dst) {
   SWE_CUDA(cudaMemcpyAsync(dst, e->d_scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
   return SWE_OK;
+}
+
+// updatenode (cellpool.h:302-321): one 48-byte Vertex per cell, to a host buffer or straight into
+// device memory (a CUDA-mapped OpenGL vertex buffer, vertexpool.hpp:155-172)
+int swe_download_vertices(swe_engine* e, void* dst) {
+  if (int rc = bind(e)) return rc;
+  if (!dst) return fail(SWE_ERR_INVALID, "dst is NULL");
+  const size_t bytes = e->host_cells() * 48;
+  if (int rc = need_scratch(e, bytes)) return rc;
+  launch_vertices_rows(e->m, e->p, e->own_lo(), e->own_hi(), e->d_scratch, e->stream);
+  if (int rc = check_launch(e, "vertices")) return rc;
+  SWE_CUDA(cudaMemcpyAsync(dst, e->d_scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  return SWE_OK;
+}
+
+int swe_write_vertices_device(swe_engine* e, void* device_dst) {
+  if (int rc = bind(e)) return rc;
+  if (!device_dst) return fail(SWE_ERR_INVALID, "device_dst is NULL");
+  if (reinterpret_cast<uintptr_t>(device_dst) & 15u) return fail(SWE_ERR_INVALID, "device_dst must be 16-byte aligned");
+  launch_vertices_rows(e->m, e->p, e->own_lo(), e->own_hi(), device_dst, e->stream);
+  return check_launch(e, "vertices");
 }
 
 // ---- generate --------------------------------------------------------------

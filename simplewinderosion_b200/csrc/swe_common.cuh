@@ -63,6 +63,8 @@ void launch_det_cascade_one(const MapView& m, const swe_params& p, int x, int z,
 void launch_det_srand(DetRand* rng, uint32_t seed, cudaStream_t st);
 void launch_normals_rows(const MapView& m, const swe_params& p, int row_lo, int row_hi, float* d_out3,
                          cudaStream_t st);
+void launch_vertices_rows(const MapView& m, const swe_params& p, int row_lo, int row_hi, void* d_out48,
+                          cudaStream_t st);
 void launch_normal_one(const MapView& m, const swe_params& p, int x, int z, float* d_out3,
                        cudaStream_t st);
 

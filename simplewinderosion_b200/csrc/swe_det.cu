@@ -215,6 +215,29 @@ __global__ void normals_kernel(MapView m, swe_params P, int row_lo, int row_hi, 
   }
 }
 
+// The Vertex record updatenode writes for every cell each frame (cellpool.h:302-321,
+// vertexpool.hpp:6-26): position = (x, mapscale*h, z), normal = map.normal(p), tangent = T - P and
+// bitangent = B - P with T, B the surface points at (x+1, z) and (x, z+1); a neighbour outside the
+// map has height 0 (node::height, cellpool.h:257-261). 12 floats = 48 B per cell, written as three
+// 16-byte stores; 4 B read + 48 B written per cell, HBM-bound.
+__global__ void vertices_kernel(MapView m, swe_params P, int row_lo, int row_hi, float4* __restrict__ out) {
+  const size_t n = (size_t)(row_hi - row_lo) * m.nz;
+  const float scale = (float)P.mapscale;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int x = row_lo + (int)(i / m.nz), z = (int)(i % m.nz);
+    const V3 nn = normal(m, P, x, z);
+    const float py = fmul(scale, m.height[m.idx(x, z)]);
+    const float ty = fmul(scale, m.oob(x + 1, z) ? 0.0f : m.height[m.idx(x + 1, z)]);
+    const float by = fmul(scale, m.oob(x, z + 1) ? 0.0f : m.height[m.idx(x, z + 1)]);
+    const float fx = (float)x, fz = (float)z;
+    const float tx = fsub((float)(x + 1), fx), bz = fsub((float)(z + 1), fz);   // 1 below 2^24
+    out[3 * i + 0] = make_float4(fx, py, fz, nn.x);
+    out[3 * i + 1] = make_float4(nn.y, nn.z, tx, fsub(ty, py));
+    out[3 * i + 2] = make_float4(fsub(fz, fz), fsub(fx, fx), fsub(by, py), bz);
+  }
+}
+
 __global__ void normal_one_kernel(MapView m, swe_params P, int x, int z, float* out3) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const V3 nn = normal(m, P, x, z);
@@ -248,6 +271,13 @@ void launch_normals_rows(const MapView& m, const swe_params& p, int row_lo, int 
   if (blocks > 148 * 16) blocks = 148 * 16;
   normals_kernel<<<blocks, 256, 0, st>>>(m, p, row_lo, row_hi, d_out3);
 }
+void launch_vertices_rows(const MapView& m, const swe_params& p, int row_lo, int row_hi, void* d_out48,
+                          cudaStream_t st) {
+  const size_t n = (size_t)(row_hi - row_lo) * m.nz;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  vertices_kernel<<<blocks, 256, 0, st>>>(m, p, row_lo, row_hi, static_cast<float4*>(d_out48));
+}
 void launch_normal_one(const MapView& m, const swe_params& p, int x, int z, float* d_out3,
                        cudaStream_t st) {
   normal_one_kernel<<<1, 32, 0, st>>>(m, p, x, z, d_out3);
@@ -263,6 +293,7 @@ void preload_det() {
   cudaFuncGetAttributes(&a, det_fly_once_kernel);
   cudaFuncGetAttributes(&a, det_cascade_one_kernel);
   cudaFuncGetAttributes(&a, normals_kernel);
+  cudaFuncGetAttributes(&a, vertices_kernel);
   cudaFuncGetAttributes(&a, normal_one_kernel);
 }
 

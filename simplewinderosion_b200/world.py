@@ -196,6 +196,17 @@ class World:
         check(lib.swe_download_normals(self._h, out.ctypes.data))
         return out
 
+    def vertices(self) -> np.ndarray:
+        """The (nx, nz, 12) Vertex records updatenode writes each frame (cellpool.h:302-321):
+        position, normal, tangent, bitangent."""
+        out = np.empty((self.nx, self.nz, 12), dtype=np.float32)
+        check(lib.swe_download_vertices(self._h, out.ctypes.data))
+        return out
+
+    def write_vertices_device(self, device_ptr: int) -> None:
+        """Same records straight into device memory (a CUDA-mapped vertex buffer), asynchronously."""
+        check(lib.swe_write_vertices_device(self._h, C.c_void_p(device_ptr)))
+
     # -- generate (quad::map::init on the device) -------------------------------------------------
     def generate_noise(self, seed: int, layers: int = 8, tile: int = 0) -> None:
         """height += the FastNoiseLite OpenSimplex2-FBm layers of map::init (cellpool.h:388-411);

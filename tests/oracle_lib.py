@@ -81,6 +81,7 @@ def port():
         L.swo_fnl_getnoise.restype = C.c_float
         L.swo_noise_stack.argtypes = [W, C.c_int, C.c_int, C.c_int]
         L.swo_normalize.argtypes = [W]
+        L.swo_vertices.argtypes = [W, C.c_void_p]
         L.swo_noise_rows.argtypes = [C.c_void_p] + [C.c_int] * 6
         _port = L
     return _port
@@ -169,6 +170,12 @@ class PortWorld:
 
     def hash_height(self) -> int:
         return self.L.swo_hash_height(self.w)
+
+    def vertices(self) -> np.ndarray:
+        """(nx, nz, 12): the Vertex records of updatenode (cellpool.h:302-321)."""
+        out = np.empty((self.nx, self.nz, 12), dtype=np.float32)
+        self.L.swo_vertices(self.w, out.ctypes.data)
+        return out
 
     def noise_stack(self, seed: int, layers: int = 8, tile: int | None = None) -> None:
         """height += the FastNoiseLite layer stack of cellpool.h:392-409."""
@@ -263,6 +270,13 @@ class RefWorld:
 
     def sum_height(self) -> float:
         return self.L.ref_sum_height()
+
+    def vertices(self) -> np.ndarray:
+        """quad::updatenode run by the reference itself; the harness' Vertexpool stub records it."""
+        out = np.empty((self.n, self.n, 12), dtype=np.float32)
+        self.L.ref_updatenode.argtypes = [C.c_void_p]
+        self.L.ref_updatenode(out.ctypes.data)
+        return out
 
     def noise_stack(self, seed: int, layers: int = 8) -> None:
         self.L.ref_noise_stack(seed, layers)
