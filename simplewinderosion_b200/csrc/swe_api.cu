@@ -519,8 +519,9 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
   TRY(cudaMemsetAsync(e->m.field, 0, n * sizeof(float4), e->stream));
   TRY(cudaMemsetAsync(e->m.track, 0, n * sizeof(float4), e->stream));
   TRY(cudaMalloc(&e->tsc.stage, n * sizeof(float)));
-  TRY(cudaMalloc(&e->tsc.flags, tile_flag_count(e->m)));
-  TRY(cudaMemsetAsync(e->tsc.flags, 0, tile_flag_count(e->m), e->stream));
+  TRY(cudaMalloc(&e->tsc.flags, 2 * tile_flag_count(e->m)));                    // flags, then hints
+  TRY(cudaMemsetAsync(e->tsc.flags, 0, 2 * tile_flag_count(e->m), e->stream));
+  e->tsc.hint = e->tsc.flags + tile_flag_count(e->m);
   TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(DevStats), e->stream));
   if (stripe) {
     TRY(cudaMalloc(&e->d_stamp, n));

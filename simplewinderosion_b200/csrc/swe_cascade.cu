@@ -62,12 +62,17 @@ __global__ void cascade_colour_kernel(MapView m, swe_params P, int cx, int cz, i
 // =============================================================================================
 constexpr int TILE_TX = 60, TILE_TZ = 216;                  // TZ: multiple of 3 and of 4
 constexpr int TILE_LX = TILE_TX + 6, TILE_PITCH = TILE_TZ + 24;
-constexpr int TILE_BX = TILE_TZ / 3 + 8, TILE_BY = 6;       // 80 x 6 = 480 threads
-constexpr int TILE_THREADS = TILE_BX * TILE_BY;
+constexpr int TILE_BX = TILE_TZ / 3 + 8, TILE_BY = 6;       // dense scan: 80 x 6 centre slots (threads 0..479)
+constexpr int TILE_THREADS = 512;                           // 16 warps: the pair scan wants 8 column strips x 2
 constexpr int TILE_OX = -2, TILE_OZ = -8;                   // tile grid origin: == 1 (mod 3); z also == 0 (mod 4)
 constexpr int TILE_FLOAT_BYTES = TILE_LX * TILE_PITCH * 4;  // 63,360 B   height tile
 constexpr int TILE_QUEUE_BYTES = ((TILE_LX / 3) * (TILE_PITCH / 3) * 2 + 15) / 16 * 16;  // centres of one colour
-constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 16;   // + queue counters, mbarrier
+// pair-bitmap mode (see tile_pair_scan): a second queue and two bit planes (one bit per tile cell)
+// (bit planes are COLUMN-major: word [col][row >> 5], bit row & 31 -- a lane of the pair scan owns a column)
+constexpr int MASK_WORDS = (TILE_LX + 31) / 32;             // 3 words per tile column
+constexpr int TILE_MASK_BYTES = TILE_PITCH * MASK_WORDS * 4;   // 2,880 B per bit plane
+constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + 2 * TILE_QUEUE_BYTES + 2 * TILE_MASK_BYTES + 128;  // + counters, mbarrier
+static_assert(TILE_PITCH == 8 * 30, "tile_pair_scan walks the tile in 8 groups of 30 columns");
 
 __device__ __forceinline__ void cswap_desc(unsigned& a, unsigned& b) {
   const unsigned hi = max(a, b), lo = min(a, b);
@@ -167,9 +172,11 @@ __device__ __forceinline__ unsigned height_key(float h, bool valid, unsigned cod
 // one element of the transfer chain (world.hpp:122-151), branch-free; thresholds >= 0 so that
 // diff == 0 implies excess <= 0 and the reference's explicit diff == 0 test is subsumed.
 // LAYERED (extension): the transfer is capped by the giving cell's sand, height - rock.
-template <bool LAYERED>
+// TRACK: `moved` collects bit `code` of every neighbour whose transfer ran (pair-bitmap mode).
+template <bool LAYERED, bool TRACK = false>
 __device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, const CascadeThr thr,
-                                           float settling, const float* rock_c_ptr, int nz, float rock_c) {
+                                           float settling, const float* rock_c_ptr, int nz, float rock_c,
+                                           unsigned* moved = nullptr) {
   const unsigned code = 15u - (k & 15u);
   const int dxm = (int)(code >> 2) - 1, dzm = (int)(code & 3u) - 1;
   float* hp = tc + dxm * TILE_PITCH + dzm;
@@ -189,13 +196,15 @@ __device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, con
   }
   const float sgn = (diff > 0.0f) ? transfer : -transfer;        // diff > 0: centre gives, else takes
   if (go) { cc = fsub(cc, sgn); *hp = fadd(hv, sgn); }
+  if (TRACK && go) *moved |= 1u << code;
 }
 
 // World::cascade at one centre of the tile whose early-out test failed.
-template <bool INTERIOR, bool LAYERED = false>
+// TRACK: *moved gets one bit per 3x3 cell whose value may have changed, bit (dx+1)*4 + (dz+1).
+template <bool INTERIOR, bool LAYERED = false, bool TRACK = false>
 __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, float settling, float hs,
                                              const Valid8 v, int gx, int gz, int nx, int nz,
-                                             const float* rock_c_ptr = nullptr) {
+                                             const float* rock_c_ptr = nullptr, unsigned* moved = nullptr) {
   unsigned k0 = height_key(tc[-TILE_PITCH - 1], v.v0, 0), k1 = height_key(tc[-TILE_PITCH], v.v1, 1),
            k2 = height_key(tc[-TILE_PITCH + 1], v.v2, 2), k3 = height_key(tc[-1], v.v3, 4),
            k4 = height_key(tc[1], v.v4, 6), k5 = height_key(tc[TILE_PITCH - 1], v.v5, 8),
@@ -212,17 +221,142 @@ __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, fl
   unsigned close = min(min(k0 ^ k1, (k2 ? k1 ^ k2 : ~0u)), min((k3 ? k2 ^ k3 : ~0u), (k4 ? k3 ^ k4 : ~0u)));
   close = min(close, min(min((k5 ? k4 ^ k5 : ~0u), (k6 ? k5 ^ k6 : ~0u)), (k7 ? k6 ^ k7 : ~0u)));
   if ((INTERIOR || k1) && close < 16u) {
-    tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, LAYERED ? rock_c_ptr : nullptr);
+    const bool ch = tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, LAYERED ? rock_c_ptr : nullptr);
+    if (TRACK) *moved = ch ? 0x777u : 0u;
     return;
   }
   float cc = tc[0];
   const float rock_c = LAYERED ? __ldg(rock_c_ptr) : 0.0f;
   const int rnz = nz;
-  chain_step<LAYERED>(tc, k0, cc, thr, hs, rock_c_ptr, rnz, rock_c); chain_step<LAYERED>(tc, k1, cc, thr, hs, rock_c_ptr, rnz, rock_c);
-  chain_step<LAYERED>(tc, k2, cc, thr, hs, rock_c_ptr, rnz, rock_c); chain_step<LAYERED>(tc, k3, cc, thr, hs, rock_c_ptr, rnz, rock_c);
-  chain_step<LAYERED>(tc, k4, cc, thr, hs, rock_c_ptr, rnz, rock_c); chain_step<LAYERED>(tc, k5, cc, thr, hs, rock_c_ptr, rnz, rock_c);
-  chain_step<LAYERED>(tc, k6, cc, thr, hs, rock_c_ptr, rnz, rock_c); chain_step<LAYERED>(tc, k7, cc, thr, hs, rock_c_ptr, rnz, rock_c);
+  unsigned mv = 0u;
+  chain_step<LAYERED, TRACK>(tc, k0, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k1, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv);
+  chain_step<LAYERED, TRACK>(tc, k2, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k3, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv);
+  chain_step<LAYERED, TRACK>(tc, k4, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k5, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv);
+  chain_step<LAYERED, TRACK>(tc, k6, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k7, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv);
   tc[0] = cc;
+  if (TRACK) *moved = mv ? (mv | (1u << 5)) : 0u;      // the centre (code 5) moved iff any transfer ran
+}
+
+// =============================================================================================
+// Pair-bitmap mode of the whole-map tile kernel (interior tiles, reference parameters).
+//
+// Near the repose angle ~88 % of the centres have a pair whose excess is > 0 but only a few per
+// cent have one whose transfer changes a value in fp32, and proving "nothing moves" centre by
+// centre costs ~100 instructions (8 pairs, each tested from both of its ends over the sweep).
+// Here every neighbour pair of the tile is tested ONCE, before colour 0, with an integer test:
+//
+//   the transfer excess/2 (settling == 1) leaves a and b unchanged if excess < min(u(a), u(b)),
+//   u(v) = distance from |v| to the next float towards zero (= ulp(v), or ulp(v)/2 when |v| is a
+//   power of two; 0 for v == 0). Then excess/2 is below half the spacing on either side of both
+//   values and round-to-nearest returns them unchanged.
+//
+// Positive floats order like their bit patterns, so with key(v) = bits(u(v)) the test per pair is
+// two subtractions and two integer compares: bits(excess) >= key(a) or >= key(b) (a negative
+// excess has its sign bit set and compares below every key). Cells that are an end of such a
+// "hot" pair get a bit in `hot`; cells a relaxation changed get a bit in `chg`. A centre needs
+// the exact test only if its own hot bit is set or a cell of its 3x3 block changed earlier in this
+// sweep -- anything else provably keeps all its pairs cold. The candidates run the exact refined
+// test and the survivors the usual relaxation, so the result stays bitwise identical; the work per
+// cell drops from ~100 to ~30 instructions when little moves (measured fractions: DESIGN.md).
+// =============================================================================================
+__device__ __forceinline__ int ulp_key(float v) {
+  const int b = __float_as_int(v) & 0x7fffffff;
+  return ((max(b, 1) - 1) & 0x7f800000) - (23 << 23);   // bits of u(v); <= 0 for tiny |v| (always hot)
+}
+
+__device__ __forceinline__ bool pair_hot(float a, int ka, float b, int kb, float t) {
+  const int eb = __float_as_int(fsub(fabsf(fsub(a, b)), t));
+  return (eb >= ka) | (eb >= kb);
+}
+
+// bit i of `mask` = row row0 + i of column `col`
+__device__ __forceinline__ void mask_or(unsigned* plane, int col, int row0, unsigned mask) {
+  if (!mask) return;
+  const int word = row0 >> 5, sh = row0 & 31;
+  atomicOr(&plane[col * MASK_WORDS + word], mask << sh);
+  if (sh && word + 1 < MASK_WORDS && (mask >> (32 - sh))) atomicOr(&plane[col * MASK_WORDS + word + 1], mask >> (32 - sh));
+}
+
+// Phase A: each warp walks a strip of 30 columns (+ one halo column each side: lanes 0 and 31) down
+// a quarter of the tile's rows, the previous row in registers. A lane tests the four pairs that
+// need only its west neighbour's values (one shuffle pair per row): W (x,z)-(x,z-1), N (x,z)-(x-1,z),
+// NW (x,z)-(x-1,z-1) and the anti-diagonal AD (x-1,z)-(x,z-1). It collects the results as one bit
+// per row; the partner cells are credited once per strip with three shuffles, and the lane ORs its
+// column's bits into the column-major plane -- no ballots or atomics inside the row loop.
+__device__ __forceinline__ void tile_pair_scan(const float* tile, unsigned* hot, const CascadeThr thr,
+                                               int warp, int lane, int nwarps) {
+  constexpr int CHUNKS = 4;                                       // <= 17 rows + 1 run-in row: fits 32 bits
+  for (int item = warp; item < 8 * CHUNKS; item += nwarps) {
+    const int g = item & 7, q = item >> 3;
+    const int r0 = (TILE_LX * q) / CHUNKS, r1 = (TILE_LX * (q + 1)) / CHUNKS;
+    const int z = 30 * g - 1 + lane;
+    const bool zin = z >= 0 && z < TILE_PITCH;
+    const bool w_ok = zin && lane >= 1 && z >= 1;                 // partner column z-1 is in the strip and the tile
+    const int xs = r0 > 0 ? r0 - 1 : 0;                           // one row of run-in above the chunk
+    const float* col = tile + (zin ? z : 0);
+    float ph = 0.0f, phw = 0.0f;
+    int pk = 0, pkw = 0;
+    unsigned aW = 0u, aN = 0u, aNW = 0u, aAD = 0u;                // bit i: my pair of that kind at row xs + i is hot
+    {                                                             // run-in row (or row 0): state only, W pairs if owned
+      const float h = zin ? col[xs * TILE_PITCH] : 0.0f;
+      const int k = ulp_key(h);
+      const float hw = __shfl_up_sync(0xffffffffu, h, 1);
+      const int kw = __shfl_up_sync(0xffffffffu, k, 1);
+      if (xs >= r0 && w_ok && pair_hot(h, k, hw, kw, thr.ortho)) aW |= 1u;
+      ph = h; phw = hw; pk = k; pkw = kw;
+    }
+#pragma unroll 4
+    for (int x = xs + 1; x < r1; x++) {
+      const float h = zin ? col[x * TILE_PITCH] : 0.0f;
+      const int k = ulp_key(h);
+      const float hw = __shfl_up_sync(0xffffffffu, h, 1);
+      const int kw = __shfl_up_sync(0xffffffffu, k, 1);
+      const unsigned bit = 1u << (x - xs);
+      if (zin && pair_hot(h, k, ph, pk, thr.ortho)) aN |= bit;
+      if (w_ok) {
+        if (pair_hot(h, k, hw, kw, thr.ortho)) aW |= bit;
+        if (pair_hot(h, k, phw, pkw, thr.diag)) aNW |= bit;
+        if (pair_hot(ph, pk, hw, kw, thr.diag)) aAD |= bit;
+      }
+      ph = h; phw = hw; pk = k; pkw = kw;
+    }
+    // credit both ends. Bit i = row xs + i. My cell (x, z): W, N, NW at row i; AD marks (x-1, z): >> 1;
+    // N marks (x-1, z) too. The lane to my right credits me with its W and AD (my cell is its
+    // (x, z-1): row i) and with its NW (my cell is its (x-1, z-1): row i-1).
+    const unsigned eW = __shfl_down_sync(0xffffffffu, aW, 1), eNW = __shfl_down_sync(0xffffffffu, aNW, 1);
+    const unsigned eAD = __shfl_down_sync(0xffffffffu, aAD, 1);
+    unsigned mine = aW | aN | aNW | ((aN | aAD) >> 1);
+    if (lane < 31) mine |= eW | eAD | (eNW >> 1);
+    if (zin) mask_or(hot, z, xs, mine);
+  }
+}
+
+// positions first, first + 3, ..., first + 3 (count - 1) that fall into word j (bit b = position 32 j + b)
+__device__ __forceinline__ unsigned stride3_mask(int j, int first, int count) {
+  const int sel = (first % 3 + j) % 3;                            // 32 j + b == first (mod 3)  <=>  b == first + j (mod 3)
+  unsigned m = sel == 0 ? 0x49249249u : (sel == 1 ? 0x92492492u : 0x24924924u);
+  const int lo = first - 32 * j, hi = first + 3 * (count - 1) - 32 * j;
+  if (lo > 31 || hi < 0) return 0u;
+  if (lo > 0) m &= 0xffffffffu << lo;
+  if (hi < 31) m &= 0xffffffffu >> (31 - hi);
+  return m;
+}
+
+// rows of word j of column `col` that have a changed cell in rows x-1..x+1 of that column
+__device__ __forceinline__ unsigned changed_near(const unsigned* chg, int col, int j) {
+  const unsigned v = chg[col * MASK_WORDS + j];
+  const unsigned l = j > 0 ? chg[col * MASK_WORDS + j - 1] : 0u;
+  const unsigned r = j + 1 < MASK_WORDS ? chg[col * MASK_WORDS + j + 1] : 0u;
+  return v | (v << 1) | (v >> 1) | (l >> 31) | (r << 31);
+}
+
+// moved: bit (dx+1)*4 + (dz+1) per 3x3 cell around (lx, lz)
+__device__ __forceinline__ void mark_changed(unsigned* chg, int lx, int lz, unsigned moved) {
+#pragma unroll
+  for (int d = 0; d < 3; d++) {                                   // column lz + d - 1: rows lx-1, lx, lx+1
+    const unsigned b3 = ((moved >> d) & 1u) | (((moved >> (4 + d)) & 1u) << 1) | (((moved >> (8 + d)) & 1u) << 2);
+    mask_or(chg, lz + d - 1, lx - 1, b3);
+  }
 }
 
 // ---- output ---------------------------------------------------------------------------------
@@ -307,12 +441,19 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
   unsigned short* queue = reinterpret_cast<unsigned short*>(smem_raw + TILE_FLOAT_BYTES);
-  unsigned* qcount = reinterpret_cast<unsigned*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES);  // [2]
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES + 8);
+  unsigned short* queue2 = reinterpret_cast<unsigned short*>(smem_raw + TILE_FLOAT_BYTES + TILE_QUEUE_BYTES);
+  unsigned* hot = reinterpret_cast<unsigned*>(smem_raw + TILE_FLOAT_BYTES + 2 * TILE_QUEUE_BYTES);
+  unsigned* chg = hot + TILE_PITCH * MASK_WORDS;
+  // [0],[1] queue counters of the dense path, [2] hot-cell count, [3] relaxed centres (dense path)
+  unsigned* qcount = reinterpret_cast<unsigned*>(smem_raw + TILE_FLOAT_BYTES + 2 * TILE_QUEUE_BYTES + 2 * TILE_MASK_BYTES);
+  unsigned* ccount = qcount + 4;                   // pair-bitmap mode: [9] candidates + [9] survivors per colour
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(qcount + 24);
   const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
+  const int tile_id = (win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x;
   const int sx0 = m.x0, sx1 = m.x0 + m.rows;       // rows present in local storage (a stripe + ghosts)
   const int gx0 = ox0 - 2, gz0 = oz0 - 8;          // global coords of tile[0][0]
-  const int tid = threadIdx.y * TILE_BX + threadIdx.x;
+  const int tid = (int)threadIdx.x;
+  const int tx = tid % TILE_BX, ty = tid / TILE_BX;  // dense scan: centre slot (ty == TILE_BY: the 16th warp sits out)
   const int nx = m.nx, nz = m.nz;
   const float hs = fmul(settling, 0.5f);
   // negative or vanishing thresholds / sub-normal products: the lean paths' shortcuts do not hold
@@ -320,9 +461,14 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
                             !(fabsf(settling) <= 1e18f) || (thr.ortho != 0.0f && thr.ortho < 1e-18f);
   const bool vec_ok = (nz & 3) == 0;               // rows are 16-byte aligned, tiles 4-aligned in z
   const bool interior = gx0 >= 0 && gz0 >= 0 && gx0 + TILE_LX <= nx && gz0 + TILE_PITCH <= nz;
+  // pair-bitmap mode: interior tile, reference parameters (settling == 1: the transfer excess/2 is
+  // exact), and the tile was not mostly moving in the previous sweep (hint byte; heuristic only)
+  bool sparse = interior && !generic_only && !m.rock && settling == 1.0f && thr.diag < 1e30f &&
+                scratch.hint != nullptr && scratch.hint[tile_id] == 0;
 
   // ---- load R_0 ---------------------------------------------------------------------------
-  if (tid == 0) { qcount[0] = 0u; qcount[1] = 0u; }
+  if (tid < 22) qcount[tid] = 0u;                  // qcount[4] + ccount[18]
+  for (int i = tid; i < 2 * TILE_PITCH * MASK_WORDS; i += TILE_THREADS) hot[i] = 0u;   // hot and chg planes
   if (USE_TMA) {
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -342,7 +488,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       tile[i] = v;
     }
   }
-  __syncthreads();   // mbarrier init + queue counters visible; plain loads complete
+  __syncthreads();   // mbarrier init + counters + bit planes visible; plain loads complete
   if (USE_TMA) {
     unsigned done = 0;
     while (!done) {
@@ -355,12 +501,97 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   }
 
   bool any_change = false;
+  const unsigned lane = tid & 31;
+
+  // ---- pair-bitmap mode: phase A, then decide ------------------------------------------------
+  unsigned hot_cells = 0u;
+  if (sparse) {
+    tile_pair_scan(tile, hot, thr, tid >> 5, (int)lane, TILE_THREADS / 32);
+    __syncthreads();
+    unsigned n = 0;
+    for (int i = tid; i < TILE_PITCH * MASK_WORDS; i += TILE_THREADS) n += __popc(hot[i]);
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0 && n) atomicAdd(&qcount[2], n);
+    __syncthreads();
+    hot_cells = qcount[2];
+    sparse = hot_cells * 100u < 35u * (unsigned)(TILE_LX * TILE_PITCH);   // CTA-uniform
+  }
+  if (sparse) {
+    const Valid8 all = centre_valid<true>(1, 1, 3, 3);
+    // no hot pair anywhere in the tile: no centre can move and nothing can become hot
+#pragma unroll 1
+    for (int c = 0; c < 9 && hot_cells != 0u; c++) {
+      const int cxc = c / 3;
+      const int ncx = TILE_TX / 3 + 2 - cxc, ncz = TILE_TZ / 3 + 8 - c;
+      // candidates: own hot bit, or a changed cell in the 3x3 block
+      for (int it = tid; it < ncz * MASK_WORDS; it += TILE_THREADS) {
+        const int t = it / MASK_WORDS, j = it - t * MASK_WORDS;
+        const int lz = c + 1 + 3 * t;
+        unsigned wb = hot[lz * MASK_WORDS + j] | changed_near(chg, lz - 1, j) | changed_near(chg, lz, j) |
+                      changed_near(chg, lz + 1, j);
+        wb &= stride3_mask(j, cxc + 1, ncx);
+        if (wb) {
+          unsigned slot = atomicAdd(&ccount[c], (unsigned)__popc(wb));
+          while (wb) {
+            const int b = __ffs(wb) - 1;
+            wb &= wb - 1u;
+            queue[slot++] = (unsigned short)((32 * j + b) * TILE_PITCH + lz);
+          }
+        }
+      }
+      __syncthreads();
+      const unsigned nc = ccount[c];
+      if (nc == 0u) continue;                                      // CTA-uniform
+      if (nc <= (unsigned)TILE_THREADS) {
+        // few candidates: exact test and relaxation by the same thread, one barrier less
+        bool did = false;
+        if ((unsigned)tid < nc) {
+          const int off = queue[tid];
+          if (centre_needs<true, true>(tile + off, thr, hs, all)) {
+            unsigned moved = 0u;
+            centre_relax<true, false, true>(tile + off, thr, settling, hs, all, 1, 1, 3, 3, nullptr, &moved);
+            if (moved) { const int lx = off / TILE_PITCH; mark_changed(chg, lx, off - lx * TILE_PITCH, moved); }
+            did = true;
+          }
+        }
+        any_change |= did;
+        __syncthreads();
+        continue;
+      }
+      // exact early-out test, dense over the candidates
+      for (unsigned base_i = 0; base_i < nc; base_i += TILE_THREADS) {
+        const unsigned i = base_i + tid;
+        int off = 0;
+        bool need = false;
+        if (i < nc) { off = queue[i]; need = centre_needs<true, true>(tile + off, thr, hs, all); }
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+          unsigned b = 0;
+          if (lane == (unsigned)(__ffs(mask) - 1)) b = atomicAdd(&ccount[9 + c], (unsigned)__popc(mask));
+          b = __shfl_sync(0xffffffffu, b, __ffs(mask) - 1);
+          if (need) queue2[b + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)off;
+        }
+      }
+      __syncthreads();
+      // relax the survivors, remember what they changed
+      const unsigned nq = ccount[9 + c];
+      any_change |= nq != 0u;
+      for (unsigned i = tid; i < nq; i += TILE_THREADS) {
+        const int off = queue2[i];
+        unsigned moved = 0u;
+        centre_relax<true, false, true>(tile + off, thr, settling, hs, all, 1, 1, 3, 3, nullptr, &moved);
+        if (moved) { const int lx = off / TILE_PITCH; mark_changed(chg, lx, off - lx * TILE_PITCH, moved); }
+      }
+      __syncthreads();
+    }
+    any_change = __syncthreads_or(any_change ? 1 : 0) != 0;        // per-thread flags in the merged path
+  } else {
   // which early-out test the scan uses: the refined test costs ~64 more instructions per
   // scanned centre and saves ~250 per centre it keeps out of the queue, so it pays unless more
   // than ~3/4 of the centres pass it. Colour 0 always probes with it; a tile whose refined
   // queue fills beyond 3/4 falls back to the coarse test for its remaining colours.
   bool refined = true;
-  const unsigned lane = tid & 31;
+  unsigned relaxed = 0u, centres = 0u;
 #pragma unroll 1
   for (int c = 0; c < 9; c++) {
     const int cxc = c / 3;
@@ -368,11 +599,11 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     unsigned* qc = qcount + (c & 1);
     // ---- scan --------------------------------------------------------------------------------
     {
-      const int lz = c + 1 + 3 * (int)threadIdx.x, gz = gz0 + lz;
-      const bool z_ok = (int)threadIdx.x < ncz && (interior || (gz >= 0 && gz < nz));
+      const int lz = c + 1 + 3 * tx, gz = gz0 + lz;
+      const bool z_ok = ty < TILE_BY && tx < ncz && (interior || (gz >= 0 && gz < nz));
 #pragma unroll 1
       for (int cx_base = 0; cx_base < ncx; cx_base += TILE_BY) {      // same trip count for all threads
-        const int cxi = cx_base + (int)threadIdx.y;
+        const int cxi = cx_base + ty;
         const int lx = cxc + 1 + 3 * cxi, gx = gx0 + lx;
         bool need = z_ok && cxi < ncx && (interior || (gx >= 0 && gx < nx));
         const int off = lx * TILE_PITCH + lz;
@@ -399,6 +630,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     const unsigned nq = *qc;
     if (tid == 0) qcount[(c + 1) & 1] = 0u;          // the other counter is idle during this phase
     any_change |= nq != 0u;                          // a queued centre always moves sand
+    relaxed += nq; centres += (unsigned)(ncx * ncz);
     refined = refined && (nq * 4u < (unsigned)(ncx * ncz) * 3u);
     for (unsigned i = tid; i < nq; i += TILE_THREADS) {
       const int off = queue[i];
@@ -420,11 +652,14 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     }
     __syncthreads();
   }
+  // hint for the next sweep: skip the pair scan while most of this tile still moves
+  if (tid == 0 && scratch.hint != nullptr) scratch.hint[tile_id] = (relaxed * 100u > 45u * centres) ? 1 : 0;
+  }
 
   // ---- store O if anything in this tile moved -----------------------------------------------
   if (any_change) {                                  // CTA-uniform (derived from shared counters)
     tile_store<TILE_TX, TILE_THREADS>(tile, m, win, scratch.stage, ox0, oz0, tid, vec_ok);
-    if (tid == 0) scratch.flags[(win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x] = 1;
+    if (tid == 0) scratch.flags[tile_id] = 1;
   }
 }
 
@@ -803,7 +1038,7 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
     }
     cascade_commit_kernel<STAMPED_TX><<<grid, 256, 0, st>>>(m, win, scratch.stage, scratch.flags);
   } else {
-    const dim3 block(TILE_BX, TILE_BY);
+    const dim3 block(TILE_THREADS);
     if (tma) {
       allow_smem(reinterpret_cast<const void*>(&cascade_tile_kernel<true>), TILE_SMEM_PLAIN);
       cascade_tile_kernel<true><<<grid, block, TILE_SMEM_PLAIN, st>>>(tm, m, p.settling, thr, win, scratch);

@@ -80,6 +80,7 @@ struct RowWindow {
 struct TileScratch {
   float* stage;
   unsigned char* flags;
+  unsigned char* hint;   // whole-map tile sweeps: 1 = the tile was mostly moving last sweep (skip the pair scan)
 };
 size_t tile_flag_count(const MapView& m);
 

@@ -301,3 +301,45 @@ def test_device_expf_matches_host_libm():
         a, na, _ = w.trace(x, z, 600)
         b, nb = ora.trace(x, z, 600)
         assert na == nb and np.array_equal(bits(a), bits(b))
+
+
+# ---- whole-map sweeps near the repose angle: the tile kernel's pair-bitmap mode ----------------
+@pytest.mark.parametrize("nx,nz", [(300, 1000), (512, 768)])
+def test_cascade_long_relaxation_bitwise(nx, nz):
+    """200 sweeps from a random map: the first ones run the dense path, later ones (little moves,
+    interior tiles) the pair-bitmap path with its hint bytes; bitwise against the oracle at
+    checkpoints, then a local disturbance of the relaxed map and more sweeps."""
+    rs = np.random.RandomState(nx)
+    hm = rs.random_sample((nx, nz)).astype(np.float32)
+    ora = PortWorld(nx, nz)
+    ora.set_plane(0, hm)
+    w = swe.World(nx, nz)
+    w.upload(hm)
+    done = 0
+    for upto in (1, 2, 30, 80, 140, 200):
+        w.cascade_sweep(upto - done); ora.cascade_sweep(upto - done)
+        done = upto
+        got, want = w.download(), ora.plane(0)
+        assert np.array_equal(bits(got), bits(want)), (upto, np.argwhere(bits(got) != bits(want))[:5])
+    h = ora.plane(0).copy()
+    h[100:104, 300:310] += np.float32(0.2)              # spikes inside an interior tile
+    h[150, 500] = np.float32(0.0); h[151, 500] = np.float32(-0.0)
+    h[160:170, 600:640] = np.float32(0.25)              # exact plateau, power of two
+    ora.set_plane(0, h); w.upload(h)
+    for _ in range(6):
+        w.cascade_sweep(1); ora.cascade_sweep(1)
+        assert np.array_equal(bits(w.download()), bits(ora.plane(0)))
+
+
+def test_cascade_long_relaxation_variants_agree_2048():
+    """Larger map, GPU only: the fused tile kernel (pair-bitmap mode once relaxed) against the
+    one-launch-per-colour global-memory kernel, hash after every 40 sweeps."""
+    n = 2048
+    hm = np.random.RandomState(77).random_sample((n, n)).astype(np.float32)
+    a, b = swe.World(n), swe.World(n)
+    b.set_option(swe.OPT_CASCADE_VARIANT, 1)
+    a.upload(hm); b.upload(hm)
+    for _ in range(4):
+        a.cascade_sweep(40); b.cascade_sweep(40)
+        assert a.hash_height() == b.hash_height()
+    assert a.max_excess() == b.max_excess()

@@ -25,9 +25,10 @@ static float ulp_of(float a) {
   if (e <= 0) return 0.0f;
   u = (uint32_t)e << 23; memcpy(&a, &u, 4); return a;
 }
+static float MARGIN = 1.0f;
 static int pair_hot(float a, float b, float t) {
   float e = fabsf(a - b) - t;
-  float u = fminf(ulp_of(a), ulp_of(b));
+  float u = fminf(ulp_of(a), ulp_of(b)) * MARGIN;
   return e > 0.0f && e >= u;
 }
 
@@ -63,6 +64,7 @@ static int cascade(int x, int z) {
 int main(int argc, char** argv) {
   N = argc > 1 ? atoi(argv[1]) : 512;
   int sweeps = argc > 2 ? atoi(argv[2]) : 200;
+  if (argc > 3) MARGIN = (float)atof(argv[3]);
   H = malloc(sizeof(float) * N * N); hot = malloc(N * N); chg = malloc(N * N);
   uint64_t s = 42;
   for (int i = 0; i < N * N; i++) { s = s * 6364136223846793005ull + 1442695040888963407ull; H[i] = (float)((s >> 40) & 0xffffff) / 16777216.0f; }
