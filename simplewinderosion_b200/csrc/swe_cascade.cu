@@ -264,9 +264,9 @@ __device__ __forceinline__ int ulp_key(float v) {
   return ((max(b, 1) - 1) & 0x7f800000) - (23 << 23);   // bits of u(v); <= 0 for tiny |v| (always hot)
 }
 
-__device__ __forceinline__ bool pair_hot(float a, int ka, float b, int kb, float t) {
+__device__ __forceinline__ unsigned pair_bit(float a, int ka, float b, int kb, float t, unsigned bit) {
   const int eb = __float_as_int(fsub(fabsf(fsub(a, b)), t));
-  return (eb >= ka) | (eb >= kb);
+  return (eb >= min(ka, kb)) ? bit : 0u;
 }
 
 // bit i of `mask` = row row0 + i of column `col`
@@ -294,32 +294,32 @@ __device__ __forceinline__ void tile_pair_scan(const float* tile, unsigned* hot,
     const bool w_ok = zin && lane >= 1 && z >= 1;                 // partner column z-1 is in the strip and the tile
     const int xs = r0 > 0 ? r0 - 1 : 0;                           // one row of run-in above the chunk
     const float* col = tile + (zin ? z : 0);
-    float ph = 0.0f, phw = 0.0f;
-    int pk = 0, pkw = 0;
+    float ph, phw;
+    int pk, pkw;
     unsigned aW = 0u, aN = 0u, aNW = 0u, aAD = 0u;                // bit i: my pair of that kind at row xs + i is hot
     {                                                             // run-in row (or row 0): state only, W pairs if owned
-      const float h = zin ? col[xs * TILE_PITCH] : 0.0f;
-      const int k = ulp_key(h);
-      const float hw = __shfl_up_sync(0xffffffffu, h, 1);
-      const int kw = __shfl_up_sync(0xffffffffu, k, 1);
-      if (xs >= r0 && w_ok && pair_hot(h, k, hw, kw, thr.ortho)) aW |= 1u;
-      ph = h; phw = hw; pk = k; pkw = kw;
+      ph = col[xs * TILE_PITCH];
+      pk = ulp_key(ph);
+      phw = __shfl_up_sync(0xffffffffu, ph, 1);
+      pkw = __shfl_up_sync(0xffffffffu, pk, 1);
+      if (xs >= r0) aW = pair_bit(ph, pk, phw, pkw, thr.ortho, 1u);
     }
+    // branch-free row loop (halo lanes compute garbage that is masked out after the loop)
+    unsigned bit = 2u;
 #pragma unroll 4
-    for (int x = xs + 1; x < r1; x++) {
-      const float h = zin ? col[x * TILE_PITCH] : 0.0f;
+    for (int x = xs + 1; x < r1; x++, bit <<= 1) {
+      const float h = col[x * TILE_PITCH];
       const int k = ulp_key(h);
       const float hw = __shfl_up_sync(0xffffffffu, h, 1);
       const int kw = __shfl_up_sync(0xffffffffu, k, 1);
-      const unsigned bit = 1u << (x - xs);
-      if (zin && pair_hot(h, k, ph, pk, thr.ortho)) aN |= bit;
-      if (w_ok) {
-        if (pair_hot(h, k, hw, kw, thr.ortho)) aW |= bit;
-        if (pair_hot(h, k, phw, pkw, thr.diag)) aNW |= bit;
-        if (pair_hot(ph, pk, hw, kw, thr.diag)) aAD |= bit;
-      }
+      aN |= pair_bit(h, k, ph, pk, thr.ortho, bit);
+      aW |= pair_bit(h, k, hw, kw, thr.ortho, bit);
+      aNW |= pair_bit(h, k, phw, pkw, thr.diag, bit);
+      aAD |= pair_bit(ph, pk, hw, kw, thr.diag, bit);
       ph = h; phw = hw; pk = k; pkw = kw;
     }
+    if (!zin) aN = 0u;
+    if (!w_ok) aW = aNW = aAD = 0u;
     // credit both ends. Bit i = row xs + i. My cell (x, z): W, N, NW at row i; AD marks (x-1, z): >> 1;
     // N marks (x-1, z) too. The lane to my right credits me with its W and AD (my cell is its
     // (x, z-1): row i) and with its NW (my cell is its (x-1, z-1): row i-1).

@@ -7,7 +7,7 @@ from simplewinderosion_b200 import generate
 
 what = sys.argv[1] if len(sys.argv) > 1 else "fly4096"
 if what == "fly4096":
-    w = swe.World(4096); w.upload(generate.fbm(4096, seed=1)); w.srand(1)
+    w = swe.World(4096); w.generate_noise(1, 8); w.normalize(); w.srand(1)   # bench.py's dune field
     for _ in range(2): w.erode(1 << 22, swe.MODE_PARALLEL)
     w.sync(); print(w.stats().last_fly_ms)
 elif what == "fly1024flat":
