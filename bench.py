@@ -285,6 +285,10 @@ def cascade_roofline(swe, device: int, peak: float, peak_src: str, quick: bool) 
         if ex < 1e-4:
             break
     w.cascade_sweep(8); relaxed_ms = w.stats().last_sweep_ms / 8
+    # a map at rest (every slope below the repose angle): the pure cost of proving that nothing moves
+    w.upload(generate.flat_sand(n, seed=1))
+    w.cascade_sweep(2)
+    w.cascade_sweep(8); rest_ms = w.stats().last_sweep_ms / 8
     w.close()
     achieved = bytes_per_sweep * sweeps / (total_ms * 1e-3) / 1e9
     return {"bound": "hbm", "workload": f"cfg5: {n}x{n} U(0,1) random-slope map relaxed until max excess < 1e-4",
@@ -293,7 +297,9 @@ def cascade_roofline(swe, device: int, peak: float, peak_src: str, quick: bool) 
             "final_max_excess": ex,
             "ms_per_sweep_mean": total_ms / sweeps, "ms_first_sweep": first[0],
             "ms_per_sweep_relaxed": relaxed_ms,
-            "frac_relaxed": bytes_per_sweep / (relaxed_ms * 1e-3) / 1e9 / peak}
+            "frac_relaxed": bytes_per_sweep / (relaxed_ms * 1e-3) / 1e9 / peak,
+            "ms_per_sweep_at_rest": rest_ms,
+            "frac_at_rest": bytes_per_sweep / (rest_ms * 1e-3) / 1e9 / peak}
 
 
 def layered_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> dict:
