@@ -71,7 +71,7 @@ constexpr int TILE_QUEUE_BYTES = ((TILE_LX / 3) * (TILE_PITCH / 3) * 2 + 15) / 1
 // (bit planes are COLUMN-major: word [col][row >> 5], bit row & 31 -- a lane of the pair scan owns a column)
 constexpr int MASK_WORDS = (TILE_LX + 31) / 32;             // 3 words per tile column
 constexpr int TILE_MASK_BYTES = TILE_PITCH * MASK_WORDS * 4;   // 2,880 B per bit plane
-constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + 2 * TILE_QUEUE_BYTES + 2 * TILE_MASK_BYTES + 128;  // + counters, mbarrier
+constexpr int TILE_SMEM_PLAIN = TILE_FLOAT_BYTES + 2 * TILE_QUEUE_BYTES + 2 * TILE_MASK_BYTES + 256;  // + counters, mbarrier, chain table
 static_assert(TILE_PITCH == 8 * 30, "tile_pair_scan walks the tile in 8 groups of 30 columns");
 
 __device__ __forceinline__ void cswap_desc(unsigned& a, unsigned& b) {
@@ -169,26 +169,37 @@ __device__ __forceinline__ unsigned height_key(float h, bool valid, unsigned cod
   return valid ? ((k & ~15u) | (15u - code)) : 0u;
 }
 
+// Neighbour table of the transfer chain, in shared memory: entry j = key & 15 = 15 - code gives the
+// neighbour's byte offset from the centre in the tile and its repose gap (ortho or diag). Entry 0 is
+// the empty slot of a centre at the map edge: it points at the centre itself with an infinite gap, so
+// it never moves anything and never reads a cell another thread may be writing.
+__device__ __forceinline__ void chain_table_init(float2* lut, int j, const CascadeThr thr) {
+  const int code = 15 - j, dxm = (code >> 2) - 1, dzm = (code & 3) - 1;
+  const bool real = j != 0 && dxm <= 1 && dzm <= 1 && !(dxm == 0 && dzm == 0);
+  lut[j] = real ? make_float2(__int_as_float((dxm * TILE_PITCH + dzm) * 4), (dxm != 0 && dzm != 0) ? thr.diag : thr.ortho)
+                : make_float2(__int_as_float(0), INFINITY);
+}
+
 // one element of the transfer chain (world.hpp:122-151), branch-free; thresholds >= 0 so that
 // diff == 0 implies excess <= 0 and the reference's explicit diff == 0 test is subsumed.
 // LAYERED (extension): the transfer is capped by the giving cell's sand, height - rock.
 // TRACK: `moved` collects bit `code` of every neighbour whose transfer ran (pair-bitmap mode).
 template <bool LAYERED, bool TRACK = false>
-__device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, const CascadeThr thr,
+__device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, const float2* lut,
                                            float settling, const float* rock_c_ptr, int nz, float rock_c,
                                            unsigned* moved = nullptr) {
-  const unsigned code = 15u - (k & 15u);
-  const int dxm = (int)(code >> 2) - 1, dzm = (int)(code & 3u) - 1;
-  float* hp = tc + dxm * TILE_PITCH + dzm;
+  const float2 e = lut[k & 15u];
+  float* hp = reinterpret_cast<float*>(reinterpret_cast<char*>(tc) + __float_as_int(e.x));
   const float hv = *hp;
-  const float t = (code & 5u) ? thr.ortho : thr.diag;
   const float diff = fsub(cc, hv);
-  const float excess = fsub(fabsf(diff), t);
-  bool go = (k != 0u) && !(excess <= 0.0f);
+  const float excess = fsub(fabsf(diff), e.y);
+  bool go = !(excess <= 0.0f);
   // (settling*excess)/2.0f == excess*(settling/2): halving is exact and commutes with the
   // rounding of the product (sub-normal products excluded: tiny thresholds use the generic core)
   float transfer = fmul(excess, settling);                       // settling: already halved
   if (LAYERED) {
+    const unsigned code = 15u - (k & 15u);
+    const int dxm = (int)(code >> 2) - 1, dzm = (int)(code & 3u) - 1;
     const float rk = (k != 0u) ? __ldg(rock_c_ptr + dxm * nz + dzm) : 0.0f;
     const float sand = (diff > 0.0f) ? fsub(cc, rock_c) : fsub(hv, rk);
     transfer = fminf(transfer, fmaxf(sand, 0.0f));
@@ -196,13 +207,13 @@ __device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, con
   }
   const float sgn = (diff > 0.0f) ? transfer : -transfer;        // diff > 0: centre gives, else takes
   if (go) { cc = fsub(cc, sgn); *hp = fadd(hv, sgn); }
-  if (TRACK && go) *moved |= 1u << code;
+  if (TRACK && go) *moved |= 0x8000u >> (k & 15u);               // 1 << code
 }
 
 // World::cascade at one centre of the tile whose early-out test failed.
 // TRACK: *moved gets one bit per 3x3 cell whose value may have changed, bit (dx+1)*4 + (dz+1).
 template <bool INTERIOR, bool LAYERED = false, bool TRACK = false>
-__device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, float settling, float hs,
+__device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, const float2* lut, float settling, float hs,
                                              const Valid8 v, int gx, int gz, int nx, int nz,
                                              const float* rock_c_ptr = nullptr, unsigned* moved = nullptr) {
   unsigned k0 = height_key(tc[-TILE_PITCH - 1], v.v0, 0), k1 = height_key(tc[-TILE_PITCH], v.v1, 1),
@@ -229,10 +240,10 @@ __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, fl
   const float rock_c = LAYERED ? __ldg(rock_c_ptr) : 0.0f;
   const int rnz = nz;
   unsigned mv = 0u;
-  chain_step<LAYERED, TRACK>(tc, k0, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k1, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv);
-  chain_step<LAYERED, TRACK>(tc, k2, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k3, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv);
-  chain_step<LAYERED, TRACK>(tc, k4, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k5, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv);
-  chain_step<LAYERED, TRACK>(tc, k6, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k7, cc, thr, hs, rock_c_ptr, rnz, rock_c, &mv);
+  chain_step<LAYERED, TRACK>(tc, k0, cc, lut, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k1, cc, lut, hs, rock_c_ptr, rnz, rock_c, &mv);
+  chain_step<LAYERED, TRACK>(tc, k2, cc, lut, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k3, cc, lut, hs, rock_c_ptr, rnz, rock_c, &mv);
+  chain_step<LAYERED, TRACK>(tc, k4, cc, lut, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k5, cc, lut, hs, rock_c_ptr, rnz, rock_c, &mv);
+  chain_step<LAYERED, TRACK>(tc, k6, cc, lut, hs, rock_c_ptr, rnz, rock_c, &mv); chain_step<LAYERED, TRACK>(tc, k7, cc, lut, hs, rock_c_ptr, rnz, rock_c, &mv);
   tc[0] = cc;
   if (TRACK) *moved = mv ? (mv | (1u << 5)) : 0u;      // the centre (code 5) moved iff any transfer ran
 }
@@ -448,6 +459,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   unsigned* qcount = reinterpret_cast<unsigned*>(smem_raw + TILE_FLOAT_BYTES + 2 * TILE_QUEUE_BYTES + 2 * TILE_MASK_BYTES);
   unsigned* ccount = qcount + 4;                   // pair-bitmap mode: [9] candidates + [9] survivors per colour
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(qcount + 24);
+  float2* lut = reinterpret_cast<float2*>(qcount + 32);   // chain table, 16 entries
   const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
   const int tile_id = (win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x;
   const int sx0 = m.x0, sx1 = m.x0 + m.rows;       // rows present in local storage (a stripe + ghosts)
@@ -468,6 +480,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
 
   // ---- load R_0 ---------------------------------------------------------------------------
   if (tid < 22) qcount[tid] = 0u;                  // qcount[4] + ccount[18]
+  if (tid >= 32 && tid < 48) chain_table_init(lut, tid - 32, thr);
   for (int i = tid; i < 2 * TILE_PITCH * MASK_WORDS; i += TILE_THREADS) hot[i] = 0u;   // hot and chg planes
   if (USE_TMA) {
     if (tid == 0) {
@@ -549,7 +562,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
           const int off = queue[tid];
           if (centre_needs<true, true>(tile + off, thr, hs, all)) {
             unsigned moved = 0u;
-            centre_relax<true, false, true>(tile + off, thr, settling, hs, all, 1, 1, 3, 3, nullptr, &moved);
+            centre_relax<true, false, true>(tile + off, thr, lut, settling, hs, all, 1, 1, 3, 3, nullptr, &moved);
             if (moved) { const int lx = off / TILE_PITCH; mark_changed(chg, lx, off - lx * TILE_PITCH, moved); }
             did = true;
           }
@@ -579,7 +592,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       for (unsigned i = tid; i < nq; i += TILE_THREADS) {
         const int off = queue2[i];
         unsigned moved = 0u;
-        centre_relax<true, false, true>(tile + off, thr, settling, hs, all, 1, 1, 3, 3, nullptr, &moved);
+        centre_relax<true, false, true>(tile + off, thr, lut, settling, hs, all, 1, 1, 3, 3, nullptr, &moved);
         if (moved) { const int lx = off / TILE_PITCH; mark_changed(chg, lx, off - lx * TILE_PITCH, moved); }
       }
       __syncthreads();
@@ -637,17 +650,17 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
       float* tc = tile + off;
       if (interior && !generic_only && !m.rock) {
         // interior: every neighbour exists; (1,1) in a 3x3 map tells the generic fallback so
-        centre_relax<true>(tc, thr, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
+        centre_relax<true>(tc, thr, lut, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
       } else {
         const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
         const int gx = gx0 + lx, gz = gz0 + lz;
         if (m.rock) {   // layered extension (single-GPU engines): sand-limited transfers
           const float* rp = m.rock + m.idx(gx, gz);
           if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, rp);
-          else centre_relax<false, true>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz, rp);
+          else centre_relax<false, true>(tc, thr, lut, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz, rp);
         }
         else if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
-        else centre_relax<false>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
+        else centre_relax<false>(tc, thr, lut, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
       }
     }
     __syncthreads();
@@ -683,7 +696,7 @@ template <int TX> struct StampedGeo {
   static constexpr int THREADS = (TX <= 30) ? 256 : 480;               // queue-driven: a flat block, whole warps
   static constexpr int FLOAT_BYTES = LX * TILE_PITCH * 4;
   static constexpr int QCAP = ((LX + 2) / 3) * (TILE_PITCH / 3);          // centres of one colour in the tile
-  static constexpr int SMEM = FLOAT_BYTES + 10 * QCAP * 2 + 96;
+  static constexpr int SMEM = FLOAT_BYTES + 10 * QCAP * 2 + 96 + 128;   // + chain table
 };
 
 template <int TX, bool USE_TMA>
@@ -701,6 +714,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
   unsigned short* rq = cq + 9 * STAMPED_QCAP;                                              // relax queue
   unsigned* cnt = reinterpret_cast<unsigned*>(rq + STAMPED_QCAP);                          // [9] touched + [9] relax
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(cnt + 18);
+  float2* lut = reinterpret_cast<float2*>(cnt + 24);      // chain table, 16 entries
   const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TILE_TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
   const int gx0 = ox0 - 2, gz0 = oz0 - 8;
   const int sx0 = m.x0, sx1 = m.x0 + m.rows;
@@ -713,6 +727,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
   const bool interior = gx0 >= 0 && gz0 >= 0 && gx0 + TILE_LX <= nx && gz0 + TILE_PITCH <= nz;
 
   if (tid < 18) cnt[tid] = 0u;
+  if (tid >= 32 && tid < 48) chain_table_init(lut, tid - 32, thr);
   if (USE_TMA && tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -839,7 +854,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
           if (m.rock && !generic_only) {
             const Valid8 v = centre_valid<false>(gx, gz, nx, nz);
             if (centre_needs<false, false>(tc, thr, hs, v)) {
-              centre_relax<false, true>(tc, thr, settling, hs, v, gx, gz, nx, nz, m.rock + m.idx(gx, gz));
+              centre_relax<false, true>(tc, thr, lut, settling, hs, v, gx, gz, nx, nz, m.rock + m.idx(gx, gz));
               any_change = true;
             }
           } else if (m.rock) {
@@ -848,13 +863,13 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
             any_change |= tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
           } else if (interior) {
             if (centre_needs<true, false>(tc, thr, hs, centre_valid<true>(1, 1, 3, 3))) {
-              centre_relax<true>(tc, thr, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
+              centre_relax<true>(tc, thr, lut, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
               any_change = true;
             }
           } else {
             const Valid8 v = centre_valid<false>(gx, gz, nx, nz);
             if (centre_needs<false, false>(tc, thr, hs, v)) {
-              centre_relax<false>(tc, thr, settling, hs, v, gx, gz, nx, nz);
+              centre_relax<false>(tc, thr, lut, settling, hs, v, gx, gz, nx, nz);
               any_change = true;
             }
           }
@@ -903,17 +918,17 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
       const int off = rq[i];
       float* tc = tile + off;
       if (interior && !generic_only && !m.rock) {
-        centre_relax<true>(tc, thr, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
+        centre_relax<true>(tc, thr, lut, settling, hs, centre_valid<true>(1, 1, 3, 3), 1, 1, 3, 3);
       } else {
         const int lx = off / TILE_PITCH, lz = off - lx * TILE_PITCH;
         const int gx = gx0 + lx, gz = gz0 + lz;
         if (m.rock) {   // layered extension (single-GPU engines): sand-limited transfers
           const float* rp = m.rock + m.idx(gx, gz);
           if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, rp);
-          else centre_relax<false, true>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz, rp);
+          else centre_relax<false, true>(tc, thr, lut, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz, rp);
         }
         else if (generic_only) tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling);
-        else centre_relax<false>(tc, thr, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
+        else centre_relax<false>(tc, thr, lut, settling, hs, centre_valid<false>(gx, gz, nx, nz), gx, gz, nx, nz);
       }
     }
     __syncthreads();
