@@ -210,6 +210,17 @@ __device__ __forceinline__ void chain_step(float* tc, unsigned k, float& cc, con
   if (TRACK && go) *moved |= 0x8000u >> (k & 15u);               // 1 << code
 }
 
+// the same chain element on register values: returns whether the transfer ran
+__device__ __forceinline__ bool chain_reg(float& cc, float& hv, float t, float half_settling) {
+  const float diff = fsub(cc, hv);
+  const float excess = fsub(fabsf(diff), t);
+  const bool go = !(excess <= 0.0f);
+  const float transfer = fmul(excess, half_settling);
+  const float sgn = (diff > 0.0f) ? transfer : -transfer;        // diff > 0: centre gives, else takes
+  if (go) { cc = fsub(cc, sgn); hv = fadd(hv, sgn); }
+  return go;
+}
+
 // World::cascade at one centre of the tile whose early-out test failed.
 // TRACK: *moved gets one bit per 3x3 cell whose value may have changed, bit (dx+1)*4 + (dz+1).
 template <bool INTERIOR, bool LAYERED = false, bool TRACK = false>
@@ -234,6 +245,34 @@ __device__ __forceinline__ void centre_relax(float* tc, const CascadeThr thr, co
   if ((INTERIOR || k1) && close < 16u) {
     const bool ch = tile_cascade_generic(tc, gx, gz, nx, nz, thr, settling, LAYERED ? rock_c_ptr : nullptr);
     if (TRACK) *moved = ch ? 0x777u : 0u;
+    return;
+  }
+  if (!LAYERED) {
+    // all eight neighbours are fetched up front (sorted order), the chain runs in registers and the
+    // changed cells are stored afterwards: no store -> load round trip through shared memory between
+    // the dependent steps (the eight cells are distinct, which the compiler cannot know)
+    const float2 e0 = lut[k0 & 15u], e1 = lut[k1 & 15u], e2 = lut[k2 & 15u], e3 = lut[k3 & 15u],
+                 e4 = lut[k4 & 15u], e5 = lut[k5 & 15u], e6 = lut[k6 & 15u], e7 = lut[k7 & 15u];
+    char* base = reinterpret_cast<char*>(tc);
+    float* p0 = reinterpret_cast<float*>(base + __float_as_int(e0.x)); float* p1 = reinterpret_cast<float*>(base + __float_as_int(e1.x));
+    float* p2 = reinterpret_cast<float*>(base + __float_as_int(e2.x)); float* p3 = reinterpret_cast<float*>(base + __float_as_int(e3.x));
+    float* p4 = reinterpret_cast<float*>(base + __float_as_int(e4.x)); float* p5 = reinterpret_cast<float*>(base + __float_as_int(e5.x));
+    float* p6 = reinterpret_cast<float*>(base + __float_as_int(e6.x)); float* p7 = reinterpret_cast<float*>(base + __float_as_int(e7.x));
+    float v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3, v4 = *p4, v5 = *p5, v6 = *p6, v7 = *p7;
+    float cc = tc[0];
+    const bool g0 = chain_reg(cc, v0, e0.y, hs), g1 = chain_reg(cc, v1, e1.y, hs), g2 = chain_reg(cc, v2, e2.y, hs),
+               g3 = chain_reg(cc, v3, e3.y, hs), g4 = chain_reg(cc, v4, e4.y, hs), g5 = chain_reg(cc, v5, e5.y, hs),
+               g6 = chain_reg(cc, v6, e6.y, hs), g7 = chain_reg(cc, v7, e7.y, hs);
+    if (g0) *p0 = v0; if (g1) *p1 = v1; if (g2) *p2 = v2; if (g3) *p3 = v3;
+    if (g4) *p4 = v4; if (g5) *p5 = v5; if (g6) *p6 = v6; if (g7) *p7 = v7;
+    tc[0] = cc;                                        // after the neighbour stores: an empty slot aliases the centre
+    if (TRACK) {
+      unsigned mv = 0u;
+      if (g0) mv |= 0x8000u >> (k0 & 15u); if (g1) mv |= 0x8000u >> (k1 & 15u); if (g2) mv |= 0x8000u >> (k2 & 15u);
+      if (g3) mv |= 0x8000u >> (k3 & 15u); if (g4) mv |= 0x8000u >> (k4 & 15u); if (g5) mv |= 0x8000u >> (k5 & 15u);
+      if (g6) mv |= 0x8000u >> (k6 & 15u); if (g7) mv |= 0x8000u >> (k7 & 15u);
+      *moved = mv ? (mv | (1u << 5)) : 0u;             // the centre (code 5) moved iff any transfer ran
+    }
     return;
   }
   float cc = tc[0];
