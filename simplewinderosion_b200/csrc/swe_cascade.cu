@@ -575,15 +575,31 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     for (int c = 0; c < 9 && hot_cells != 0u; c++) {
       const int cxc = c / 3;
       const int ncx = TILE_TX / 3 + 2 - cxc, ncz = TILE_TZ / 3 + 8 - c;
-      // candidates: own hot bit, or a changed cell in the 3x3 block
-      for (int it = tid; it < ncz * MASK_WORDS; it += TILE_THREADS) {
-        const int t = it / MASK_WORDS, j = it - t * MASK_WORDS;
-        const int lz = c + 1 + 3 * t;
-        unsigned wb = hot[lz * MASK_WORDS + j] | changed_near(chg, lz - 1, j) | changed_near(chg, lz, j) |
-                      changed_near(chg, lz + 1, j);
-        wb &= stride3_mask(j, cxc + 1, ncx);
-        if (wb) {
-          unsigned slot = atomicAdd(&ccount[c], (unsigned)__popc(wb));
+      // candidates: own hot bit, or a changed cell in the 3x3 block (one queue reservation per warp)
+      for (int it0 = 0; it0 < ncz * MASK_WORDS; it0 += TILE_THREADS) {      // one trip: ncz * 3 <= 240
+        const int it = it0 + tid;
+        unsigned wb = 0u;
+        int lz = 0, j = 0;
+        if (it < ncz * MASK_WORDS) {
+          const int t = it / MASK_WORDS;
+          j = it - t * MASK_WORDS;
+          lz = c + 1 + 3 * t;
+          wb = hot[lz * MASK_WORDS + j] | changed_near(chg, lz - 1, j) | changed_near(chg, lz, j) |
+               changed_near(chg, lz + 1, j);
+          wb &= stride3_mask(j, cxc + 1, ncx);
+        }
+        if (__any_sync(0xffffffffu, wb != 0u)) {
+          const unsigned n = (unsigned)__popc(wb);
+          unsigned incl = n;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += up;
+          }
+          unsigned base = 0u;
+          if (lane == 31u) base = atomicAdd(&ccount[c], incl);
+          base = __shfl_sync(0xffffffffu, base, 31);
+          unsigned slot = base + incl - n;
           while (wb) {
             const int b = __ffs(wb) - 1;
             wb &= wb - 1u;
