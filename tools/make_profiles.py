@@ -30,7 +30,10 @@ if os.path.exists(os.path.join(G, f"launches_{tag}.csv")):
 traffic = {}
 for name, title in (("par_round", "par_round_kernel, 4096^2 FBm map, 4,194,304 particles, one round (step ~150 of a call)"),
                     ("cascade_stamped", "cascade_tile_kernel<stamped,TMA>, same run: World::cascade at the cells touched in the round"),
-                    ("cascade_sweep8192", "cascade_tile_kernel<plain,TMA>, 8192^2 U(0,1) map, one whole-map sweep")):
+                    ("cascade_sweep8192", "cascade_tile_kernel<plain,TMA>, 8192^2 U(0,1) map, one whole-map sweep (sweep 3: dense path, everything moves)"),
+                    ("noise_stack", "noise_stack_kernel, 4096^2, eight layers of FastNoiseLite OpenSimplex2 FBm (map::init generate on the device)"),
+                    ("cascade_sweep_at_rest", "cascade_tile_kernel<plain,TMA>, 8192^2 map at rest (all slopes below the repose angle): pair scan only"),
+                    ("cascade_sweep_converged", "cascade_tile_kernel<plain,TMA>, 4096^2 U(0,1) map, sweep 161 of the relaxation (pair-bitmap mode, ~10 % of the cells still move)")):
     rep = os.path.join(G, f"{name}_{tag}.ncu-rep")
     if os.path.exists(rep):
         txt = ncu_summary(rep, os.path.join(P, f"{tag}_{name}_ncu.txt"), title)
