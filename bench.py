@@ -302,6 +302,39 @@ def cascade_roofline(swe, device: int, peak: float, peak_src: str, quick: bool) 
             "frac_at_rest": bytes_per_sweep / (rest_ms * 1e-3) / 1e9 / peak}
 
 
+def dune_formation_extra(swe, device: int, steps: int) -> dict:
+    """BASELINE.json configs[1]: 1024x1024 flat-sand dune formation, 1,048,576 particles per
+    World::erode (SURVEY 8(d) cfg2: height = 0.25 + 1e-3 U(-1,1)). Reported beside the headline."""
+    import torch
+    from simplewinderosion_b200 import analysis, generate
+    n, particles = 1024, 1 << 20
+    w = swe.World(n, device=device)
+    w.upload(generate.flat_sand(n, seed=42))
+    w.srand(1)
+    stream = torch.cuda.Stream()
+    w.set_stream(stream.cuda_stream)
+    for _ in range(3):
+        w.erode(particles, swe.MODE_PARALLEL)
+    w.sync()
+    s0 = w.stats().steps
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            w.erode(particles, swe.MODE_PARALLEL)
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    done = w.stats().steps - s0
+    h = w.download()
+    w.close()
+    return {"workload": f"cfg2: {n}x{n} flat sand (0.25 + 1e-3 U(-1,1)), {particles} particles per World::erode, "
+                        f"{3 + steps} calls from the flat bed",
+            "value": done / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "dominant_wavelength_cells": analysis.dominant_wavelength(h),
+            "height_std": float(h.std())}
+
+
 def layered_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> dict:
     """BASELINE.json configs[2] as named: dune field with a rock pyramid obstacle and abrasion on.
     Rock/abrasion do not exist in the reference snapshot, so this runs the engine's layered-terrain
@@ -524,6 +557,7 @@ def run_ours(args) -> None:
     }
     if world == 1 and not args.skip_layered:
         line["layered_extension"] = layered_extra(swe, local, n, particles, hm, args.steps)
+        line["dune_formation_cfg2"] = dune_formation_extra(swe, local, args.steps)
     if not args.skip_cascade and world == 1:
         line["cascade_roofline"] = cascade_roofline(swe, local, peak, peak_src, args.quick)
     if world == 1 and not args.skip_cpu:

@@ -21,7 +21,7 @@ import pytest
 
 import simplewinderosion_b200 as swe
 from simplewinderosion_b200 import analysis, generate
-from tests.oracle_lib import PortWorld
+from tests.oracle_lib import PortWorld, noise_map
 
 pytestmark = pytest.mark.gpu
 
@@ -42,10 +42,12 @@ def run_pair(n, frames, cycles, hm, seed=1, **opts):
 
 
 @pytest.mark.parametrize("name,n,frames,cycles", [("gauss", 256, 30, 2048), ("flat", 256, 120, 2048),
-                                                  ("fbm", 512, 10, 4096)])
+                                                  ("fbm", 512, 10, 4096), ("noise", 512, 10, 4096)])
 def test_statistics_match_sequential_reference(name, n, frames, cycles):
+    # "noise": map::init's FastNoiseLite layers (seed 1) -- bench.py's dune-field input at test size
     hm = {"gauss": generate.gaussian_hill, "flat": generate.flat_sand,
-          "fbm": lambda k: generate.fbm(k, seed=3)}[name](n)
+          "fbm": lambda k: generate.fbm(k, seed=3),
+          "noise": lambda k: noise_map(k, seed=1, layers=8, workers=4)}[name](n)
     ora, so, w = run_pair(n, frames, cycles, hm)
     st = w.stats()
     ho, hg = np.array(ora.plane(0)), w.download()
