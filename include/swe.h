@@ -79,7 +79,13 @@ typedef enum swe_option {
   SWE_OPT_KERNEL_TIMING = 3,
   /* 1 (default) = a parallel swe_erode on a single-GPU engine is captured once per (cycles, params,
    * options) as a CUDA graph of ~1550 nodes and replayed; 0 = launch kernel by kernel. */
-  SWE_OPT_CUDA_GRAPH = 4
+  SWE_OPT_CUDA_GRAPH = 4,
+  /* 1 (default) = the kernels of a parallel swe_erode round (particle step, stamped cascade, commit)
+   * are chained with programmatic dependent launches: each may be set up while its predecessor
+   * drains and waits on-device (griddepcontrol.wait) before touching its results. Hides part of the
+   * launch latency when a call has few particles (the reference's own 8*tilesize frame: 2-5 %);
+   * 0 = plain stream order. Results are identical either way. */
+  SWE_OPT_PDL = 5
 } swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:

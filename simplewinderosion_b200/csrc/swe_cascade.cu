@@ -451,6 +451,7 @@ __device__ __forceinline__ void tile_store(const float* tile, const MapView& m, 
 template <int TX>
 __global__ void __launch_bounds__(256)
 cascade_commit_kernel(MapView m, RowWindow win, const float* __restrict__ stage, unsigned char* __restrict__ flags) {
+  pdl_sync();
   const int tile_id = (win.tile_y0 + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x;
   if (!flags[tile_id]) return;
   const int ox0 = TILE_OX + (win.tile_y0 + (int)blockIdx.y) * TX, oz0 = TILE_OZ + (int)blockIdx.x * TILE_TZ;
@@ -760,6 +761,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
                             const unsigned char* __restrict__ stamp, unsigned char stamp_now,
                             const unsigned* __restrict__ gate, RowWindow win, TileScratch scratch) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  pdl_sync();
   if (gate && *gate == 0u) return;
   constexpr int TILE_LX = StampedGeo<TX>::LX, TILE_THREADS = StampedGeo<TX>::THREADS;     // shadow the 60-row geometry
   constexpr int TILE_FLOAT_BYTES = StampedGeo<TX>::FLOAT_BYTES, STAMPED_QCAP = StampedGeo<TX>::QCAP;
@@ -1080,7 +1082,7 @@ static void allow_smem(const void* kernel, int bytes) {
 // from a halo of 5 rows below / 7 above (the <= 4/6-row dependency cone of the nine colours).
 static void launch_tile_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                               const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                              int row_lo, int row_hi, TileScratch scratch, cudaStream_t st) {
+                              int row_lo, int row_hi, TileScratch scratch, cudaStream_t st, bool pdl = false) {
   CascadeThr thr;
   thr.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;      // host IEEE fp32: same values as the device helper
   thr.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
@@ -1101,12 +1103,14 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
     const dim3 block(G::THREADS, 1);
     if (tma) {
       allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<STAMPED_TX, true>), G::SMEM);
-      cascade_tile_stamped_kernel<STAMPED_TX, true><<<grid, block, G::SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
+      launch_chain(cascade_tile_stamped_kernel<STAMPED_TX, true>, grid, block, G::SMEM, st, pdl, tm, m, p.settling, thr, stamp,
+                   stamp_now, gate, win, scratch);
     } else {
       allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<STAMPED_TX, false>), G::SMEM);
-      cascade_tile_stamped_kernel<STAMPED_TX, false><<<grid, block, G::SMEM, st>>>(tm, m, p.settling, thr, stamp, stamp_now, gate, win, scratch);
+      launch_chain(cascade_tile_stamped_kernel<STAMPED_TX, false>, grid, block, G::SMEM, st, pdl, tm, m, p.settling, thr, stamp,
+                   stamp_now, gate, win, scratch);
     }
-    cascade_commit_kernel<STAMPED_TX><<<grid, 256, 0, st>>>(m, win, scratch.stage, scratch.flags);
+    launch_chain(cascade_commit_kernel<STAMPED_TX>, grid, dim3(256), 0, st, pdl, m, win, (const float*)scratch.stage, scratch.flags);
   } else {
     const dim3 block(TILE_THREADS);
     if (tma) {
@@ -1122,8 +1126,8 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
 
 void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                             const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                            int row_lo, int row_hi, TileScratch scratch, cudaStream_t st) {
-  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, row_lo, row_hi, scratch, st);
+                            int row_lo, int row_hi, TileScratch scratch, cudaStream_t st, bool pdl) {
+  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, row_lo, row_hi, scratch, st, pdl);
 }
 
 size_t tile_flag_count(const MapView& m) {

@@ -259,6 +259,7 @@ par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restr
                  int steps_per_round, uint2 key, uint32_t call, unsigned char* stamp,
                  unsigned char stamp_now, const unsigned* live_in, unsigned* live_out,
                  DevStats* stats, StripeRound sr, const CallCtl* __restrict__ ctl) {
+  pdl_sync();
   if (live_in && *live_in == 0u) return;
   if (ctl) { key = make_uint2(ctl->key_x, ctl->key_y); call = ctl->call; }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,12 +366,13 @@ void launch_par_begin(const ParticleBuf& buf, const MapView& m, int n, uint64_t 
 
 void launch_par_round(const ParticleBuf& buf, const MapView& m, const swe_params& p, int n, int round,
                       int steps_per_round, uint64_t seed, uint32_t call, const CallCtl* ctl,
-                      unsigned char* stamp, unsigned char stamp_now, DevStats* stats, cudaStream_t st) {
+                      unsigned char* stamp, unsigned char stamp_now, DevStats* stats, cudaStream_t st,
+                      bool pdl) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   StripeRound none{};
-  par_round_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(m, make_const(p), buf.a, buf.b, n, steps_per_round,
-                                                           key, call, stamp, stamp_now, buf.live + round,
-                                                           buf.live + round + 1, stats, none, ctl);
+  launch_chain(par_round_kernel<false>, dim3((n + 255) / 256), dim3(256), 0, st, pdl, m, make_const(p), buf.a, buf.b, n,
+               steps_per_round, key, call, stamp, stamp_now, (const unsigned*)(buf.live + round), buf.live + round + 1,
+               stats, none, ctl);
 }
 
 // ---- stripe (multi-GPU) launchers ---------------------------------------------------------------

@@ -5,8 +5,11 @@ import sys
 sys.path.insert(0, ".")
 import simplewinderosion_b200 as swe  # noqa: E402
 
+pdl = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+print("PDL", pdl)
 for n in (512, 1024, 4096, 16384):
     w = swe.World(n)
+    w.set_option(swe.OPT_PDL, pdl)
     w.generate_noise(1, 8); w.normalize(); w.srand(1)
     cycles = 8 * n
     for _ in range(3):
