@@ -85,14 +85,7 @@ typedef enum swe_option {
    * drains and waits on-device (griddepcontrol.wait) before touching its results. Hides part of the
    * launch latency when a call has few particles (the reference's own 8*tilesize frame: 2-5 %);
    * 0 = plain stream order. Results are identical either way. */
-  SWE_OPT_PDL = 5,
-  /* How the per-round cascade of a parallel swe_erode finds the touched cells of a tile: 0 (default) =
-   * nine per-colour queues filled while the stamp bytes are read, so that the early-out tests run on
-   * densely packed warps; 1 = stamp bytes kept in shared memory and every colour phase walks its
-   * centres in the regular order. Same centres in the same colour order: identical results
-   * (tests/test_gpu_parallel.py). Measured on B200 at 0.25 particles per cell the walk is 5 % slower
-   * per call (its tests run on quarter-full warps); kept as a cross-check. */
-  SWE_OPT_STAMPED_DENSE = 6
+  SWE_OPT_PDL = 5
 } swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:

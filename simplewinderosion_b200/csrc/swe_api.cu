@@ -79,7 +79,6 @@ struct swe_engine {
   int opt_kernel_timing = 0;          // record an event pair around every round / cascade launch
   int opt_cuda_graph = 1;             // replay the parallel erode of a single-GPU engine as one CUDA graph
   int opt_pdl = 1;                    // programmatic dependent launches between the round kernels
-  int opt_stamped_dense = 0;          // stamped cascade: 0 queue-driven (default), 1 dense walk over the stamp bytes
   CallCtl* d_ctl = nullptr;           // seed / call index of the current call (read by graph-replayed kernels)
   struct CachedGraph { uint64_t key; cudaGraphExec_t exec; };
   std::vector<CachedGraph> graphs;
@@ -327,7 +326,6 @@ int parallel_rounds(swe_engine* e, int cycles, const CallCtl* ctl) {
   if (int rc = check_launch(e, "par_begin", 2)) return rc;
   const bool kt = e->opt_kernel_timing != 0 && ctl == nullptr;
   const bool pdl = e->opt_pdl != 0 && !kt;             // chain the round kernels with programmatic dependent launches
-  const bool dense = e->opt_stamped_dense != 0;         // alternative cell discovery of the stamped cascade (see swe.h)
   for (int r = 0; r < rounds; r++) {
     if (r % 255 == 0) SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
     const unsigned char now = (unsigned char)(1 + r % 255);
@@ -341,7 +339,7 @@ int parallel_rounds(swe_engine* e, int cycles, const CallCtl* ctl) {
                      e->d_stats, e->stream, pdl);
     if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
     // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
-    launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->tsc, e->stream, pdl, dense);
+    launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->tsc, e->stream, pdl);
     if (kt) { SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 2], e->stream)); e->kt_rounds = r + 1; }
     if (int rc = check_launch(e, "par_round", 3)) return rc;
   }
@@ -361,7 +359,6 @@ uint64_t graph_key(const swe_engine* e, int cycles) {
   mix(&e->p, sizeof e->p);
   mix(&e->opt_cascade_interval, sizeof(int));
   mix(&e->opt_pdl, sizeof(int));
-  mix(&e->opt_stamped_dense, sizeof(int));
   mix(&e->stream, sizeof e->stream);
   mix(&e->m.rock, sizeof e->m.rock);
   mix(&e->pbuf.a, sizeof e->pbuf.a);
@@ -1263,8 +1260,6 @@ int swe_set_option(swe_engine* e, int option, int value) {
       e->opt_cuda_graph = value ? 1 : 0; return SWE_OK;
     case SWE_OPT_PDL:
       e->opt_pdl = value ? 1 : 0; return SWE_OK;
-    case SWE_OPT_STAMPED_DENSE:
-      e->opt_stamped_dense = value ? 1 : 0; return SWE_OK;
     default:
       return fail(SWE_ERR_INVALID, "unknown option %d", option);
   }

@@ -759,7 +759,7 @@ template <int TX, bool USE_TMA>
 __global__ void __launch_bounds__(StampedGeo<TX>::THREADS, (TX <= 30) ? 4 : 2)
 cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
                             const unsigned char* __restrict__ stamp, unsigned char stamp_now,
-                            const unsigned* __restrict__ gate, RowWindow win, TileScratch scratch, int dense_hint) {
+                            const unsigned* __restrict__ gate, RowWindow win, TileScratch scratch) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   pdl_sync();
   if (gate && *gate == 0u) return;
@@ -783,15 +783,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
   const bool vec_ok = (nz & 3) == 0;
   const bool interior = gx0 >= 0 && gz0 >= 0 && gx0 + TILE_LX <= nx && gz0 + TILE_PITCH <= nz;
 
-  // Alternative cell discovery (SWE_OPT_STAMPED_DENSE, off by default): the tile's stamp bytes are kept
-  // in shared memory (in the space of the per-colour queues, which this path does not use) and every
-  // colour phase walks its centres in the regular order, like the whole-map kernel, testing "touched
-  // && some pair exceeds its gap". It avoids one shared-memory atomic per touched cell (the queue
-  // build is a third of the kernel's instructions at 0.25 particles per cell) but its early-out tests
-  // run on quarter-full warps: measured 5 % slower per call than the packed queues. Cross-check only.
-  const bool dense = dense_hint != 0 && interior && !generic_only && !m.rock && (nz & 7) == 0;
-  unsigned char* stamp_s = reinterpret_cast<unsigned char*>(cq);
-  if (tid < 18 || tid == 20) cnt[tid] = 0u;          // [18], [19] hold the mbarrier
+  if (tid < 18) cnt[tid] = 0u;
   if (tid >= 32 && tid < 48) chain_table_init(lut, tid - 32, thr);
   if (USE_TMA && tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -807,29 +799,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
     const unsigned slot = atomicAdd(&cnt[c], 1u);
     cq[c * STAMPED_QCAP + slot] = (unsigned short)(lx * TILE_PITCH + lz);
   };
-  if (dense) {
-    const unsigned pat = 0x01010101u * stamp_now;
-    constexpr int QPR = TILE_PITCH / 8;                       // 30 uint2 per tile row
-    constexpr int NV = TILE_LX * QPR;
-    constexpr int PER = (NV + TILE_THREADS - 1) / TILE_THREADS;
-    uint2 v[PER];
-#pragma unroll
-    for (int k = 0; k < PER; k++) {                           // interior tile: every stamp exists
-      const int i = tid + k * TILE_THREADS;
-      const int lx = i / QPR, q = i - lx * QPR;
-      v[k] = make_uint2(~pat, ~pat);
-      if (i < NV) v[k] = __ldcg(reinterpret_cast<const uint2*>(stamp + m.idx(gx0 + lx, gz0 + 8 * q)));
-    }
-    unsigned nm = 0u;
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-      const int i = tid + k * TILE_THREADS;
-      if (i < NV) reinterpret_cast<uint2*>(stamp_s)[i] = v[k];
-      nm += __popc(__vcmpeq4(v[k].x, pat) & 0x01010101u) + __popc(__vcmpeq4(v[k].y, pat) & 0x01010101u);
-    }
-    for (int o = 16; o > 0; o >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, o);
-    if ((tid & 31) == 0 && nm) atomicAdd(&cnt[20], nm);
-  } else if ((nz & 7) == 0) {
+  if ((nz & 7) == 0) {
     // 8 stamps per 64-bit load (rows are 8-byte aligned and every tile's z origin, -16 + 216 j, is
     // == 0 mod 8); all loads of a thread are issued before any is inspected, and a word is only
     // taken apart if the "has a zero byte" test says one of its stamps matches
@@ -885,7 +855,7 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
   }
   __syncthreads();
   {
-    unsigned total = cnt[20];
+    unsigned total = 0;
 #pragma unroll
     for (int c = 0; c < 9; c++) total += cnt[c];
     if (total == 0u) return;                       // nothing touched here: no height traffic at all
@@ -921,39 +891,6 @@ cascade_tile_stamped_kernel(const __grid_constant__ CUtensorMap tmap, MapView m,
 
   bool any_change = false;
   const unsigned lane = tid & 31;
-  if (dense) {
-    constexpr int ROWS = TILE_THREADS / TILE_BX;   // centre rows per pass (3 for 256 threads)
-    const int tx = tid % TILE_BX, ty = tid / TILE_BX;
-    const Valid8 all = centre_valid<true>(1, 1, 3, 3);
-#pragma unroll 1
-    for (int c = 0; c < 9; c++) {
-      const int cxc = c / 3;
-      const int ncx = TILE_TX / 3 + 2 - cxc, ncz = TILE_TZ / 3 + 8 - c;
-      unsigned* qc = cnt + 9 + c;
-      const int lz = c + 1 + 3 * tx;
-      const bool z_ok = ty < ROWS && tx < ncz;
-#pragma unroll 1
-      for (int cx_base = 0; cx_base < ncx; cx_base += ROWS) {       // same trip count for all threads
-        const int cxi = cx_base + ty;
-        const int off = (cxc + 1 + 3 * cxi) * TILE_PITCH + lz;
-        bool need = z_ok && cxi < ncx;
-        if (need) need = stamp_s[off] == stamp_now && centre_needs<true, false>(tile + off, thr, hs, all);
-        const unsigned mask = __ballot_sync(0xffffffffu, need);
-        if (mask) {
-          unsigned b = 0;
-          if (lane == (unsigned)(__ffs(mask) - 1)) b = atomicAdd(qc, (unsigned)__popc(mask));
-          b = __shfl_sync(0xffffffffu, b, __ffs(mask) - 1);
-          if (need) rq[b + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)off;
-        }
-      }
-      __syncthreads();
-      const unsigned nq = *qc;
-      any_change |= nq != 0u;
-      for (unsigned i = tid; i < nq; i += TILE_THREADS)
-        centre_relax<true>(tile + rq[i], thr, lut, settling, hs, all, 1, 1, 3, 3);
-      __syncthreads();
-    }
-  } else
 #pragma unroll 1
   for (int c = 0; c < 9; c++) {
     const unsigned nc = cnt[c];
@@ -1145,8 +1082,7 @@ static void allow_smem(const void* kernel, int bytes) {
 // from a halo of 5 rows below / 7 above (the <= 4/6-row dependency cone of the nine colours).
 static void launch_tile_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                               const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                              int row_lo, int row_hi, TileScratch scratch, cudaStream_t st, bool pdl = false,
-                              bool dense_hint = false) {
+                              int row_lo, int row_hi, TileScratch scratch, cudaStream_t st, bool pdl = false) {
   CascadeThr thr;
   thr.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;      // host IEEE fp32: same values as the device helper
   thr.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
@@ -1168,11 +1104,11 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
     if (tma) {
       allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<STAMPED_TX, true>), G::SMEM);
       launch_chain(cascade_tile_stamped_kernel<STAMPED_TX, true>, grid, block, G::SMEM, st, pdl, tm, m, p.settling, thr, stamp,
-                   stamp_now, gate, win, scratch, dense_hint ? 1 : 0);
+                   stamp_now, gate, win, scratch);
     } else {
       allow_smem(reinterpret_cast<const void*>(&cascade_tile_stamped_kernel<STAMPED_TX, false>), G::SMEM);
       launch_chain(cascade_tile_stamped_kernel<STAMPED_TX, false>, grid, block, G::SMEM, st, pdl, tm, m, p.settling, thr, stamp,
-                   stamp_now, gate, win, scratch, dense_hint ? 1 : 0);
+                   stamp_now, gate, win, scratch);
     }
     launch_chain(cascade_commit_kernel<STAMPED_TX>, grid, dim3(256), 0, st, pdl, m, win, (const float*)scratch.stage, scratch.flags);
   } else {
@@ -1190,8 +1126,8 @@ static void launch_tile_sweep(const MapView& m, const swe_params& p, const Heigh
 
 void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                             const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                            int row_lo, int row_hi, TileScratch scratch, cudaStream_t st, bool pdl, bool dense_hint) {
-  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, row_lo, row_hi, scratch, st, pdl, dense_hint);
+                            int row_lo, int row_hi, TileScratch scratch, cudaStream_t st, bool pdl) {
+  launch_tile_sweep(m, p, tmap, stamp, stamp_now, gate, row_lo, row_hi, scratch, st, pdl);
 }
 
 size_t tile_flag_count(const MapView& m) {

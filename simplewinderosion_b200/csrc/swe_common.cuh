@@ -122,8 +122,7 @@ int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTens
 // (gate: device counter; the sweep is skipped when *gate == 0, i.e. no particle flew)
 void launch_cascade_stamped(const MapView& m, const swe_params& p, const HeightTensorMap* tmap,
                             const unsigned char* stamp, unsigned char stamp_now, const unsigned* gate,
-                            int row_lo, int row_hi, TileScratch scratch, cudaStream_t st, bool pdl = false,
-                            bool dense_hint = false);   // dense_hint: many particles per tile this round
+                            int row_lo, int row_hi, TileScratch scratch, cudaStream_t st, bool pdl = false);
 void launch_max_excess(const MapView& m, const swe_params& p, float* d_out, cudaStream_t st);
 
 // Per-call values the particle kernels read from device memory instead of their parameter list, so

@@ -203,34 +203,3 @@ def test_programmatic_dependent_launch_is_transparent():
     st = w.stats()
     assert st.particles == 150000 == st.exits_oob + st.exits_age
     assert abs(w.sum_plane() + st.sediment_lost - s0) < 2e-5 * s0
-
-
-def test_stamped_cascade_dense_walk_equals_queue_driven():
-    """SWE_OPT_STAMPED_DENSE: the two ways the per-round cascade finds a tile's touched cells process
-    the same centres in the same colour order. One particle per call is deterministic (no concurrent
-    float atomics), so both must agree BITWISE, on maps with interior tiles (the dense walk is used
-    there) and with several cells touched per call (a long flight)."""
-    nx, nz = 200, 700
-    hm = (generate.gaussian_hill(nz)[:nx] + np.float32(0.02) * generate.random_slopes(nx, nz, seed=3)).astype(np.float32)
-    outs = []
-    for dense in (0, 1):
-        w = swe.World(nx, nz)
-        w.set_option(swe.OPT_STAMPED_DENSE, dense)
-        w.upload(hm)
-        w.srand(11)
-        for _ in range(12):
-            w.erode(1, swe.MODE_PARALLEL)
-        outs.append((w.download().view(np.uint32), w.stats().steps))
-    assert outs[0][1] == outs[1][1] and outs[0][1] > 100
-    assert np.array_equal(outs[0][0], outs[1][0])
-    # and at real densities: accounting and mass balance with the walk forced on and off
-    for dense in (0, 1):
-        w = swe.World(512)
-        w.set_option(swe.OPT_STAMPED_DENSE, dense)
-        w.upload(generate.gaussian_hill(512))
-        w.srand(2)
-        s0 = w.sum_plane()
-        w.erode(100000, swe.MODE_PARALLEL)
-        st = w.stats()
-        assert st.particles == 100000 == st.exits_oob + st.exits_age
-        assert abs(w.sum_plane() + st.sediment_lost - s0) < 2e-5 * s0
