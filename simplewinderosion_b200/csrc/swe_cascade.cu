@@ -567,7 +567,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     if (lane == 0 && n) atomicAdd(&qcount[2], n);
     __syncthreads();
     hot_cells = qcount[2];
-    sparse = hot_cells * 100u < 35u * (unsigned)(TILE_LX * TILE_PITCH);   // CTA-uniform
+    sparse = hot_cells * 100u < 27u * (unsigned)(TILE_LX * TILE_PITCH);   // CTA-uniform
   }
   if (sparse) {
     const Valid8 all = centre_valid<true>(1, 1, 3, 3);
@@ -722,7 +722,7 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     __syncthreads();
   }
   // hint for the next sweep: skip the pair scan while most of this tile still moves
-  if (tid == 0 && scratch.hint != nullptr) scratch.hint[tile_id] = (relaxed * 100u > 45u * centres) ? 1 : 0;
+  if (tid == 0 && scratch.hint != nullptr) scratch.hint[tile_id] = (relaxed * 100u > 26u * centres) ? 1 : 0;
   }
 
   // ---- store O if anything in this tile moved -----------------------------------------------
