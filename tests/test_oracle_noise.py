@@ -72,3 +72,16 @@ def test_port_equals_unmodified_fastnoiselite():
         assert np.array_equal(bits(r.plane(0)), bits(w.plane(0)))
         r.normalize(); w.normalize()
         assert np.array_equal(bits(r.plane(0)), bits(w.plane(0)))
+
+
+def test_banded_multithreaded_map_equals_whole_map():
+    """tests.oracle_lib.noise_map (what bench.py --impl reference feeds the CPU arm): row bands on
+    several threads, then the normalisation -- the same bits as the one-piece stack."""
+    from tests.oracle_lib import noise_map
+    got = noise_map(64, seed=1, layers=8, workers=3)
+    assert np.array_equal(bits(got), bits(G["stack_norm_seed1"]))
+    rag = noise_map(37, 50, seed=4711, layers=5, workers=2)
+    w = PortWorld(37, 50)
+    w.noise_stack(4711, 5)
+    w.normalize()
+    assert np.array_equal(bits(rag), bits(w.plane(0)))
