@@ -112,3 +112,26 @@ def test_stripes_generate_their_rows_and_ghosts(nx, nz, world):
     g.cascade_sweep(1)
     single.cascade_sweep(1)
     assert np.array_equal(bits(g.gather()), bits(single.download()))
+
+
+def test_cfg1_variant_noise_map_then_deterministic_erode():
+    """BASELINE configs[0] in SURVEY 8(d)'s 256^2 noise-map variant: heightmap = the eight noise layers
+    (SEED 1) normalised, generated on the device, then World::erode(8*256) frames in deterministic
+    mode -- every plane bitwise equal to the oracle fed with ITS OWN restatement of the generator."""
+    n, frames = 256, 2
+    ora = PortWorld(n)
+    ora.noise_stack(1, 8)
+    ora.normalize()
+    ora.srand(1)
+    w = swe.World(n)
+    w.generate_noise(1, 8)
+    w.normalize()
+    w.srand(1)
+    assert np.array_equal(bits(w.download()), bits(ora.plane(0)))
+    steps = 0
+    for _ in range(frames):
+        w.erode(8 * n, swe.MODE_DETERMINISTIC)
+        steps += ora.erode(8 * n).steps
+    assert w.stats().steps == steps
+    for k in range(9):
+        assert np.array_equal(bits(w.download(k)), bits(ora.plane(k))), k
