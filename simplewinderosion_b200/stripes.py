@@ -61,6 +61,18 @@ def allgather_bytes(blob: bytes, world_size: int, group=None, device=None) -> li
     return [bytes(g.cpu().tolist()) for g in gathered]
 
 
+def reduce_range(lo: float, hi: float, group=None, device=None) -> tuple[float, float]:
+    """Global (min, max) of per-rank height ranges (torch.distributed plumbing; gloo or nccl): what the
+    normalisation of map::init (cellpool.h:416-428) needs when the map is cut into stripes."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", device or 0) if backend == "nccl" else torch.device("cpu")
+    t = torch.tensor([-lo, hi], dtype=torch.float32, device=dev)     # one MAX reduction for both ends
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return -float(t[0].item()), float(t[1].item())
+
+
 class StripeGroup:
     """Several stripes of one map driven from THIS host thread (logical stripes on one GPU, or a
     process owning several GPUs). The C library interleaves the launches exchange by exchange."""
@@ -150,6 +162,14 @@ class StripedWorld(_world.World):
 
     def max_excess_local(self) -> float:
         return super().max_excess()
+
+    def normalize_collective(self, group=None) -> tuple[float, float]:
+        """map::init's normalisation (cellpool.h:416-428) on a striped map: every rank folds its owned
+        rows, the ranges are reduced over the ranks, every rank rescales its rows and ghost rows with
+        the global range (collective: every rank must call it). Returns the global (min, max)."""
+        lo, hi = reduce_range(*self.height_range(), group=group, device=self.device)
+        self.normalize(lo, hi)
+        return lo, hi
 
 
 def gather_global(worlds: list[StripedWorld], plane: int = _world.HEIGHT) -> np.ndarray:

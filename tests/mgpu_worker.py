@@ -34,6 +34,21 @@ def main():
     got = w.download()
     assert np.array_equal(got.view(np.uint32), np.array(ora.plane(0))[lo:hi].view(np.uint32)), "striped sweep != oracle"
 
+    # generate on the stripes: noise layers in global coordinates, collective normalisation; bitwise
+    # equal to the oracle's whole-map generator, ghost rows included (a sweep follows without a sync)
+    w.upload_global(np.zeros((n, n), np.float32))
+    w.sync_halos()
+    w.generate_noise(9, 8)
+    rng = w.normalize_collective()
+    og = PortWorld(n)
+    og.noise_stack(9, 8)
+    raw = np.array(og.plane(0))
+    assert rng == (min(0.0, float(raw.min())), max(0.0, float(raw.max()))), rng
+    og.normalize()
+    assert np.array_equal(w.download().view(np.uint32), np.array(og.plane(0))[lo:hi].view(np.uint32)), "striped generate != oracle"
+    w.cascade_sweep(1); og.cascade_sweep(1)
+    assert np.array_equal(w.download().view(np.uint32), np.array(og.plane(0))[lo:hi].view(np.uint32)), "sweep after generate != oracle"
+
     hm2 = generate.gaussian_hill(n)
     w.upload_global(hm2)
     w.sync_halos()

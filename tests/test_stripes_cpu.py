@@ -45,6 +45,10 @@ def _worker(rank, world, port, q):
         ok = all(g == bytes([r + 1]) * stripes.STRIPE_IPC_BYTES for r, g in enumerate(got))
         # every rank derives the same partition and knows its neighbours
         nbrs = [r for r in (rank - 1, rank + 1) if 0 <= r < world]
+        # normalisation of a striped map: per-rank (min, max) -> the global range, exactly (fp32 values)
+        mine = [(-0.5191119, 0.25), (-0.125, 0.3582528)][rank]
+        rng = stripes.reduce_range(*mine)
+        ok = ok and rng == (float(__import__("numpy").float32(-0.5191119)), float(__import__("numpy").float32(0.3582528)))
         q.put((rank, ok, b, nbrs))
     finally:
         dist.destroy_process_group()
