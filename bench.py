@@ -535,6 +535,10 @@ def run_ours(args) -> None:
             f"~{particles_call // world} particles per GPU), "
             f"P2P halo push + particle hand-off kernels over NVLink",
             "stripe_overflow": int(overflow_total),
+            **({} if world == 1 else {"exchange": {
+                "per_round_per_interior_rank_bytes": int((7 + 5) * n * 5),
+                "what": "7 boundary rows pushed down + 5 up, height (4 B) + stamp (1 B) per cell, by P2P store kernels; "
+                        "plus 36 B per particle handed to a neighbour's inbox", "rounds_per_step": 514}}),
             "l2": "working set 720 MiB (height 64 + track 256 + field 256 + particles 128 + stamps 16) > 126 MB L2; no flush needed",
             "steps_per_particle": total_steps / max(1.0, total_particles),
         },
