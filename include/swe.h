@@ -85,7 +85,14 @@ typedef enum swe_option {
    * drains and waits on-device (griddepcontrol.wait) before touching its results. Hides part of the
    * launch latency when a call has few particles (the reference's own 8*tilesize frame: 2-5 %);
    * 0 = plain stream order. Results are identical either way. */
-  SWE_OPT_PDL = 5
+  SWE_OPT_PDL = 5,
+  /* Parallel mode, single-GPU engines: the particles of one swe_erode call fly as B successive batches
+   * (default 1 = all at once), each spread over the whole map and seeing the terrain the previous
+   * batches left. The reference flies its particles strictly one after another; with many particles
+   * per cell in flight at once the parallel mode exports more sand than the reference (measured:
+   * +24 % at 0.25 particles per cell, within 1.3 % at 0.03), and batches trade throughput for that
+   * fidelity. Track reset and EMA stay once per call. */
+  SWE_OPT_CALL_BATCHES = 6
 } swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:

@@ -79,6 +79,7 @@ struct swe_engine {
   int opt_kernel_timing = 0;          // record an event pair around every round / cascade launch
   int opt_cuda_graph = 1;             // replay the parallel erode of a single-GPU engine as one CUDA graph
   int opt_pdl = 1;                    // programmatic dependent launches between the round kernels
+  int opt_call_batches = 1;           // a parallel call's particles fly as this many successive batches
   CallCtl* d_ctl = nullptr;           // seed / call index of the current call (read by graph-replayed kernels)
   struct CachedGraph { uint64_t key; cudaGraphExec_t exec; };
   std::vector<CachedGraph> graphs;
@@ -322,26 +323,35 @@ int stripe_erode_round(swe_engine* e) {
 int parallel_rounds(swe_engine* e, int cycles, const CallCtl* ctl) {
   const int k = e->opt_cascade_interval;
   const int rounds = (e->p.max_age + 2 + k - 1) / k;   // every particle is dead after maxAge+2 calls
-  launch_par_begin(e->pbuf, e->m, cycles, e->seed, e->call_index, ctl, e->d_stats, e->stream);
-  if (int rc = check_launch(e, "par_begin", 2)) return rc;
   const bool kt = e->opt_kernel_timing != 0 && ctl == nullptr;
   const bool pdl = e->opt_pdl != 0 && !kt;             // chain the round kernels with programmatic dependent launches
-  for (int r = 0; r < rounds; r++) {
-    if (r % 255 == 0) SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
-    const unsigned char now = (unsigned char)(1 + r % 255);
-    if (kt) {
-      while ((int)e->kt_events.size() < 3 * (r + 1)) {
-        cudaEvent_t ev; SWE_CUDA(cudaEventCreate(&ev)); e->kt_events.push_back(ev);
+  // SWE_OPT_CALL_BATCHES: the call's particles fly as B successive batches, each spread over the whole
+  // map and seeing the terrain the previous batches left (closer to the reference's one-after-another
+  // order when a call has many particles per cell). Batch b draws from the RNG stream call + b * 2^24.
+  const int batches = e->opt_call_batches < cycles ? e->opt_call_batches : (cycles > 0 ? cycles : 1);
+  int g = 0;                                            // rounds launched so far in this call (stamp values)
+  for (int b = 0; b < batches; b++) {
+    const int n_b = cycles / batches + (b < cycles % batches ? 1 : 0);
+    const uint32_t call_arg = (ctl ? 0u : e->call_index) + (uint32_t)b * 0x01000000u;
+    launch_par_begin(e->pbuf, e->m, n_b, e->seed, call_arg, ctl, e->d_stats, e->stream);
+    if (int rc = check_launch(e, "par_begin", 2)) return rc;
+    for (int r = 0; r < rounds; r++, g++) {
+      if (g % 255 == 0) SWE_CUDA(cudaMemsetAsync(e->d_stamp, 0, e->cells(), e->stream));
+      const unsigned char now = (unsigned char)(1 + g % 255);
+      if (kt) {
+        while ((int)e->kt_events.size() < 3 * (g + 1)) {
+          cudaEvent_t ev; SWE_CUDA(cudaEventCreate(&ev)); e->kt_events.push_back(ev);
+        }
+        SWE_CUDA(cudaEventRecord(e->kt_events[3 * g], e->stream));
       }
-      SWE_CUDA(cudaEventRecord(e->kt_events[3 * r], e->stream));
+      launch_par_round(e->pbuf, e->m, e->p, n_b, r, k, e->seed, call_arg, ctl, e->d_stamp, now,
+                       e->d_stats, e->stream, pdl);
+      if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * g + 1], e->stream));
+      // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
+      launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->tsc, e->stream, pdl);
+      if (kt) { SWE_CUDA(cudaEventRecord(e->kt_events[3 * g + 2], e->stream)); e->kt_rounds = g + 1; }
+      if (int rc = check_launch(e, "par_round", 3)) return rc;
     }
-    launch_par_round(e->pbuf, e->m, e->p, cycles, r, k, e->seed, e->call_index, ctl, e->d_stamp, now,
-                     e->d_stats, e->stream, pdl);
-    if (kt) SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 1], e->stream));
-    // wind.hpp:114, deferred: World::cascade once at every cell touched in this round
-    launch_cascade_stamped(e->m, e->p, &e->tmap, e->d_stamp, now, e->pbuf.live + r, 0, e->m.nx, e->tsc, e->stream, pdl);
-    if (kt) { SWE_CUDA(cudaEventRecord(e->kt_events[3 * r + 2], e->stream)); e->kt_rounds = r + 1; }
-    if (int rc = check_launch(e, "par_round", 3)) return rc;
   }
   return SWE_OK;
 }
@@ -359,6 +369,7 @@ uint64_t graph_key(const swe_engine* e, int cycles) {
   mix(&e->p, sizeof e->p);
   mix(&e->opt_cascade_interval, sizeof(int));
   mix(&e->opt_pdl, sizeof(int));
+  mix(&e->opt_call_batches, sizeof(int));
   mix(&e->stream, sizeof e->stream);
   mix(&e->m.rock, sizeof e->m.rock);
   mix(&e->pbuf.a, sizeof e->pbuf.a);
@@ -392,10 +403,11 @@ int erode_parallel_graph(swe_engine* e, int cycles) {
     if (inst != cudaSuccess) return fail(SWE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(inst));
     if (e->graphs.size() >= 4) { cudaGraphExecDestroy(e->graphs.front().exec); e->graphs.erase(e->graphs.begin()); }
     e->graphs.push_back({key, exec});
-    e->launches -= (uint64_t)0;   // the capture pass already counted one call's worth of launches
+    // (the capture pass already counted one call's worth of launches)
   } else {
     const int k = e->opt_cascade_interval;
-    e->launches += 3ull + 3ull * (uint64_t)((e->p.max_age + 2 + k - 1) / k);   // kernels inside the replayed graph
+    const uint64_t b = (uint64_t)(e->opt_call_batches < cycles ? e->opt_call_batches : cycles);
+    e->launches += 1ull + b * (2ull + 3ull * (uint64_t)((e->p.max_age + 2 + k - 1) / k));   // kernels inside the replayed graph
   }
   SWE_CUDA(cudaEventRecord(e->ev_a, e->stream));
   SWE_CUDA(cudaEventRecord(e->ev_f0, e->stream));
@@ -1260,6 +1272,9 @@ int swe_set_option(swe_engine* e, int option, int value) {
       e->opt_cuda_graph = value ? 1 : 0; return SWE_OK;
     case SWE_OPT_PDL:
       e->opt_pdl = value ? 1 : 0; return SWE_OK;
+    case SWE_OPT_CALL_BATCHES:
+      if (value < 1 || value > 64) return fail(SWE_ERR_INVALID, "call batches must be in [1, 64]");
+      e->opt_call_batches = value; return SWE_OK;
     default:
       return fail(SWE_ERR_INVALID, "unknown option %d", option);
   }

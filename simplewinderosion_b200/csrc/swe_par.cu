@@ -205,7 +205,7 @@ __global__ void par_spawn_kernel(float4* __restrict__ pa, float4* __restrict__ p
                                  int nz, uint2 key, uint32_t call, const CallCtl* __restrict__ ctl) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (ctl) { key = make_uint2(ctl->key_x, ctl->key_y); call = ctl->call; }
+  if (ctl) { key = make_uint2(ctl->key_x, ctl->key_y); call += ctl->call; }   // graph replay: the argument is the batch salt
   float px, pz;
   spawn_position(i, n, nx, nz, key, call, px, pz);
   pa[i] = make_float4(px, 0.0f, pz, 0.0f);
@@ -261,7 +261,7 @@ par_round_kernel(MapView m, ParConst C, float4* __restrict__ pa, float4* __restr
                  DevStats* stats, StripeRound sr, const CallCtl* __restrict__ ctl) {
   pdl_sync();
   if (live_in && *live_in == 0u) return;
-  if (ctl) { key = make_uint2(ctl->key_x, ctl->key_y); call = ctl->call; }
+  if (ctl) { key = make_uint2(ctl->key_x, ctl->key_y); call += ctl->call; }   // graph replay: the argument is the batch salt
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned steps = 0, n_oob = 0, n_age = 0, alive = 0;
   float lost = 0.0f;
