@@ -10,7 +10,11 @@
  *   source/world.hpp:79-153     World::cascade     -> swo_cascade
  *   source/cellpool.h:200-223   quad::_normal      -> swo_normal
  *   source/cellpool.h:432-476   map::oob/get/height-> inlined bounds tests, index x*nz+z
- *   source/cellpool.h:339-428   map::init (Gaussian hill + normalise) -> swo_init_gaussian
+ *   source/cellpool.h:339-428   map::init (Gaussian hill + normalise) -> swo_init_gaussian, swo_hill_raw, swo_normalize
+ *   source/cellpool.h:366-368,388-411 + source/include/FastNoiseLite.h:322-340,500-553,687-721,866-887,1054-1147
+ *                               map::init's noise layers (a comment in the snapshot) over FastNoiseLite's
+ *                               OpenSimplex2 FBm -> swo_fnl_single3, swo_fnl_getnoise, swo_noise_stack, swo_noise_rows
+ *   source/cellpool.h:302-321   quad::updatenode (Vertex records)     -> swo_vertices
  *   glibc 2.39 rand()/srand() (TYPE_3 additive feedback) -> swo_srand / swo_rand
  *   glibc 2.39 expf (sysdeps/ieee754/flt-32/e_expf.c)    -> swo_expf
  *   glm 0.9.9 scalar vec ops (dot/cross/normalize/mix/length/round) -> inlined
@@ -19,7 +23,9 @@
  * restatement is pinned against the reference itself compiled headless here
  * (oracle/_ref, built by oracle/Makefile from the unmodified headers) -- bit-exact on
  * heights, trajectories, step counts -- and against fixtures generated from it and
- * committed under tests/golden/ (tests/golden/make_golden.py). The glm semantics are an
+ * committed under tests/golden/ (tests/golden/make_golden.py, make_noise_golden.py,
+ * make_vertices_golden.py: the noise against the unmodified FastNoiseLite class, the vertex
+ * records against the reference's own updatenode). The glm semantics are an
  * assumption (glm is absent from the container); they are cross-checked by the survey's
  * independent probe fingerprints (tests/test_oracle_ref.py).
  */
