@@ -458,9 +458,13 @@ cascade_commit_kernel(MapView m, RowWindow win, const float* __restrict__ stage,
   const int nz = m.nz;
   const bool vec_ok = (nz & 3) == 0;
   if (vec_ok) {
-    for (int i = threadIdx.x; i < TX * (TILE_TZ / 4); i += 256) {
-      const int ox = i / (TILE_TZ / 4), q = i - ox * (TILE_TZ / 4);
-      if (!tile_border<TX>(ox, 4 * q)) continue;
+    // only the border slots are enumerated: 6 full rows (first 4, last 2) of TZ/4 float4, then the first
+    // 4 and last 2 float4 of every row in between
+    constexpr int QR = TILE_TZ / 4, N_FULL = 6 * QR, N_ALL = N_FULL + 6 * (TX - 6);
+    for (int i = threadIdx.x; i < N_ALL; i += 256) {
+      int ox, q;
+      if (i < N_FULL) { const int r = i / QR; q = i - r * QR; ox = r < 4 ? r : TX - 6 + r; }
+      else { const int j = i - N_FULL, r = j / 6, s_ = j - r * 6; ox = 4 + r; q = s_ < 4 ? s_ : QR - 6 + s_; }
       const int gx = ox0 + ox, gz = oz0 + 4 * q;
       if (gx >= win.store_lo && gx < win.store_hi && gz >= 0 && gz < nz)
         *reinterpret_cast<float4*>(m.height + m.idx(gx, gz)) = *reinterpret_cast<const float4*>(stage + m.idx(gx, gz));
