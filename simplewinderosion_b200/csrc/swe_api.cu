@@ -80,6 +80,15 @@ struct swe_engine {
   int opt_cuda_graph = 1;             // replay the parallel erode of a single-GPU engine as one CUDA graph
   int opt_pdl = 1;                    // programmatic dependent launches between the round kernels
   int opt_call_batches = 1;           // a parallel call's particles fly as this many successive batches
+  int opt_schedule = 0;               // 0 = colour-queue scheduler (swe_queue.cu), 1 = lock-step rounds + stamped cascade
+  int opt_stagger = -1;               // colour queues: rounds over which the call's particles are injected (-1 = auto)
+  ColourQueues cq{};                  // queues + claim plane of the colour-queue scheduler
+  int sm_count = 148;
+  int last_micro_rounds = 0;          // micro-rounds the last colour-queue call needed
+  int opt_persistent = 1;             // colour queues: one cooperative launch per call (0 = one launch per micro-round)
+  int coop_ok = 0;                    // device supports cooperative launches
+  uint64_t claim_tags_used = 0;       // upper bound of the claim tags handed out since the last clearing
+  int persist_blocks_per_sm = 0;
   CallCtl* d_ctl = nullptr;           // seed / call index of the current call (read by graph-replayed kernels)
   struct CachedGraph { uint64_t key; cudaGraphExec_t exec; };
   std::vector<CachedGraph> graphs;
@@ -194,6 +203,28 @@ int need_stamp(swe_engine* e) {
   return SWE_OK;
 }
 
+int need_queues(swe_engine* e, int cycles) {
+  const int cap = ((cycles > 1024 ? cycles : 1024) + 255) / 256 * 256;
+  if (!e->cq.claim) {
+    SWE_CUDA(cudaMalloc(&e->cq.claim, e->cells() * sizeof(unsigned short)));
+    SWE_CUDA(cudaMalloc(&e->cq.count, 20 * 32 * sizeof(unsigned)));
+    SWE_CUDA(cudaMemsetAsync(e->cq.count, 0, 20 * 32 * sizeof(unsigned), e->stream));
+    const size_t lattice = (size_t)((e->m.rows + 2) / 3) * (size_t)((e->m.nz + 2) / 3);
+    SWE_CUDA(cudaMalloc(&e->cq.claim32, lattice * sizeof(unsigned)));
+    SWE_CUDA(cudaMemsetAsync(e->cq.claim32, 0, lattice * sizeof(unsigned), e->stream));
+    SWE_CUDA(cudaMalloc(&e->cq.persist, 512));
+    SWE_CUDA(cudaMemsetAsync(e->cq.persist, 0, 512, e->stream));
+  }
+  if (e->cq.cap >= cap) return SWE_OK;
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(e->cq.a); cudaFree(e->cq.b);
+  e->cq.a = e->cq.b = nullptr; e->cq.cap = 0;
+  SWE_CUDA(cudaMalloc(&e->cq.a, 18 * (size_t)cap * sizeof(float4)));
+  SWE_CUDA(cudaMalloc(&e->cq.b, 18 * (size_t)cap * sizeof(float4)));
+  e->cq.cap = cap;
+  return SWE_OK;
+}
+
 int check_launch(swe_engine* e, const char* what, int n = 1) {
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(SWE_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(err));
@@ -252,6 +283,8 @@ void stripe_exchange_end(swe_engine* e, unsigned s, int* launches) {
 }
 
 void finish_timers(swe_engine* e);
+int erode_epilogue(swe_engine* e);
+int erode_prologue(swe_engine* e);
 
 // ---- striped parallel erode, in phases so that a single host thread can interleave several
 // in-process stripes round by round (swe_stripe_group_erode) --------------------------------------
@@ -370,6 +403,8 @@ uint64_t graph_key(const swe_engine* e, int cycles) {
   mix(&e->opt_cascade_interval, sizeof(int));
   mix(&e->opt_pdl, sizeof(int));
   mix(&e->opt_call_batches, sizeof(int));
+  mix(&e->opt_schedule, sizeof(int));
+  mix(&e->opt_stagger, sizeof(int));
   mix(&e->stream, sizeof e->stream);
   mix(&e->m.rock, sizeof e->m.rock);
   mix(&e->pbuf.a, sizeof e->pbuf.a);
@@ -418,6 +453,148 @@ int erode_parallel_graph(swe_engine* e, int cycles) {
   e->call_index++;
   e->erode_calls++;
   return SWE_OK;
+}
+
+// ---- colour-queue scheduler (swe_queue.cu) ---------------------------------------------------------
+// Stagger: the call's particles are injected evenly over the first S rounds (9 micro-rounds each).
+// auto: S = 8 * density * (maxAge + 2) rounds, i.e. 2 x the particle lifetime at 0.25 particles per
+// cell (the setting the statistical-parity tests pass with), capped at 4 lifetimes; calls thinner
+// than 0.02 particles per cell (the reference's own frames) are injected at once.
+int colour_stagger_micro(const swe_engine* e, int cycles) {
+  const int life = e->p.max_age + 2;
+  long long rounds = e->opt_stagger;
+  if (rounds < 0) {
+    const double density = (double)cycles / ((double)e->m.nx * (double)e->m.nz);
+    rounds = density < 0.02 ? 0 : (long long)(8.0 * density * life + 0.5);
+    if (rounds > 4LL * life) rounds = 4LL * life;
+  }
+  long long micro = 9 * rounds;
+  if (micro > cycles) micro = cycles;
+  return micro < 1 ? 1 : (int)micro;
+}
+
+int colour_main_micro(const swe_engine* e, int cycles) {
+  const int k = colour_stagger_micro(e, cycles) + 9 * (e->p.max_age + 2);
+  return (k + 17) / 18 * 18;
+}
+
+int colour_grid(const swe_engine* e, int cycles) {
+  long long blocks = ((long long)cycles / 3 + 255) / 256 + 1;
+  const long long cap = (long long)e->sm_count * 6;
+  return (int)(blocks > cap ? cap : blocks);
+}
+
+// micro-rounds [k0, k1) of a call: colour k % 9, parity of colour c toggles after each of its turns
+int colour_rounds(swe_engine* e, int cycles, int k0, int k1, const CallCtl* ctl) {
+  const int S = colour_stagger_micro(e, cycles);
+  const bool pdl = e->opt_pdl != 0;
+  const int grid = colour_grid(e, cycles);
+  for (int k = k0; k < k1; k++) {
+    MicroRoundArgs r{};
+    r.colour = k % 9;
+    // colour c has been served floor((k - c + 8) / 9) times before micro-round k
+    unsigned pin = 0u;
+    for (int c = 0; c < 9; c++) pin |= (unsigned)(((k - c + 8) / 9) & 1) << c;
+    r.pin = pin;
+    r.index = (unsigned)k;
+    r.tag = 1u + (unsigned)(k / 9) % 65535u;
+    r.n_total = cycles;
+    if (k < S) { r.inj_first = k; r.inj_stride = S; r.inj_count = (cycles - k + S - 1) / S; }
+    launch_colour_round(e->m, e->p, e->cq, r, e->seed, ctl ? 0u : e->call_index, ctl, e->d_stats, e->stream, pdl, grid);
+  }
+  return check_launch(e, "colour_round", k1 - k0);
+}
+
+// host-side completion check: a call is over when every injected particle has died
+int colour_finish(swe_engine* e, int cycles, int k_done, uint64_t particles_before) {
+  for (int guard = 0; guard < 4096; guard++) {
+    DevStats s;
+    SWE_CUDA(cudaMemcpyAsync(&s, e->d_stats, sizeof s, cudaMemcpyDeviceToHost, e->stream));
+    SWE_CUDA(cudaStreamSynchronize(e->stream));
+    if (s.particles - particles_before == (uint64_t)cycles && s.particles == s.exits_oob + s.exits_age) {
+      e->last_micro_rounds = k_done;
+      return SWE_OK;
+    }
+    if (int rc = colour_rounds(e, cycles, k_done, k_done + 288, nullptr)) return rc;
+    k_done += 288;
+  }
+  return fail(SWE_ERR_STATE, "colour-queue erode did not finish");
+}
+
+// one cooperative launch for the whole particle phase; fully asynchronous (the kernel ends itself)
+int erode_colour_persistent(swe_engine* e, int cycles) {
+  if (int rc = need_queues(e, cycles)) return rc;
+  if (int rc = erode_prologue(e)) return rc;
+  long long blocks = ((long long)cycles / 3 + 255) / 256 + 1;
+  const long long cap = (long long)e->sm_count * e->persist_blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  const unsigned stagger = (unsigned)colour_stagger_micro(e, cycles);
+  const unsigned max_micro = 64u * (unsigned)colour_main_micro(e, cycles);
+  // claim tags grow by at most max_micro + 2 per call: clear the lattice before they could wrap
+  if (e->claim_tags_used + max_micro + 2ull >= 0xffff0000ull) {
+    const size_t lattice = (size_t)((e->m.rows + 2) / 3) * (size_t)((e->m.nz + 2) / 3);
+    SWE_CUDA(cudaMemsetAsync(e->cq.claim32, 0, lattice * sizeof(unsigned), e->stream));
+    SWE_CUDA(cudaMemsetAsync(static_cast<char*>(e->cq.persist) + 260, 0, sizeof(unsigned), e->stream));   // PersistCtl::tag_base
+    e->claim_tags_used = 0;
+  }
+  e->claim_tags_used += max_micro + 2ull;
+  const cudaError_t err = launch_colour_persistent(e->m, e->p, e->cq, cycles, stagger, max_micro, e->seed, e->call_index,
+                                                   e->d_stats, e->stream, (int)blocks);
+  if (err != cudaSuccess) return fail(SWE_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(err));
+  e->launches++;
+  e->last_micro_rounds = -1;   // read back lazily (swe_get_stats)
+  return erode_epilogue(e);
+}
+
+int erode_colour(swe_engine* e, int cycles) {
+  if (e->opt_persistent && e->coop_ok && e->persist_blocks_per_sm > 0 && !(e->m.rock && colour_persistent_blocks_per_sm(true) < 1))
+    return erode_colour_persistent(e, cycles);
+  if (int rc = need_queues(e, cycles)) return rc;
+  finish_timers(e);
+  DevStats s0;
+  SWE_CUDA(cudaMemcpyAsync(&s0, e->d_stats, sizeof s0, cudaMemcpyDeviceToHost, e->stream));
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  if (s0.particles != s0.exits_oob + s0.exits_age)
+    return fail(SWE_ERR_STATE, "particle counters are inconsistent (an earlier call failed?)");
+  const int k_main = colour_main_micro(e, cycles);
+  const bool use_graph = e->opt_cuda_graph != 0;
+  const CallCtl ctl_host{(uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->call_index, 0u};
+  SWE_CUDA(cudaMemcpyAsync(e->d_ctl, &ctl_host, sizeof ctl_host, cudaMemcpyHostToDevice, e->stream));
+  SWE_CUDA(cudaEventRecord(e->ev_a, e->stream));
+  SWE_CUDA(cudaEventRecord(e->ev_f0, e->stream));
+  if (use_graph) {
+    const uint64_t key = graph_key(e, cycles);
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : e->graphs) if (g.key == key) exec = g.exec;
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      SWE_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = SWE_OK;
+      if (cudaMemsetAsync(e->m.track, 0, e->cells() * sizeof(float4), e->stream) != cudaSuccess) rc = SWE_ERR_CUDA;
+      if (rc == SWE_OK && cudaMemsetAsync(e->cq.claim, 0, e->cells() * sizeof(unsigned short), e->stream) != cudaSuccess) rc = SWE_ERR_CUDA;
+      if (rc == SWE_OK) rc = colour_rounds(e, cycles, 0, k_main, e->d_ctl);
+      const cudaError_t end = cudaStreamEndCapture(e->stream, &graph);
+      if (rc != SWE_OK || end != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        return rc != SWE_OK ? rc : fail(SWE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(end));
+      }
+      const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (inst != cudaSuccess) return fail(SWE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(inst));
+      if (e->graphs.size() >= 4) { cudaGraphExecDestroy(e->graphs.front().exec); e->graphs.erase(e->graphs.begin()); }
+      e->graphs.push_back({key, exec});
+    } else {
+      e->launches += (uint64_t)k_main;
+    }
+    SWE_CUDA(cudaGraphLaunch(exec, e->stream));
+  } else {
+    SWE_CUDA(cudaMemsetAsync(e->m.track, 0, e->cells() * sizeof(float4), e->stream));
+    SWE_CUDA(cudaMemsetAsync(e->cq.claim, 0, e->cells() * sizeof(unsigned short), e->stream));
+    if (int rc = colour_rounds(e, cycles, 0, k_main, nullptr)) return rc;
+  }
+  if (int rc = colour_finish(e, cycles, k_main, s0.particles)) return rc;
+  return erode_epilogue(e);
 }
 
 int erode_prologue(swe_engine* e) {
@@ -563,7 +740,11 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
     e->pbuf.live = nullptr; e->pbuf.live_slots = 0;
   }
   make_height_tensor_map(e->m, &e->tmap);   // optional: plain-load kernels are used when it fails
-  preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe(); preload_noise();
+  preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe(); preload_noise(); preload_queue();
+  if (cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || e->sm_count < 1) e->sm_count = 148;
+  if (cudaDeviceGetAttribute(&e->coop_ok, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) e->coop_ok = 0;
+  e->persist_blocks_per_sm = colour_persistent_blocks_per_sm(false);
+  (void)cudaGetLastError();
   (void)cudaGetLastError();
   launch_det_srand(e->d_rng, 1u, e->stream);
   TRY(cudaGetLastError());
@@ -601,6 +782,8 @@ void swe_destroy(swe_engine* e) {
   cudaFree(e->pbuf.a); cudaFree(e->pbuf.b); cudaFree(e->pbuf.live); cudaFree(e->d_stamp);
   cudaFree(e->st.arena); cudaFree(e->st.d_pid); cudaFree(e->st.d_vars);
   cudaFree(e->tsc.stage); cudaFree(e->tsc.flags); cudaFree(e->d_rock); cudaFree(e->d_ctl);
+  cudaFree(e->cq.a); cudaFree(e->cq.b); cudaFree(e->cq.count); cudaFree(e->cq.claim);
+  cudaFree(e->cq.claim32); cudaFree(e->cq.persist);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : e->st.ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -822,6 +1005,8 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
     return fail(SWE_ERR_INVALID, "unknown mode %d", mode);
   if (e->st.enabled)
     if (int rc = stripe_erode_check(e, cycles, mode)) return rc;
+  if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_schedule == 0)
+    return erode_colour(e, cycles);
   if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_cuda_graph && !e->opt_kernel_timing)
     return erode_parallel_graph(e, cycles);
   // world.hpp:38-44: reset the four track members of every cell
@@ -1142,6 +1327,19 @@ int swe_get_stats(swe_engine* e, swe_stats* out) {
     out->stripe_overflow = vars[1];
     if (vars[2]) return fail(SWE_ERR_STATE, "stripe neighbour exchange timed out (a rank is missing or crashed)");
   }
+  if (e->cq.persist) {
+    unsigned pc[4] = {0, 0, 0, 0};   // PersistCtl line 2: live, tag_base, micro, error
+    SWE_CUDA(cudaMemcpy(pc, static_cast<char*>(e->cq.persist) + 256, sizeof pc, cudaMemcpyDeviceToHost));
+    if (e->last_micro_rounds < 0) e->last_micro_rounds = (int)pc[2];
+    if (pc[3] == 1u) return fail(SWE_ERR_STATE, "colour-queue kernel: grid barrier watchdog fired");
+    if (pc[3] == 2u) return fail(SWE_ERR_STATE, "colour-queue kernel: micro-round cap reached with particles alive");
+  }
+  out->last_micro_rounds = (uint64_t)(e->last_micro_rounds < 0 ? 0 : e->last_micro_rounds);
+  if (e->cq.count) {
+    unsigned dropped = 0;
+    SWE_CUDA(cudaMemcpy(&dropped, e->cq.count + 19 * 32, sizeof dropped, cudaMemcpyDeviceToHost));
+    out->queue_dropped = dropped;
+  }
   out->last_fly_ms = e->last_fly_ms;
   out->last_round_ms = e->last_round_ms;
   out->last_cascade_ms = e->last_cascade_ms;
@@ -1275,6 +1473,14 @@ int swe_set_option(swe_engine* e, int option, int value) {
     case SWE_OPT_CALL_BATCHES:
       if (value < 1 || value > 64) return fail(SWE_ERR_INVALID, "call batches must be in [1, 64]");
       e->opt_call_batches = value; return SWE_OK;
+    case SWE_OPT_SCHEDULE:
+      if (value < 0 || value > 1) return fail(SWE_ERR_INVALID, "schedule must be 0 (colour queues) or 1 (lock-step rounds)");
+      e->opt_schedule = value; return SWE_OK;
+    case SWE_OPT_PERSISTENT:
+      e->opt_persistent = value ? 1 : 0; return SWE_OK;
+    case SWE_OPT_STAGGER_ROUNDS:
+      if (value < -1 || value > (1 << 20)) return fail(SWE_ERR_INVALID, "stagger rounds must be -1 (auto) or in [0, 2^20]");
+      e->opt_stagger = value; return SWE_OK;
     default:
       return fail(SWE_ERR_INVALID, "unknown option %d", option);
   }

@@ -174,6 +174,35 @@ void launch_par_round(const ParticleBuf& buf, const MapView& m, const swe_params
                       unsigned char* stamp, unsigned char stamp_now, DevStats* stats, cudaStream_t st,
                       bool pdl = false);
 
+// colour-queue scheduler of the single-GPU parallel erode: swe_queue.cu
+// 9 colours x 2 parities of particle queues (32-byte records as in ParticleBuf), one 16-bit claim word
+// per cell, 18 counters + ticket + dropped (128 B apart).
+struct ColourQueues {
+  float4* a;
+  float4* b;
+  unsigned* count;          // [20 * 32]
+  unsigned short* claim;    // [cells]  launch-per-micro-round form: 16-bit tags, cleared per call
+  unsigned* claim32;        // [ceil(rows/3) * ceil(nz/3)]  persistent form: one word per 3x3 lattice cell, monotonic
+                            // 32-bit tags (atomicMax), shared by the nine colours, cleared when the tags would wrap
+  void* persist;            // PersistCtl of the persistent kernel (barrier, live count, claim-tag base)
+  int cap;                  // records per queue
+};
+struct MicroRoundArgs {
+  int colour;               // colour served by this micro-round
+  unsigned pin;             // bit c = parity of colour c's input side
+  unsigned index;           // micro-round number within the call
+  unsigned tag;             // claim value (1..65535)
+  int inj_first, inj_stride, inj_count, n_total;   // staggered injection: ids inj_first + j*inj_stride, j < inj_count
+};
+void launch_colour_round(const MapView& m, const swe_params& p, const ColourQueues& cq, const MicroRoundArgs& r,
+                         uint64_t seed, uint32_t call, const CallCtl* ctl, DevStats* stats, cudaStream_t st, bool pdl,
+                         int grid_blocks);
+int colour_persistent_blocks_per_sm(bool layered);
+cudaError_t launch_colour_persistent(const MapView& m, const swe_params& p, const ColourQueues& cq, int n_total,
+                                     unsigned stagger, unsigned max_micro, uint64_t seed, uint32_t call,
+                                     DevStats* stats, cudaStream_t st, int grid_blocks);
+void preload_queue();
+
 // stripe exchange primitives: swe_stripe.cu
 void launch_stripe_push(const float* src_h, float* dst_h, const unsigned char* src_s, unsigned char* dst_s,
                         size_t cells, cudaStream_t st);
