@@ -15,9 +15,15 @@ the reference snapshot). One JSON line is printed by rank 0.
   e2e       the same metric through the host-buffer C-ABI: every step uploads the height
             plane from pinned host memory, erodes, and downloads height + the four flow
             fields (what the reference's renderer reads each frame)
-  roofline  the particle kernel: 104 algorithmic B/step / its device time,
-            against MEASURED_PEAKS.json hbm_gbs; cascade_roofline is the same for the
+  roofline  the flight kernel (colour_persistent_kernel: Wind::fly + erosion + World::cascade of
+            every particle step, one cooperative launch per call): 104 algorithmic B/step
+            (3x3 heights read + written, four tracks read + written) / its device
+            time, against MEASURED_PEAKS.json hbm_gbs; cascade_roofline is the same for the
             whole-map cascade sweep (8 B/cell/sweep) on the 8192^2 random-slope workload
+  schedule  the headline runs the colour-queue scheduler (parity-green against the sequential
+            oracle at this density, tests/test_gpu_density.py); round 1's lock-step schedule,
+            which is faster but exports +24 % more sand than the reference, is timed beside it
+            as `lockstep_all_at_once`
   cpu_baseline  the unmodified reference (oracle/_ref) timed on one host core on a bounded
             sample of the same workload (the reference is single-threaded, world.hpp:100)
 """
@@ -365,6 +371,30 @@ def layered_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> d
     return out
 
 
+def lockstep_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> dict:
+    """Round 1's schedule (SWE_OPT_SCHEDULE = 1): every particle of the call steps once per round, then one
+    stamped cascade over the touched cells. Timed beside the headline because it is what round 1 reported;
+    it is NOT parity-green at this density (tests/test_gpu_density.py, profiles/r1_stat_parity_density.txt)."""
+    w = swe.World(n, device=device)
+    w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_LOCKSTEP)
+    w.upload(hm)
+    w.srand(1)
+    for _ in range(2):
+        w.erode(particles, swe.MODE_PARALLEL)
+    w.sync()
+    s0 = w.stats().steps
+    ms = 0.0
+    for _ in range(steps):
+        w.erode(particles, swe.MODE_PARALLEL)
+        ms += w.stats().last_erode_ms
+    out = {"schedule": "lock-step rounds, all particles in flight at once (round 1)",
+           "value": (w.stats().steps - s0) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "parity": "fails: +24 % exported sand, erosion-field correlation 0.80 against the sequential oracle at 0.25 "
+                     "particles per cell"}
+    w.close()
+    return out
+
+
 def run_ours(args) -> None:
     import numpy as np
     import torch
@@ -461,23 +491,25 @@ def run_ours(args) -> None:
     overflow_total = sum_over_ranks(float(st1.stripe_overflow))
     value = total_steps / (dev_ms * 1e-3)
 
-    # per-kernel times (CUDA events on the launch stream around every round / cascade launch):
-    # an extra pass outside the timed region, with the engine's kernel-timing option on
-    w.set_option(swe.OPT_KERNEL_TIMING, 1)
-    round_ms = casc_ms = fly_ms = 0.0
+    # device time of the particle phase (CUDA events on the launch stream around the flight kernel(s) of each
+    # call, swe_stats.last_fly_ms): an extra pass outside the timed region, one stats read-back per call
+    lockstep = world > 1          # the stripe engines run round 1's lock-step schedule
+    if lockstep:
+        w.set_option(swe.OPT_KERNEL_TIMING, 1)
+    round_ms = casc_ms = fly_ms = erode_ms = 0.0
     fly_steps = 0
+    micro_rounds = 0
     for _ in range(args.steps):
         s_before = w.stats().steps
         w.erode(particles_call, swe.MODE_PARALLEL)
         s = w.stats()
-        round_ms += s.last_round_ms; casc_ms += s.last_cascade_ms; fly_ms += s.last_erode_ms
+        round_ms += s.last_round_ms; casc_ms += s.last_cascade_ms; fly_ms += s.last_fly_ms; erode_ms += s.last_erode_ms
         fly_steps += s.steps - s_before
-    w.set_option(swe.OPT_KERNEL_TIMING, 0)
+        micro_rounds += s.last_micro_rounds
+    if lockstep:
+        w.set_option(swe.OPT_KERNEL_TIMING, 0)
     rounds_per_call = w.params.max_age + 2
-    if round_ms <= 0.0:
-        round_ms = casc_ms = fly_ms / 2
-    achieved = BYTES_PER_STEP * fly_steps / (round_ms * 1e-3) / 1e9
-    pipeline = BYTES_PER_STEP * fly_steps / ((round_ms + casc_ms) * 1e-3) / 1e9
+    achieved = BYTES_PER_STEP * fly_steps / (fly_ms * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer C-ABI ---------------------------------------------
     def pinned(shape):
@@ -490,15 +522,13 @@ def run_ours(args) -> None:
     h_in, p_in = pinned((rows_local, n))
     h_out, p_out = pinned((5, rows_local, n))
     h_in[...] = w.download()
-    planes = (swe.HEIGHT, swe.MASSFLOW, swe.MOMENTUMX, swe.MOMENTUMY, swe.MOMENTUMZ)
 
     def e2e_step():
         w.upload(h_in)
         if world > 1:
             w.sync_halos()
         w.erode(particles_call, swe.MODE_PARALLEL)
-        for i, pl in enumerate(planes):
-            w.download(pl, out=h_out[i])
+        w.download_frame(out=h_out)   # height + massflow + momentum x/y/z: what the renderer reads each frame
         h_in[...] = h_out[0]          # the host owns the canonical map between calls
 
     e2e_step()
@@ -539,7 +569,8 @@ def run_ours(args) -> None:
                 "per_round_per_interior_rank_bytes": int((7 + 5) * n * 5),
                 "what": "7 boundary rows pushed down + 5 up, height (4 B) + stamp (1 B) per cell, by P2P store kernels; "
                         "plus 36 B per particle handed to a neighbour's inbox", "rounds_per_step": 514}}),
-            "l2": "working set 720 MiB (height 64 + track 256 + field 256 + particles 128 + stamps 16) > 126 MB L2; no flush needed",
+            "l2": "working set > 600 MiB per GPU (height 64 + track 256 + field 256 MiB + live particle records + claim lattice) "
+                  "> 126 MB L2; no flush needed",
             "steps_per_particle": total_steps / max(1.0, total_particles),
         },
         "clocks": clocks,
@@ -547,18 +578,31 @@ def run_ours(args) -> None:
                 "d2h_bytes_per_step": int(5 * 4 * rows_local * n), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "result_check_mean_height": mean_h},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "par_round_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("par_round"),
-                     "peak_source": peak_src, "algorithmic_bytes_per_step": BYTES_PER_STEP,
-                     "launches_per_step": rounds_per_call,
-                     "kernel_ms_per_launch": round_ms / args.steps / rounds_per_call,
-                     "share_of_step": {"par_round_kernel": round_ms / fly_ms,
-                                       ("cascade_tile_stamped_kernel+commit" if world == 1 else
-                                        "halo exchange+hand-off+cascade"): casc_ms / fly_ms},
-                     "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
-                     "note": "104 B/step is SURVEY 8(d)'s figure for flight+cascade; `achieved` charges it "
-                             "to the particle kernel alone, `pipeline_*` to particle + per-round cascade kernels"},
+        "roofline": ({
+            "bound": "hbm", "kernel": "colour_persistent_kernel (Wind::fly + erosion + World::cascade per particle step)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic("colour_persistent"), "peak_source": peak_src,
+            "algorithmic_bytes_per_step": BYTES_PER_STEP, "launches_per_step": 1,
+            "kernel_ms_per_launch": fly_ms / args.steps,
+            "share_of_step": {"colour_persistent_kernel": fly_ms / erode_ms, "track reset + EMA": 1.0 - fly_ms / erode_ms},
+            "micro_rounds_per_step": micro_rounds / args.steps,
+            "note": "104 B/step is SURVEY 8(d)'s figure for flight + cascade, which this one kernel does; it is bound by "
+                    "dependent-access latency and the grid barrier per micro-round, not by HBM bandwidth (DESIGN.md 4)"}
+            if not lockstep else {
+            "bound": "hbm", "kernel": "par_round_kernel + cascade_tile_stamped_kernel + cascade_commit_kernel (+ stripe exchange)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_step": BYTES_PER_STEP,
+            "launches_per_step": 6 * rounds_per_call,
+            "share_of_step": {"par_round_kernel": round_ms / max(fly_ms, 1e-9),
+                              "halo exchange+hand-off+cascade": casc_ms / max(fly_ms, 1e-9)}}),
     }
+    line["config"]["schedule"] = (
+        "lock-step rounds (stripe engines; round 1's schedule: NOT parity-green at this density, DESIGN.md 6)" if lockstep else
+        f"colour queues: 9-colour micro-rounds, one particle per cell, in-register cascade, automatic stagger "
+        f"({int(8 * particles / (n * n) * rounds_per_call + 0.5)} rounds); parity-green at this density "
+        f"(tests/test_gpu_density.py)")
+    if world == 1:
+        line["lockstep_all_at_once"] = lockstep_extra(swe, local, n, particles, hm, args.steps)
     if world == 1 and not args.skip_layered:
         line["layered_extension"] = layered_extra(swe, local, n, particles, hm, args.steps)
         line["dune_formation_cfg2"] = dune_formation_extra(swe, local, args.steps)

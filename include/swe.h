@@ -86,7 +86,7 @@ typedef enum swe_option {
    * launch latency when a call has few particles (the reference's own 8*tilesize frame: 2-5 %);
    * 0 = plain stream order. Results are identical either way. */
   SWE_OPT_PDL = 5,
-  /* Parallel mode, single-GPU engines: the particles of one swe_erode call fly as B successive batches
+  /* Parallel mode, single-GPU engines, lock-step schedule (SWE_OPT_SCHEDULE = 1) only: the particles of one swe_erode call fly as B successive batches
    * (default 1 = all at once), each spread over the whole map and seeing the terrain the previous
    * batches left. The reference flies its particles strictly one after another; with many particles
    * per cell in flight at once the parallel mode exports more sand than the reference (measured:
@@ -195,6 +195,10 @@ int swe_import_state(swe_engine* e, const void* buf, size_t bytes);
  * between consecutive cells in the host buffer (4 = packed plane, 36 = reference AoS). */
 int swe_upload_plane(swe_engine* e, int plane, const float* src, ptrdiff_t stride_bytes);
 int swe_download_plane(swe_engine* e, int plane, float* dst, ptrdiff_t stride_bytes);
+/* The per-frame read-back of the reference's render loop (SimpleWindErosion.cpp:219-230: updatenode reads
+ * height, the wind map reads the momentum fields): five packed planes height, massflow, momentumx,
+ * momentumy, momentumz (5*nx*nz floats) with one pass over the field plane and one synchronisation. */
+int swe_download_frame(swe_engine* e, float* dst5);
 /* Whole reference pool in one go: `cells` points at nx*nz 36-byte quad::cell records. */
 int swe_upload_cells(swe_engine* e, const void* cells);
 int swe_download_cells(swe_engine* e, void* cells);

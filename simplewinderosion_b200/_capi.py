@@ -108,6 +108,7 @@ PROTOTYPES = {
     "swe_import_state": (C.c_int, [_E, C.c_void_p, C.c_size_t]),
     "swe_upload_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_download_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
+    "swe_download_frame": (C.c_int, [_E, C.c_void_p]),
     "swe_upload_cells": (C.c_int, [_E, C.c_void_p]),
     "swe_download_cells": (C.c_int, [_E, C.c_void_p]),
     "swe_upload_rock": (C.c_int, [_E, C.c_void_p, C.c_ssize_t]),

@@ -923,6 +923,24 @@ int swe_download_plane(swe_engine* e, int plane, float* dst, ptrdiff_t stride_by
   return SWE_OK;
 }
 
+// What the reference's frame loop reads after World::erode (SimpleWindErosion.cpp:219-230): height (updatenode)
+// and the flow fields (wind map), as five packed planes in one call: one unpack pass over the field plane, two
+// device-to-host copies, one synchronisation (five swe_download_plane calls cost five passes and five syncs).
+int swe_download_frame(swe_engine* e, float* dst5) {
+  if (int rc = bind(e)) return rc;
+  if (!dst5) return fail(SWE_ERR_INVALID, "dst is NULL");
+  const size_t n = e->host_cells(), bytes = n * sizeof(float);
+  const MapView ov = e->owned();
+  if (int rc = need_scratch(e, 4 * bytes)) return rc;
+  launch_unpack_field(ov, false, e->d_scratch, e->stream);
+  if (int rc = check_launch(e, "unpack_field")) return rc;
+  SWE_CUDA(cudaMemcpyAsync(dst5, ov.height, bytes, cudaMemcpyDeviceToHost, e->stream));
+  SWE_CUDA(cudaMemcpyAsync(dst5 + n, e->d_scratch, 4 * bytes, cudaMemcpyDeviceToHost, e->stream));
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  finish_timers(e);
+  return SWE_OK;
+}
+
 int swe_upload_rock(swe_engine* e, const float* src, ptrdiff_t stride_bytes) {
   if (int rc = bind(e)) return rc;
   if (e->st.enabled) return fail(SWE_ERR_STATE, "the layered extension is not available on stripe engines");

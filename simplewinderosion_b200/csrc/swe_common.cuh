@@ -231,6 +231,7 @@ void launch_stripe_wait_merge(const StripeOutbox& in_a, const StripeOutbox& in_b
 void launch_ema(const MapView& m, float lrate, cudaStream_t st);
 void launch_pack_plane(const MapView& m, int plane, const float* d_src, cudaStream_t st);
 void launch_unpack_plane(const MapView& m, int plane, float* d_dst, cudaStream_t st);
+void launch_unpack_field(const MapView& m, bool track, float* d_dst4, cudaStream_t st);
 void launch_cells_to_planes(const MapView& m, const float* d_cells, cudaStream_t st);
 void launch_planes_to_cells(const MapView& m, float* d_cells, cudaStream_t st);
 void launch_sum_plane(const MapView& m, int plane, double* d_out, cudaStream_t st);

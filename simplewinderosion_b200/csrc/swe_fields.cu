@@ -46,6 +46,15 @@ __global__ void unpack_plane_kernel(MapView m, int plane, float* __restrict__ ds
     dst[i] = *plane_elem(m, plane, i);
 }
 
+// the four members of one float4 plane as four packed planes (dst[0..n), dst[n..2n), ...): one pass over the
+// plane, float4 loads, coalesced stores -- the per-frame read-back of the flow fields (SimpleWindErosion.cpp:224-230)
+__global__ void unpack_vec_plane_kernel(const float4* __restrict__ src, size_t n, float* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(src + i);
+    dst[i] = v.x; dst[n + i] = v.y; dst[2 * n + i] = v.z; dst[3 * n + i] = v.w;
+  }
+}
+
 // reference AoS record = 9 floats in swe_plane order (cellpool.h:226-240)
 __global__ void cells_to_planes_kernel(MapView m, const float* __restrict__ cells) {
   const size_t n = (size_t)m.rows * m.nz;
@@ -104,6 +113,10 @@ void launch_pack_plane(const MapView& m, int plane, const float* d_src, cudaStre
 void launch_unpack_plane(const MapView& m, int plane, float* d_dst, cudaStream_t st) {
   unpack_plane_kernel<<<grid_for((size_t)m.rows * m.nz, 256, 8), 256, 0, st>>>(m, plane, d_dst);
 }
+void launch_unpack_field(const MapView& m, bool track, float* d_dst4, cudaStream_t st) {
+  const size_t n = (size_t)m.rows * m.nz;
+  unpack_vec_plane_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(track ? m.track : m.field, n, d_dst4);
+}
 void launch_cells_to_planes(const MapView& m, const float* d_cells, cudaStream_t st) {
   cells_to_planes_kernel<<<grid_for((size_t)m.rows * m.nz, 256, 8), 256, 0, st>>>(m, d_cells);
 }
@@ -122,6 +135,7 @@ void preload_fields() {
   cudaFuncGetAttributes(&a, ema_kernel);
   cudaFuncGetAttributes(&a, pack_plane_kernel);
   cudaFuncGetAttributes(&a, unpack_plane_kernel);
+  cudaFuncGetAttributes(&a, unpack_vec_plane_kernel);
   cudaFuncGetAttributes(&a, cells_to_planes_kernel);
   cudaFuncGetAttributes(&a, planes_to_cells_kernel);
   cudaFuncGetAttributes(&a, sum_plane_kernel);

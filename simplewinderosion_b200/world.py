@@ -160,6 +160,15 @@ class World:
         check(lib.swe_download_plane(self._h, plane, out.ctypes.data, 4))
         return out
 
+    def download_frame(self, out: np.ndarray | None = None) -> np.ndarray:
+        """What the reference's frame loop reads after World::erode (SimpleWindErosion.cpp:219-230): the (5, nx, nz)
+        stack height, massflow, momentumx, momentumy, momentumz in one call and one synchronisation."""
+        if out is None:
+            out = np.empty((5, self.nx, self.nz), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == 5 * self.nx * self.nz
+        check(lib.swe_download_frame(self._h, out.ctypes.data))
+        return out
+
     # layered-terrain extension (bedrock under the sand; not in the reference snapshot)
     def upload_rock(self, rock: np.ndarray) -> None:
         a = np.ascontiguousarray(rock, dtype=np.float32)

@@ -108,6 +108,28 @@ def test_det_reference_fingerprints(run):
     assert abs(w.sum_plane(swe.HEIGHT) - run["sum_final"]) < 1e-9
 
 
+SFP = json.load(open(os.path.join(G, "survey_fingerprints.json")))
+
+
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize("run", [r for r in SFP["erode"] if r["n"] <= 1024], ids=lambda r: f"n{r['n']}x{r['calls']}")
+def test_det_survey_long_run_fingerprints(run):
+    """The long runs of SURVEY.md 8(c) in deterministic mode, bit for bit against the unmodified reference:
+    256^2 x 100 World::erode(2048) = BASELINE.json configs[0] ("100 headless erode cycles"; 37,259,394 steps,
+    hash c748ab2d23943aa6, ~2 minutes: deterministic mode is one GPU thread) and 1024^2 x 3 x erode(8192)."""
+    ora = gaussian(run["n"])
+    w = swe.World(run["n"])
+    w.upload(ora.plane(0))
+    w.srand(run["seed"])
+    for _ in range(run["calls"]):
+        w.erode(run["cycles"], swe.MODE_DETERMINISTIC)
+    st = w.stats()
+    assert st.steps == run["steps"]
+    assert st.exits_oob == run["exits_oob"] and st.exits_age == run["exits_age"]
+    assert f"{w.hash_height():016x}" == run["hash"]
+    assert abs(st.sediment_lost - run["sediment_lost"]) < 1e-9
+
+
 def test_det_survey_fingerprint_512_one_call():
     """First World::erode(4096) of the survey's 512^2 run (SURVEY.md 8c): 1,164,517 steps."""
     ora = gaussian(512)

@@ -61,9 +61,11 @@ def test_striped_erode_accounts_for_every_particle(n, world, cycles):
     for w in ws:
         w.srand(7)
     single = swe.World(n)
+    single.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_LOCKSTEP)   # the stripe engines run the lock-step schedule
     single.upload(hm)
     single.srand(7)
     other = swe.World(n)          # same engine, another seed: how much two runs differ anyway
+    other.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_LOCKSTEP)
     other.upload(hm)
     other.srand(8)
     s0 = float(hm.astype(np.float64).sum())
