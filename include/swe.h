@@ -308,13 +308,20 @@ int swe_sync(swe_engine* e);
  *      ship the SWE_STRIPE_IPC_BYTES blob (e.g. torch.distributed all_gather), swe_stripe_open_ipc
  *   3. swe_stripe_connect(below, above)  (NULL at the map edges)
  *   4. swe_upload_plane(owned rows) on every rank, then swe_stripe_sync_halos */
-#define SWE_STRIPE_IPC_BYTES 256
+#define SWE_STRIPE_IPC_BYTES 512
 typedef struct swe_stripe_link {   /* a neighbour's buffers as device pointers valid on THIS GPU */
   void* height;
   void* stamp;
   void* arena;
   int32_t x0;              /* global row of the neighbour's first stored row */
   int32_t inbox_capacity;
+  /* colour-queue scheduler (swe_stripe_connect_ring): the rank's particle queues and barrier block */
+  void* queue_a;
+  void* queue_b;
+  void* queue_count;
+  void* persist;
+  int32_t queue_cap;
+  int32_t reserved;
 } swe_stripe_link;
 int swe_stripe_create(swe_engine** out, int nx, int nz, int own_lo, int own_hi, int max_particles,
                       const swe_params* params, int device);
@@ -322,6 +329,17 @@ int swe_stripe_export(swe_engine* e, swe_stripe_link* out);
 int swe_stripe_export_ipc(swe_engine* e, void* buf, size_t buf_bytes);
 int swe_stripe_open_ipc(swe_engine* e, const void* buf, size_t buf_bytes, swe_stripe_link* out);
 int swe_stripe_connect(swe_engine* e, const swe_stripe_link* below, const swe_stripe_link* above);
+/* Same wiring plus what the colour-queue scheduler needs on stripes: `links` holds the links of ALL n ranks in
+ * row order (the entry of this rank, links[rank], is ignored; n <= 8). Neighbours rank-1 / rank+1 serve the halo
+ * and hand-off paths as in swe_stripe_connect; in addition every rank's barrier mailbox is mapped, because the
+ * persistent flight kernels of all ranks run the same micro-round sequence and meet at a barrier that spans the
+ * GPUs (peer stores over NVLink, system-scope release/acquire). With it a stripe engine runs the colour-queue
+ * schedule (SWE_OPT_SCHEDULE = 0, parity-green at high particle density); a particle in a boundary row reads and
+ * writes the neighbour's rows of its 3x3 block directly in the neighbour's memory. `colocated` = stripe engines
+ * sharing this GPU (1 with one process per GPU; logical stripes in one process: their number), which caps the
+ * co-resident grid of each kernel. Without it (swe_stripe_connect only) a stripe engine runs the lock-step
+ * schedule. */
+int swe_stripe_connect_ring(swe_engine* e, int rank, int n, const swe_stripe_link* links, int colocated);
 int swe_stripe_sync_halos(swe_engine* e);
 int swe_stripe_rows(const swe_engine* e, int* own_lo, int* own_hi);
 /* One host thread driving several stripes (logical stripes on one GPU, or a process that owns

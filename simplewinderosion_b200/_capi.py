@@ -73,10 +73,12 @@ class Stats(C.Structure):
 class StripeLink(C.Structure):
     """struct swe_stripe_link (include/swe.h)"""
     _fields_ = [("height", C.c_void_p), ("stamp", C.c_void_p), ("arena", C.c_void_p),
-                ("x0", C.c_int32), ("inbox_capacity", C.c_int32)]
+                ("x0", C.c_int32), ("inbox_capacity", C.c_int32),
+                ("queue_a", C.c_void_p), ("queue_b", C.c_void_p), ("queue_count", C.c_void_p), ("persist", C.c_void_p),
+                ("queue_cap", C.c_int32), ("reserved", C.c_int32)]
 
 
-STRIPE_IPC_BYTES = 256
+STRIPE_IPC_BYTES = 512
 STATE_BYTES = 256
 
 # name -> (restype, argtypes); must list every symbol include/swe.h declares
@@ -98,6 +100,7 @@ PROTOTYPES = {
     "swe_stripe_export_ipc": (C.c_int, [_E, C.c_void_p, C.c_size_t]),
     "swe_stripe_open_ipc": (C.c_int, [_E, C.c_void_p, C.c_size_t, C.POINTER(StripeLink)]),
     "swe_stripe_connect": (C.c_int, [_E, C.POINTER(StripeLink), C.POINTER(StripeLink)]),
+    "swe_stripe_connect_ring": (C.c_int, [_E, C.c_int, C.c_int, C.POINTER(StripeLink), C.c_int]),
     "swe_stripe_sync_halos": (C.c_int, [_E]),
     "swe_stripe_rows": (C.c_int, [_E, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "swe_stripe_group_erode": (C.c_int, [C.POINTER(_E), C.c_int, C.c_int]),

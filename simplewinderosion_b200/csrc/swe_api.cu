@@ -112,6 +112,10 @@ struct swe_engine {
     swe_stripe_link below{}, above{};
     unsigned seq = 0;
     std::vector<void*> ipc_opened;       // peer mappings to close at destroy
+    bool ring = false;                   // swe_stripe_connect_ring: colour-queue scheduler available
+    int rank = 0, nranks = 1, colocated = 1;
+    void* mailboxes[SWE_MAX_STRIPE_RANKS] = {};
+    int persist_blocks_per_sm = 0;
   } st;
 
   size_t cells() const { return (size_t)m.rows * (size_t)m.nz; }           // stored (owned + ghosts)
@@ -205,15 +209,16 @@ int need_stamp(swe_engine* e) {
 
 int need_queues(swe_engine* e, int cycles) {
   const int cap = ((cycles > 1024 ? cycles : 1024) + 255) / 256 * 256;
+  if (e->st.enabled) return SWE_OK;   // a stripe's queues are allocated at create (they are exported to the peers)
   if (!e->cq.claim) {
     SWE_CUDA(cudaMalloc(&e->cq.claim, e->cells() * sizeof(unsigned short)));
     SWE_CUDA(cudaMalloc(&e->cq.count, 20 * 32 * sizeof(unsigned)));
     SWE_CUDA(cudaMemsetAsync(e->cq.count, 0, 20 * 32 * sizeof(unsigned), e->stream));
-    const size_t lattice = (size_t)((e->m.rows + 2) / 3) * (size_t)((e->m.nz + 2) / 3);
+    const size_t lattice = (size_t)((e->m.rows + 2) / 3 + 1) * (size_t)((e->m.nz + 2) / 3);
     SWE_CUDA(cudaMalloc(&e->cq.claim32, lattice * sizeof(unsigned)));
     SWE_CUDA(cudaMemsetAsync(e->cq.claim32, 0, lattice * sizeof(unsigned), e->stream));
-    SWE_CUDA(cudaMalloc(&e->cq.persist, 512));
-    SWE_CUDA(cudaMemsetAsync(e->cq.persist, 0, 512, e->stream));
+    SWE_CUDA(cudaMalloc(&e->cq.persist, SWE_PERSIST_BYTES));
+    SWE_CUDA(cudaMemsetAsync(e->cq.persist, 0, SWE_PERSIST_BYTES, e->stream));
   }
   if (e->cq.cap >= cap) return SWE_OK;
   SWE_CUDA(cudaStreamSynchronize(e->stream));
@@ -302,6 +307,10 @@ StripeRound stripe_round_ctx(swe_engine* e) {
   sr.own_lo = S.own_lo; sr.own_hi = S.own_hi;
   sr.pid = S.d_pid; sr.n_used = S.d_vars + 0; sr.overflow = S.d_vars + 1;
   return sr;
+}
+
+bool stripe_uses_colour_queues(const swe_engine* e) {
+  return e->st.enabled && e->st.ring && e->opt_schedule == 0 && e->coop_ok && e->st.persist_blocks_per_sm > 0;
 }
 
 int stripe_erode_begin(swe_engine* e, int cycles) {
@@ -522,27 +531,53 @@ int colour_finish(swe_engine* e, int cycles, int k_done, uint64_t particles_befo
 }
 
 // one cooperative launch for the whole particle phase; fully asynchronous (the kernel ends itself)
-int erode_colour_persistent(swe_engine* e, int cycles) {
-  if (int rc = need_queues(e, cycles)) return rc;
-  if (int rc = erode_prologue(e)) return rc;
+int colour_launch_persistent(swe_engine* e, int cycles) {
   long long blocks = ((long long)cycles / 3 + 255) / 256 + 1;
-  const long long cap = (long long)e->sm_count * e->persist_blocks_per_sm;
+  const bool stripe = e->st.enabled;
+  long long cap = stripe ? (long long)e->sm_count * e->st.persist_blocks_per_sm / (e->st.colocated > 0 ? e->st.colocated : 1)
+                         : (long long)e->sm_count * e->persist_blocks_per_sm;
+  if (cap < 1) cap = 1;
   if (blocks > cap) blocks = cap;
   const unsigned stagger = (unsigned)colour_stagger_micro(e, cycles);
   const unsigned max_micro = 64u * (unsigned)colour_main_micro(e, cycles);
   // claim tags grow by at most max_micro + 2 per call: clear the lattice before they could wrap
   if (e->claim_tags_used + max_micro + 2ull >= 0xffff0000ull) {
-    const size_t lattice = (size_t)((e->m.rows + 2) / 3) * (size_t)((e->m.nz + 2) / 3);
+    const size_t lattice = (size_t)((e->m.rows + 2) / 3 + 1) * (size_t)((e->m.nz + 2) / 3);
     SWE_CUDA(cudaMemsetAsync(e->cq.claim32, 0, lattice * sizeof(unsigned), e->stream));
     SWE_CUDA(cudaMemsetAsync(static_cast<char*>(e->cq.persist) + 260, 0, sizeof(unsigned), e->stream));   // PersistCtl::tag_base
     e->claim_tags_used = 0;
   }
   e->claim_tags_used += max_micro + 2ull;
+  StripeQueues sq{};
+  if (stripe) {
+    auto& S = e->st;
+    sq.own_lo = S.own_lo; sq.own_hi = S.own_hi; sq.rank = S.rank; sq.nranks = S.nranks;
+    if (S.has_below) {
+      sq.below_h = static_cast<float*>(S.below.height); sq.below_x0 = S.below.x0;
+      sq.below_a = static_cast<float4*>(S.below.queue_a); sq.below_b = static_cast<float4*>(S.below.queue_b);
+      sq.below_count = static_cast<unsigned*>(S.below.queue_count); sq.below_cap = S.below.queue_cap;
+    }
+    if (S.has_above) {
+      sq.above_h = static_cast<float*>(S.above.height); sq.above_x0 = S.above.x0;
+      sq.above_a = static_cast<float4*>(S.above.queue_a); sq.above_b = static_cast<float4*>(S.above.queue_b);
+      sq.above_count = static_cast<unsigned*>(S.above.queue_count); sq.above_cap = S.above.queue_cap;
+    }
+    for (int i = 0; i < S.nranks; i++)
+      sq.mailbox[i] = reinterpret_cast<unsigned long long*>(static_cast<char*>(S.mailboxes[i]) + SWE_MAILBOX_OFFSET);
+  }
   const cudaError_t err = launch_colour_persistent(e->m, e->p, e->cq, cycles, stagger, max_micro, e->seed, e->call_index,
-                                                   e->d_stats, e->stream, (int)blocks);
+                                                   e->d_stats, e->stream, (int)blocks, stripe ? &sq : nullptr,
+                                                   !(stripe && e->st.colocated > 1));
   if (err != cudaSuccess) return fail(SWE_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(err));
   e->launches++;
   e->last_micro_rounds = -1;   // read back lazily (swe_get_stats)
+  return SWE_OK;
+}
+
+int erode_colour_persistent(swe_engine* e, int cycles) {
+  if (int rc = need_queues(e, cycles)) return rc;
+  if (int rc = erode_prologue(e)) return rc;
+  if (int rc = colour_launch_persistent(e, cycles)) return rc;
   return erode_epilogue(e);
 }
 
@@ -738,6 +773,20 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
     TRY(cudaMalloc(&e->pbuf.a, (size_t)e->pbuf.capacity * sizeof(float4)));
     TRY(cudaMalloc(&e->pbuf.b, (size_t)e->pbuf.capacity * sizeof(float4)));
     e->pbuf.live = nullptr; e->pbuf.live_slots = 0;
+    {
+      // colour-queue scheduler on stripes: the queues must exist before the links are exported
+      const int qcap = ((e->pbuf.capacity > 1024 ? e->pbuf.capacity : 1024) + 255) / 256 * 256;
+      const size_t lattice = (size_t)((e->m.rows + 2) / 3 + 1) * (size_t)((e->m.nz + 2) / 3);
+      TRY(cudaMalloc(&e->cq.a, 18 * (size_t)qcap * sizeof(float4)));
+      TRY(cudaMalloc(&e->cq.b, 18 * (size_t)qcap * sizeof(float4)));
+      TRY(cudaMalloc(&e->cq.count, 20 * 32 * sizeof(unsigned)));
+      TRY(cudaMemsetAsync(e->cq.count, 0, 20 * 32 * sizeof(unsigned), e->stream));
+      TRY(cudaMalloc(&e->cq.claim32, lattice * sizeof(unsigned)));
+      TRY(cudaMemsetAsync(e->cq.claim32, 0, lattice * sizeof(unsigned), e->stream));
+      TRY(cudaMalloc(&e->cq.persist, SWE_PERSIST_BYTES));
+      TRY(cudaMemsetAsync(e->cq.persist, 0, SWE_PERSIST_BYTES, e->stream));
+      e->cq.cap = qcap;
+    }
   }
   make_height_tensor_map(e->m, &e->tmap);   // optional: plain-load kernels are used when it fails
   preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe(); preload_noise(); preload_queue();
@@ -1030,7 +1079,16 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
   // world.hpp:38-44: reset the four track members of every cell
   if (int rc = erode_prologue(e)) return rc;
   // world.hpp:47-66: the particles
-  if (e->st.enabled) {
+  if (e->st.enabled && stripe_uses_colour_queues(e)) {
+    if (cycles > 0) {
+      if (int rc = colour_launch_persistent(e, cycles)) return rc;
+      // the kernel works on the owners' memory; bring this rank's ghost rows up to date for what follows
+      int nl = 0;
+      const unsigned q = stripe_exchange_begin(e, false, &nl);
+      stripe_exchange_end(e, q, &nl);
+      if (int rc = check_launch(e, "stripe halo refresh", nl)) return rc;
+    }
+  } else if (e->st.enabled) {
     if (cycles > 0) {
       if (int rc = stripe_erode_begin(e, cycles)) return rc;
       for (int r = 0; r < e->p.max_age + 2; r++)
@@ -1061,13 +1119,24 @@ int swe_stripe_group_erode(swe_engine** engines, int n, int cycles) {
     if (int rc = stripe_erode_check(engines[i], cycles, SWE_MODE_PARALLEL)) return rc;
     if (engines[i]->p.max_age != engines[0]->p.max_age) return fail(SWE_ERR_INVALID, "stripes disagree on max_age");
   }
+  const bool colour = stripe_uses_colour_queues(engines[0]);
+  for (int i = 0; i < n; i++)
+    if (stripe_uses_colour_queues(engines[i]) != colour) return fail(SWE_ERR_STATE, "stripes disagree on the schedule");
   for (int i = 0; i < n; i++) {
     if (int rc = bind(engines[i])) return rc;
     if (int rc = erode_prologue(engines[i])) return rc;
-    if (cycles > 0)
+    if (cycles > 0 && !colour)
       if (int rc = stripe_erode_begin(engines[i], cycles)) return rc;
   }
-  if (cycles > 0)
+  if (cycles > 0 && colour) {
+    // one persistent kernel per stripe, all resident together (they meet at the cross-stripe barrier), then
+    // one halo refresh
+    for (int i = 0; i < n; i++) {
+      if (int rc = bind(engines[i])) return rc;
+      if (int rc = colour_launch_persistent(engines[i], cycles)) return rc;
+    }
+    if (int rc = swe_stripe_group_sync_halos(engines, n)) return rc;
+  } else if (cycles > 0)
     for (int r = 0; r < engines[0]->p.max_age + 2; r++)
       for (int i = 0; i < n; i++) {
         if (int rc = bind(engines[i])) return rc;
@@ -1399,8 +1468,11 @@ int swe_hash_height(swe_engine* e, uint64_t* out) {
 int swe_stripe_export(swe_engine* e, swe_stripe_link* out) {
   if (!e || !out) return fail(SWE_ERR_INVALID, "NULL argument");
   if (!e->st.enabled) return fail(SWE_ERR_STATE, "not a stripe engine");
+  std::memset(out, 0, sizeof *out);
   out->height = e->m.height; out->stamp = e->d_stamp; out->arena = e->st.arena;
   out->x0 = e->m.x0; out->inbox_capacity = e->st.inbox_capacity;
+  out->queue_a = e->cq.a; out->queue_b = e->cq.b; out->queue_count = e->cq.count; out->persist = e->cq.persist;
+  out->queue_cap = e->cq.cap;
   return SWE_OK;
 }
 
@@ -1410,13 +1482,17 @@ int swe_stripe_export_ipc(swe_engine* e, void* buf, size_t buf_bytes) {
   if (!buf || buf_bytes < SWE_STRIPE_IPC_BYTES) return fail(SWE_ERR_INVALID, "buffer must hold SWE_STRIPE_IPC_BYTES");
   unsigned char* b = static_cast<unsigned char*>(buf);
   std::memset(b, 0, SWE_STRIPE_IPC_BYTES);
-  cudaIpcMemHandle_t h[3];
+  cudaIpcMemHandle_t h[7];
   SWE_CUDA(cudaIpcGetMemHandle(&h[0], e->m.height));
   SWE_CUDA(cudaIpcGetMemHandle(&h[1], e->d_stamp));
   SWE_CUDA(cudaIpcGetMemHandle(&h[2], e->st.arena));
-  static_assert(3 * sizeof(cudaIpcMemHandle_t) + 2 * sizeof(int) <= SWE_STRIPE_IPC_BYTES, "ipc blob size");
+  SWE_CUDA(cudaIpcGetMemHandle(&h[3], e->cq.a));
+  SWE_CUDA(cudaIpcGetMemHandle(&h[4], e->cq.b));
+  SWE_CUDA(cudaIpcGetMemHandle(&h[5], e->cq.count));
+  SWE_CUDA(cudaIpcGetMemHandle(&h[6], e->cq.persist));
+  static_assert(7 * sizeof(cudaIpcMemHandle_t) + 3 * sizeof(int) <= SWE_STRIPE_IPC_BYTES, "ipc blob size");
   std::memcpy(b, h, sizeof h);
-  const int meta[2] = {e->m.x0, e->st.inbox_capacity};
+  const int meta[3] = {e->m.x0, e->st.inbox_capacity, e->cq.cap};
   std::memcpy(b + sizeof h, meta, sizeof meta);
   return SWE_OK;
 }
@@ -1425,17 +1501,19 @@ int swe_stripe_open_ipc(swe_engine* e, const void* buf, size_t buf_bytes, swe_st
   if (int rc = bind(e)) return rc;
   if (!buf || !out || buf_bytes < SWE_STRIPE_IPC_BYTES) return fail(SWE_ERR_INVALID, "bad ipc blob");
   const unsigned char* b = static_cast<const unsigned char*>(buf);
-  cudaIpcMemHandle_t h[3];
+  cudaIpcMemHandle_t h[7];
   std::memcpy(h, b, sizeof h);
-  int meta[2];
+  int meta[3];
   std::memcpy(meta, b + sizeof h, sizeof meta);
-  void* ptr[3] = {nullptr, nullptr, nullptr};
-  for (int i = 0; i < 3; i++) {
+  void* ptr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 7; i++) {
     SWE_CUDA(cudaIpcOpenMemHandle(&ptr[i], h[i], cudaIpcMemLazyEnablePeerAccess));
     e->st.ipc_opened.push_back(ptr[i]);
   }
+  std::memset(out, 0, sizeof *out);
   out->height = ptr[0]; out->stamp = ptr[1]; out->arena = ptr[2];
-  out->x0 = meta[0]; out->inbox_capacity = meta[1];
+  out->queue_a = ptr[3]; out->queue_b = ptr[4]; out->queue_count = ptr[5]; out->persist = ptr[6];
+  out->x0 = meta[0]; out->inbox_capacity = meta[1]; out->queue_cap = meta[2];
   return SWE_OK;
 }
 
@@ -1454,6 +1532,29 @@ int swe_stripe_connect(swe_engine* e, const swe_stripe_link* below, const swe_st
   if (below) S.below = *below;
   if (above) S.above = *above;
   S.connected = true;
+  return SWE_OK;
+}
+
+int swe_stripe_connect_ring(swe_engine* e, int rank, int n, const swe_stripe_link* links, int colocated) {
+  if (int rc = bind(e)) return rc;
+  if (!e->st.enabled) return fail(SWE_ERR_STATE, "not a stripe engine");
+  if (!links || n < 1 || n > SWE_MAX_STRIPE_RANKS || rank < 0 || rank >= n)
+    return fail(SWE_ERR_INVALID, "need the links of all n <= %d ranks and 0 <= rank < n", SWE_MAX_STRIPE_RANKS);
+  if (colocated < 1) return fail(SWE_ERR_INVALID, "colocated must be >= 1");
+  if (int rc = swe_stripe_connect(e, rank > 0 ? &links[rank - 1] : nullptr, rank + 1 < n ? &links[rank + 1] : nullptr)) return rc;
+  auto& S = e->st;
+  for (int i = 0; i < n; i++) {
+    if (i == rank) { S.mailboxes[i] = e->cq.persist; continue; }
+    if (!links[i].persist) return fail(SWE_ERR_INVALID, "link %d carries no barrier block", i);
+    S.mailboxes[i] = links[i].persist;
+  }
+  for (const swe_stripe_link* l : {rank > 0 ? &links[rank - 1] : nullptr, rank + 1 < n ? &links[rank + 1] : nullptr})
+    if (l && (!l->queue_a || !l->queue_b || !l->queue_count || l->queue_cap < 1))
+      return fail(SWE_ERR_INVALID, "neighbour link carries no particle queues");
+  S.rank = rank; S.nranks = n; S.colocated = colocated;
+  S.persist_blocks_per_sm = colour_persistent_blocks_per_sm_stripe();
+  (void)cudaGetLastError();
+  S.ring = true;
   return SWE_OK;
 }
 

@@ -197,10 +197,26 @@ struct MicroRoundArgs {
 void launch_colour_round(const MapView& m, const swe_params& p, const ColourQueues& cq, const MicroRoundArgs& r,
                          uint64_t seed, uint32_t call, const CallCtl* ctl, DevStats* stats, cudaStream_t st, bool pdl,
                          int grid_blocks);
+// Stripe context of the persistent kernel: the neighbours' height planes and colour queues and every rank's
+// barrier mailbox, as device pointers valid on this GPU (peer mappings).
+struct StripeQueues {
+  int own_lo, own_hi;                  // global rows this rank owns
+  int rank, nranks;
+  float* below_h; int below_x0;        // neighbour's height plane and the global row of its first stored row
+  float* above_h; int above_x0;
+  float4* below_a; float4* below_b; unsigned* below_count; int below_cap;
+  float4* above_a; float4* above_b; unsigned* above_count; int above_cap;
+  unsigned long long* mailbox[8];      // [rank] -> that rank's mailbox: slot (parity * 8 + source rank), 128 B apart
+};
+constexpr int SWE_MAX_STRIPE_RANKS = 8;
+constexpr size_t SWE_PERSIST_BYTES = 4096;        // PersistCtl at 0, barrier mailbox at 1024
+constexpr size_t SWE_MAILBOX_OFFSET = 1024;
 int colour_persistent_blocks_per_sm(bool layered);
+int colour_persistent_blocks_per_sm_stripe();
 cudaError_t launch_colour_persistent(const MapView& m, const swe_params& p, const ColourQueues& cq, int n_total,
                                      unsigned stagger, unsigned max_micro, uint64_t seed, uint32_t call,
-                                     DevStats* stats, cudaStream_t st, int grid_blocks);
+                                     DevStats* stats, cudaStream_t st, int grid_blocks, const StripeQueues* stripe = nullptr,
+                                     bool cooperative = true);
 void preload_queue();
 
 // stripe exchange primitives: swe_stripe.cu

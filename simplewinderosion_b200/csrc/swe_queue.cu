@@ -318,8 +318,9 @@ struct PersistCtl {
   unsigned tag_base;            // claim tags used so far (monotonic across calls)
   unsigned micro;               // micro-rounds of the last call (output)
   unsigned error;               // 1 = barrier watchdog fired, 2 = micro-round cap reached with particles alive
+  unsigned long long xseq;      // stripes: micro-rounds run so far = sequence number of the cross-GPU barrier (same on every rank)
 };
-static_assert(sizeof(PersistCtl) == 272, "PersistCtl layout (swe_api.cu reads it back)");
+static_assert(sizeof(PersistCtl) == 280, "PersistCtl layout (swe_api.cu reads it back)");
 
 __device__ __forceinline__ unsigned long long atom_add_acqrel_u64(unsigned long long* p, unsigned long long v) {
   unsigned long long old;
@@ -391,6 +392,31 @@ __device__ __forceinline__ unsigned atom_max_l2(unsigned* a, unsigned v, unsigne
 #endif
 }
 
+// ---- multi-GPU row stripes ---------------------------------------------------------------------------------
+// Every rank runs the same micro-round sequence; the grid barrier of a stripe kernel extends over all ranks
+// (mailbox words written into every rank's memory over NVLink, system-scope release/acquire), so the colouring
+// holds GLOBALLY: a particle in a stripe's first or last row reads and writes the neighbour's rows of its 3x3
+// block directly in the neighbour's memory (peer loads / stores) with the same exclusive ownership as inside
+// one GPU -- no ghost rows, no halo exchange, and the result has the single-GPU semantics. A particle whose
+// next cell lies in a neighbour's rows is appended to the neighbour's colour queue (system-scope atomic for
+// the slot, peer stores for the record).
+__device__ __forceinline__ float ld_peer(const float* a) {
+  float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void st_peer(float* a, float v) {
+  asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_h(const float* a, bool remote, unsigned long long pol) { return remote ? ld_peer(a) : ld_l2(a, pol); }
+__device__ __forceinline__ void st_h(float* a, float v, bool remote, unsigned long long pol) { if (remote) st_peer(a, v); else st_l2(a, v, pol); }
+
 __device__ __forceinline__ unsigned pin_mask(unsigned k) {
   // colour c has been served floor((k - c + 8) / 9) times before micro-round k
   unsigned pin = 0u;
@@ -402,11 +428,11 @@ __device__ __forceinline__ unsigned pin_mask(unsigned k) {
 #ifndef SWE_PERSIST_BLOCKS
 #define SWE_PERSIST_BLOCKS 4   // resident 256-thread blocks per SM the register budget is tuned for (63 registers, no spills)
 #endif
-template <bool LAYERED>
+template <bool LAYERED, bool STRIPE>
 __global__ void __launch_bounds__(256, SWE_PERSIST_BLOCKS)
 colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsigned* __restrict__ claim, uint2 key,
                          uint32_t call, int n_total, unsigned stagger, unsigned max_micro, PersistCtl* ctl,
-                         DevStats* stats) {
+                         DevStats* stats, const StripeQueues S) {
   __shared__ unsigned s_cnt[18], s_base[18];
   __shared__ unsigned s_stat[4];
   __shared__ float s_lost;
@@ -419,6 +445,8 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
   if (tid == 0) s_rel = ld_relaxed_u64(&ctl->release);
   __syncthreads();
   const unsigned tag0 = *reinterpret_cast<volatile unsigned*>(&ctl->tag_base);   // stable until the final barrier
+  const unsigned long long xseq0 = STRIPE ? *reinterpret_cast<volatile unsigned long long*>(&ctl->xseq) : 0ull;
+  const int lat0 = m.x0 / 3;                               // first lattice row of the local claim table
   unsigned long long rel = s_rel;
   unsigned n_steps = 0, n_oob = 0, n_age = 0, n_new = 0;
   float lost = 0.0f;
@@ -453,15 +481,22 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
         const bool xm = ix > 0, xp = ix + 1 < m.nx, zm = iz > 0, zp = iz + 1 < nz;
         const unsigned valid = (xm && zm ? 1u : 0u) | (xm ? 2u : 0u) | (xm && zp ? 4u : 0u) | (zm ? 8u : 0u) |
                                (zp ? 16u : 0u) | (xp && zm ? 32u : 0u) | (xp ? 64u : 0u) | (xp && zp ? 128u : 0u);
+        // rows of the 3x3 block: a stripe reads / writes a neighbour's row in the neighbour's memory
+        const bool rem_m = STRIPE && xm && ix - 1 < S.own_lo, rem_p = STRIPE && xp && ix + 1 >= S.own_hi;
+        float* row_m = rem_m ? S.below_h + (size_t)(ix - 1 - S.below_x0) * (size_t)nz + iz : hp - nz;
+        float* row_p = rem_p ? S.above_h + (size_t)(ix + 1 - S.above_x0) * (size_t)nz + iz : hp + nz;
         // one claim word per 3x3 lattice cell: the cells of the served colour map one-to-one onto it, the tags
         // grow with every micro-round, so the table (1/9 of a plane: L2-resident) serves all colours.
         // The block is loaded while the claim is in flight (harmless if the claim is lost).
-        const unsigned seen = atom_max_l2(claim + (size_t)(ix / 3) * (size_t)claim_pitch + (size_t)(iz / 3), tag, keep);
+        const unsigned seen = atom_max_l2(claim + (size_t)(ix / 3 - lat0) * (size_t)claim_pitch + (size_t)(iz / 3), tag, keep);
         float h[8];
         const float hc = ld_l2(hp, keep);
 #pragma unroll
-        for (int q8 = 0; q8 < 8; q8++)
-          h[q8] = ((valid >> q8) & 1u) ? ld_l2(hp + block::slot_dx(q8) * nz + block::slot_dz(q8), keep) : hc;
+        for (int q8 = 0; q8 < 8; q8++) {
+          const int dx = block::slot_dx(q8), dz = block::slot_dz(q8);
+          const float* src = dx < 0 ? row_m + dz : (dx > 0 ? row_p + dz : hp + dz);
+          h[q8] = ((valid >> q8) & 1u) ? ld_h(src, dx < 0 ? rem_m : (dx > 0 ? rem_p : false), keep) : hc;
+        }
         if (seen >= tag) {
           target = (int)(tin ^ 1u);                        // the cell is taken: wait for the colour's next turn
         } else {
@@ -495,7 +530,11 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
           if (moved != 0u || dh != 0.0f) st_l2(hp, c1, keep);
 #pragma unroll
           for (int i = 0; i < 8; i++)
-            if ((moved >> i) & 1u) st_l2(hp + block::slot_dx(s[i]) * nz + block::slot_dz(s[i]), v[i], keep);
+            if ((moved >> i) & 1u) {
+              const int dx = block::slot_dx(s[i]), dz = block::slot_dz(s[i]);
+              float* dst = dx < 0 ? row_m + dz : (dx > 0 ? row_p + dz : hp + dz);
+              st_h(dst, v[i], dx < 0 ? rem_m : (dx > 0 ? rem_p : false), keep);
+            }
           n_steps++;
           ra = make_float4(q.px, q.py, q.pz, q.sed);
           rb = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
@@ -505,6 +544,22 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
           else {
             const unsigned cn = (unsigned)cell_colour(jx, jz);
             target = (int)(cn * 2u + (((pin >> cn) & 1u) ^ (cn == colour ? 1u : 0u)));
+            if (STRIPE && (jx < S.own_lo || jx >= S.own_hi)) {
+              // hand the particle to the owner of its next cell: append to the neighbour's queue of that colour
+              const bool dn = jx < S.own_lo;
+              unsigned* pc = (dn ? S.below_count : S.above_count) + target * 32;
+              const int pcap = dn ? S.below_cap : S.above_cap;
+              const unsigned slot = atomicAdd_system(pc, 1u);
+              if (slot < (unsigned)pcap) {
+                const size_t o = (size_t)target * (size_t)pcap + slot;
+                (dn ? S.below_a : S.above_a)[o] = ra;
+                (dn ? S.below_b : S.above_b)[o] = rb;
+              } else {
+                atomicAdd(Q.dropped, 1u);
+                lost += ra.w; n_age++; delta--;
+              }
+              target = -1;                                 // (the global live count is the sum over the ranks)
+            }
           }
         }
       } else if (j < total) {
@@ -513,13 +568,18 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
         spawn_position_iid(id, m.nx, m.nz, key, call, px, pz);
         ra = make_float4(px, 0.0f, pz, 0.0f);
         rb = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
-        n_new++;
         const int jx = __float2int_rd(px + 0.5f), jz = __float2int_rd(pz + 0.5f);
-        if (m.oob(jx, jz)) n_oob++;
-        else {
-          delta++;
-          const unsigned cn = (unsigned)cell_colour(jx, jz);
-          target = (int)(cn * 2u + (((pin >> cn) & 1u) ^ (cn == colour ? 1u : 0u)));
+        // a stripe materialises the particles whose first cell lies in its rows (every rank evaluates the whole
+        // injection list of the micro-round; a cell beyond the last row belongs to the last rank)
+        const bool mine = !STRIPE || (jx >= S.own_lo && (jx < S.own_hi || S.own_hi == m.nx));
+        if (mine) {
+          n_new++;
+          if (m.oob(jx, jz)) n_oob++;
+          else {
+            delta++;
+            const unsigned cn = (unsigned)cell_colour(jx, jz);
+            target = (int)(cn * 2u + (((pin >> cn) & 1u) ^ (cn == colour ? 1u : 0u)));
+          }
         }
       }
       const unsigned has = __ballot_sync(0xffffffffu, target >= 0);
@@ -533,7 +593,8 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
         rank = wb + (unsigned)__popc(grp & ((1u << lane) - 1u));
       }
       __syncthreads();
-      if (tid < 18 && s_cnt[tid] != 0u) s_base[tid] = atomicAdd(Q.count + tid * 32, s_cnt[tid]);
+      if (tid < 18 && s_cnt[tid] != 0u)
+        s_base[tid] = STRIPE ? atomicAdd_system(Q.count + tid * 32, s_cnt[tid]) : atomicAdd(Q.count + tid * 32, s_cnt[tid]);
       __syncthreads();
       if (target >= 0) {
         const unsigned slot = s_base[target] + rank;
@@ -558,17 +619,40 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
       // to whoever acquires the arrival word; acquire: the last block sees everybody else's
       const unsigned long long old = atom_add_acqrel_u64(&ctl->arrive, 1ull + ((unsigned long long)(long long)d << 32));
       if ((unsigned)(old & 0xffffffffull) == gridDim.x - 1u) {
-        const int live = ctl->live + (int)(unsigned)((old + ((unsigned long long)(long long)d << 32)) >> 32);
+        int live = ctl->live + (int)(unsigned)((old + ((unsigned long long)(long long)d << 32)) >> 32);
         ctl->live = live;
         ctl->arrive = 0ull;
         Q.count[tin * 32u] = 0u;                           // the served queue is empty again
         const unsigned kn = k + 1u;
+        bool timed_out = false;
+        if (STRIPE) {
+          // cross-GPU barrier: publish (sequence number, local live count) into every rank's mailbox, wait for all
+          // ranks' words of this micro-round (two slots per rank by parity: a rank can be one barrier ahead)
+          const unsigned long long seq = xseq0 + (unsigned long long)kn;
+          const unsigned long long word = (seq << 32) | (unsigned long long)(unsigned)live;
+          const int par = (int)(seq & 1ull);
+          __threadfence_system();
+          for (int i = 0; i < S.nranks; i++) st_release_sys_u64(S.mailbox[i] + (par * 8 + S.rank) * 16, word);
+          int total = 0;
+          const long long t0 = clock64();
+          for (int i = 0; i < S.nranks && !timed_out; i++) {
+            unsigned long long w;
+            unsigned spins = 0;
+            while (((w = ld_acquire_sys_u64(S.mailbox[S.rank] + (par * 8 + i) * 16)) >> 32) != (seq & 0xffffffffull)) {
+              __nanosleep(60);
+              if ((++spins & 1023u) == 0u && clock64() - t0 > 16000000000LL) { timed_out = true; break; }   // ~8 s
+            }
+            total += (int)(unsigned)(w & 0xffffffffull);
+          }
+          live = total;
+        }
         const unsigned cn = kn % 9u;
         const unsigned tn = cn * 2u + ((pin_mask(kn) >> cn) & 1u);
         const unsigned next_n = tn == tin ? 0u : min(__ldcg(Q.count + tn * 32u), (unsigned)Q.cap);
         unsigned done = (live == 0 && kn >= stagger) ? 1u : 0u;
         if (!done && kn >= max_micro) { done = 1u; ctl->error = 2u; }
-        if (done) { ctl->micro = kn; ctl->tag_base = tag0 + kn + 2u; }
+        if (timed_out) { done = 1u; ctl->error = 1u; }
+        if (done) { ctl->micro = kn; ctl->tag_base = tag0 + kn + 2u; if (STRIPE) ctl->xseq = xseq0 + (unsigned long long)kn; }
         const unsigned long long gen = (rel >> 34) + 1ull;
         rel = (gen << 34) | ((unsigned long long)done << 32) | (unsigned long long)next_n;
         st_release_u64(&ctl->release, rel);
@@ -621,14 +705,21 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
 int colour_persistent_blocks_per_sm(bool layered) {
   int n = 0;
   const cudaError_t err = layered
-      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<true>, 256, 0)
-      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<false>, 256, 0);
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<true, false>, 256, 0)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<false, false>, 256, 0);
+  return err == cudaSuccess ? n : 0;
+}
+
+int colour_persistent_blocks_per_sm_stripe() {
+  int n = 0;
+  const cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<false, true>, 256, 0);
   return err == cudaSuccess ? n : 0;
 }
 
 cudaError_t launch_colour_persistent(const MapView& m, const swe_params& p, const ColourQueues& cq, int n_total,
                                      unsigned stagger, unsigned max_micro, uint64_t seed, uint32_t call,
-                                     DevStats* stats, cudaStream_t st, int grid_blocks) {
+                                     DevStats* stats, cudaStream_t st, int grid_blocks, const StripeQueues* stripe,
+                                     bool cooperative) {
   uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   block::Thr T;
   T.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;
@@ -641,9 +732,15 @@ cudaError_t launch_colour_persistent(const MapView& m, const swe_params& p, cons
   ParConst C = make_const(p);
   unsigned* claim = cq.claim32;
   PersistCtl* ctl = reinterpret_cast<PersistCtl*>(cq.persist);
-  void* args[] = {&mv, &C, &T, &Q, &claim, &key, &call, &n_total, &stagger, &max_micro, &ctl, &stats};
-  const void* fn = m.rock ? reinterpret_cast<const void*>(&colour_persistent_kernel<true>)
-                          : reinterpret_cast<const void*>(&colour_persistent_kernel<false>);
+  StripeQueues sq{};
+  if (stripe) sq = *stripe;
+  void* args[] = {&mv, &C, &T, &Q, &claim, &key, &call, &n_total, &stagger, &max_micro, &ctl, &stats, &sq};
+  const void* fn = stripe ? reinterpret_cast<const void*>(&colour_persistent_kernel<false, true>)
+                 : m.rock ? reinterpret_cast<const void*>(&colour_persistent_kernel<true, false>)
+                          : reinterpret_cast<const void*>(&colour_persistent_kernel<false, false>);
+  // several logical stripes on ONE GPU (tests): their kernels must run side by side, which plain launches of
+  // grids sized to a share of the device do; a cooperative launch is what guarantees co-residency otherwise
+  if (!cooperative) return cudaLaunchKernel(fn, dim3(grid_blocks), dim3(256), args, 0, st);
   return cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(256), args, 0, st);
 }
 
@@ -673,8 +770,9 @@ void preload_queue() {
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, colour_round_kernel<false>);
   cudaFuncGetAttributes(&a, colour_round_kernel<true>);
-  cudaFuncGetAttributes(&a, colour_persistent_kernel<false>);
-  cudaFuncGetAttributes(&a, colour_persistent_kernel<true>);
+  cudaFuncGetAttributes(&a, colour_persistent_kernel<false, false>);
+  cudaFuncGetAttributes(&a, colour_persistent_kernel<true, false>);
+  cudaFuncGetAttributes(&a, colour_persistent_kernel<false, true>);
 }
 
 }  // namespace swe

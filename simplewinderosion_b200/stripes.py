@@ -121,12 +121,20 @@ class StripedWorld(_world.World):
         check(lib.swe_stripe_connect(self._h, C.byref(below) if below is not None else None,
                                      C.byref(above) if above is not None else None))
 
+    def connect_ring(self, links: list[StripeLink], colocated: int = 1) -> None:
+        """Neighbour wiring plus every rank's barrier mailbox: enables the colour-queue schedule on stripes."""
+        arr = (StripeLink * len(links))(*links)
+        check(lib.swe_stripe_connect_ring(self._h, self.rank, len(links), arr, int(colocated)))
+
     @staticmethod
-    def connect_in_process(worlds: list["StripedWorld"]) -> None:
+    def connect_in_process(worlds: list["StripedWorld"], ring: bool = True) -> None:
         """All stripes live in this process (several logical stripes on one or more GPUs)."""
         links = [w.export_link() for w in worlds]
         for r, w in enumerate(worlds):
-            w.connect_links(links[r - 1] if r > 0 else None, links[r + 1] if r + 1 < len(worlds) else None)
+            if ring and len(worlds) <= 8:
+                w.connect_ring(links, colocated=sum(1 for o in worlds if o.device == w.device))
+            else:
+                w.connect_links(links[r - 1] if r > 0 else None, links[r + 1] if r + 1 < len(worlds) else None)
 
     def connect(self, group=None) -> None:
         """One process per GPU: exchange CUDA IPC handles through torch.distributed (collective)."""
@@ -134,14 +142,26 @@ class StripedWorld(_world.World):
         blob = (C.c_ubyte * STRIPE_IPC_BYTES)()
         check(lib.swe_stripe_export_ipc(self._h, blob, STRIPE_IPC_BYTES))
         gathered = allgather_bytes(bytes(blob), self.world_size, group, self.device)
-        links = {}
-        for nb in (self.rank - 1, self.rank + 1):
-            if 0 <= nb < self.world_size:
-                buf = (C.c_ubyte * STRIPE_IPC_BYTES).from_buffer_copy(gathered[nb])
+        if self.world_size <= 8:
+            # every rank's buffers are mapped: the neighbours' for halos / hand-off / peer block access, everybody's
+            # barrier mailbox for the cross-GPU grid barrier of the colour-queue kernels
+            links = []
+            for r in range(self.world_size):
                 link = StripeLink()
-                check(lib.swe_stripe_open_ipc(self._h, buf, STRIPE_IPC_BYTES, C.byref(link)))
-                links[nb] = link
-        self.connect_links(links.get(self.rank - 1), links.get(self.rank + 1))
+                if r != self.rank:
+                    buf = (C.c_ubyte * STRIPE_IPC_BYTES).from_buffer_copy(gathered[r])
+                    check(lib.swe_stripe_open_ipc(self._h, buf, STRIPE_IPC_BYTES, C.byref(link)))
+                links.append(link)
+            self.connect_ring(links)
+        else:
+            links = {}
+            for nb in (self.rank - 1, self.rank + 1):
+                if 0 <= nb < self.world_size:
+                    buf = (C.c_ubyte * STRIPE_IPC_BYTES).from_buffer_copy(gathered[nb])
+                    link = StripeLink()
+                    check(lib.swe_stripe_open_ipc(self._h, buf, STRIPE_IPC_BYTES, C.byref(link)))
+                    links[nb] = link
+            self.connect_links(links.get(self.rank - 1), links.get(self.rank + 1))
         dist.barrier(group=group)
 
     # -- map transfer -------------------------------------------------------------------------------

@@ -27,9 +27,9 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-def make_stripes(nx, nz, world, max_particles, hm):
+def make_stripes(nx, nz, world, max_particles, hm, ring=True):
     ws = [stripes.StripedWorld(nx, nz, r, world, max_particles) for r in range(world)]
-    stripes.StripedWorld.connect_in_process(ws)
+    stripes.StripedWorld.connect_in_process(ws, ring=ring)
     for w in ws:
         w.upload_global(hm)
     g = stripes.StripeGroup(ws)
@@ -53,19 +53,24 @@ def test_striped_cascade_sweep_bitwise(nx, nz, world):
     assert all(s.stripe_overflow == 0 for s in g.stats())
 
 
-@pytest.mark.parametrize("n,world,cycles", [(128, 2, 4096), (256, 4, 16384)])
-def test_striped_erode_accounts_for_every_particle(n, world, cycles):
+@pytest.mark.parametrize("n,world,cycles,ring", [(128, 2, 4096, True), (256, 4, 16384, True), (128, 2, 4096, False),
+                                                 (256, 4, 16384, False)])
+def test_striped_erode_accounts_for_every_particle(n, world, cycles, ring):
+    """ring = True: colour-queue schedule on stripes (one persistent kernel per stripe, barrier across the stripes,
+    boundary blocks read/written in the neighbour's memory); ring = False: round 1's lock-step schedule with halo
+    exchange per round. Compared with a single engine running the same schedule."""
     hm = generate.gaussian_hill(n)
-    g = make_stripes(n, n, world, cycles, hm)
+    g = make_stripes(n, n, world, cycles, hm, ring=ring)
     ws = g.worlds
     for w in ws:
         w.srand(7)
+    sched = swe.SCHEDULE_COLOUR_QUEUES if ring else swe.SCHEDULE_LOCKSTEP
     single = swe.World(n)
-    single.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_LOCKSTEP)   # the stripe engines run the lock-step schedule
+    single.set_option(swe.OPT_SCHEDULE, sched)
     single.upload(hm)
     single.srand(7)
     other = swe.World(n)          # same engine, another seed: how much two runs differ anyway
-    other.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_LOCKSTEP)
+    other.set_option(swe.OPT_SCHEDULE, sched)
     other.upload(hm)
     other.srand(8)
     s0 = float(hm.astype(np.float64).sum())
@@ -79,6 +84,9 @@ def test_striped_erode_accounts_for_every_particle(n, world, cycles):
     assert sum(s.exits_oob + s.exits_age for s in sts) == 2 * cycles
     steps = sum(s.steps for s in sts)
     ss = single.stats()
+    if ring:
+        assert all(s.last_micro_rounds == sts[0].last_micro_rounds > 0 for s in sts)   # one global micro-round sequence
+        assert sum(s.queue_dropped for s in sts) == 0
     assert abs(steps / ss.steps - 1.0) < 0.01
     lost = sum(s.sediment_lost for s in sts)
     total = sum(w.sum_plane() for w in ws)
