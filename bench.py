@@ -371,6 +371,70 @@ def layered_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> d
     return out
 
 
+def cfg4_strong(swe, rank: int, world: int, device: int, barrier, max_over_ranks, sum_over_ranks) -> dict:
+    """BASELINE.json configs[3]: a 16384 x 16384 map row-tiled over the GPUs, 16,777,216 particles per World::erode
+    (0.0625 per cell), generated on the GPUs (map::init's noise layers, collective normalisation). With N > 1 rank 0
+    also times the SAME call on its single GPU, so that the strong-scaling speed-up is measured inside one run."""
+    import torch
+    n, particles, steps = 16384, 1 << 24, 2
+
+    def timed(w):
+        w.srand(1)
+        w.erode(particles, swe.MODE_PARALLEL)          # warm-up
+        w.sync()
+        s0 = w.stats().steps
+        stream = torch.cuda.Stream()
+        w.set_stream(stream.cuda_stream)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        return s0, stream, ev0, ev1
+
+    one = None
+    if rank == 0:
+        w1 = swe.World(n, device=device)
+        w1.generate_noise(1, 8); w1.normalize()
+        s0, stream, ev0, ev1 = timed(w1)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(steps):
+                w1.erode(particles, swe.MODE_PARALLEL)
+            ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        one = {"value": (w1.stats().steps - s0) / (ms * 1e-3), "ms_per_step": ms / steps}
+        w1.close()
+    out = {"workload": f"cfg4: {n}x{n} FBm dune field, {particles} particles per World::erode (0.0625 per cell), "
+                       f"colour-queue schedule, {steps} timed calls after 1 warm-up",
+           "unit": UNIT, "n_gpus": world}
+    if world == 1:
+        out.update(one)
+        return out
+    from simplewinderosion_b200 import stripes
+    barrier()
+    w = stripes.StripedWorld(n, n, rank, world, particles, device=device)
+    w.connect()
+    w.generate_noise(1, 8)
+    w.normalize_collective()
+    w.sync_halos()
+    s0, stream, ev0, ev1 = timed(w)
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            w.erode(particles, swe.MODE_PARALLEL)
+        ev1.record(stream)
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    st = w.stats()
+    total = sum_over_ranks(float(st.steps - s0))
+    dropped = sum_over_ranks(float(st.queue_dropped + st.stripe_overflow))
+    w.close()
+    out.update({"value": total / (ms * 1e-3), "ms_per_step": ms / steps, "dropped_particles": int(dropped)})
+    if rank == 0:
+        out["one_gpu_same_run"] = one
+        out["speedup_vs_1gpu"] = out["value"] / one["value"]
+    return out
+
+
 def lockstep_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> dict:
     """Round 1's schedule (SWE_OPT_SCHEDULE = 1): every particle of the call steps once per round, then one
     stamped cascade over the touched cells. Timed beside the headline because it is what round 1 reported;
@@ -459,6 +523,24 @@ def run_ours(args) -> None:
         w.upload(hm)
     if world > 1:
         w.sync_halos()
+    stripe_check = None
+    if world > 1:
+        # the real-peer bitwise check (the 1-GPU test box skips tests/test_gpu_stripes.py::test_real_multi_gpu): three
+        # striped whole-map cascade sweeps against a single engine sweeping the same global map on this GPU
+        gmap = hm if args.strong else np.concatenate([hm] * world, axis=0)
+        ref = swe.World(gmap.shape[0], n, device=local)
+        ref.upload(gmap)
+        ref.cascade_sweep(3)
+        w.cascade_sweep(3)
+        lo, hi = w.bounds[rank]
+        same = bool(np.array_equal(w.download().view(np.uint32), ref.download()[lo:hi].view(np.uint32)))
+        ref.close()
+        stripe_check = "bitwise" if sum_over_ranks(0.0 if same else 1.0) == 0.0 else "MISMATCH"
+        if args.strong:
+            w.upload_global(hm)
+        else:
+            w.upload(hm)
+        w.sync_halos()
     w.srand(1)
     # GLOBAL particle count of one World::erode call
     particles_call = particles if (world == 1 or args.strong) else particles * world
@@ -493,7 +575,7 @@ def run_ours(args) -> None:
 
     # device time of the particle phase (CUDA events on the launch stream around the flight kernel(s) of each
     # call, swe_stats.last_fly_ms): an extra pass outside the timed region, one stats read-back per call
-    lockstep = world > 1          # the stripe engines run round 1's lock-step schedule
+    lockstep = False              # stripes wired as a ring run the colour-queue schedule too
     if lockstep:
         w.set_option(swe.OPT_KERNEL_TIMING, 1)
     round_ms = casc_ms = fly_ms = erode_ms = 0.0
@@ -546,6 +628,11 @@ def run_ours(args) -> None:
         swe.lib.swe_host_free(p)
     w.close()
 
+    # ---- BASELINE cfg4: ONE 16384^2 map, 16,777,216 particles per call, cut into `world` row stripes (strong scaling)
+    cfg4 = None
+    if not args.skip_cfg4 and not args.strong and n == N_MAP:
+        cfg4 = cfg4_strong(swe, rank, world, local, barrier, max_over_ranks, sum_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -563,12 +650,15 @@ def run_ours(args) -> None:
             "parallelism": "single GPU" if world == 1 else
             f"{world} row stripes of a {n if args.strong else n * world}x{n} map ({rows_local} rows and "
             f"~{particles_call // world} particles per GPU), "
-            f"P2P halo push + particle hand-off kernels over NVLink",
+            f"one persistent colour-queue kernel per GPU; grid barrier across the GPUs every micro-round (mailbox words in peer "
+            f"memory over NVLink); 3x3 blocks on a stripe boundary are read and written in the neighbour's memory; particles "
+            f"crossing a boundary are appended to the neighbour's queue (system-scope atomics)",
             "stripe_overflow": int(overflow_total),
             **({} if world == 1 else {"exchange": {
-                "per_round_per_interior_rank_bytes": int((7 + 5) * n * 5),
-                "what": "7 boundary rows pushed down + 5 up, height (4 B) + stamp (1 B) per cell, by P2P store kernels; "
-                        "plus 36 B per particle handed to a neighbour's inbox", "rounds_per_step": 514}}),
+                "per_micro_round_per_rank_bytes": int(8 * world),
+                "what": "one 8-byte barrier word to every rank per micro-round; 32 B per particle handed to a neighbour's queue; "
+                        "4 B loads/stores of the neighbour's boundary rows by the particles standing next to them; "
+                        "one halo refresh (12 rows) per call", "micro_rounds_per_step": micro_rounds / max(1, args.steps)}}),
             "l2": "working set > 600 MiB per GPU (height 64 + track 256 + field 256 MiB + live particle records + claim lattice) "
                   "> 126 MB L2; no flush needed",
             "steps_per_particle": total_steps / max(1.0, total_particles),
@@ -601,6 +691,10 @@ def run_ours(args) -> None:
         f"colour queues: 9-colour micro-rounds, one particle per cell, in-register cascade, automatic stagger "
         f"({int(8 * particles / (n * n) * rounds_per_call + 0.5)} rounds); parity-green at this density "
         f"(tests/test_gpu_density.py)")
+    if world > 1:
+        line["stripe_check"] = stripe_check
+    if cfg4 is not None:
+        line["cfg4_strong"] = cfg4
     if world == 1:
         line["lockstep_all_at_once"] = lockstep_extra(swe, local, n, particles, hm, args.steps)
     if world == 1 and not args.skip_layered:
@@ -637,6 +731,7 @@ def main() -> None:
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cascade", action="store_true")
     ap.add_argument("--skip-layered", action="store_true")
+    ap.add_argument("--skip-cfg4", action="store_true", help="do not run the 16384^2 strong-scaling case (BASELINE cfg4)")
     ap.add_argument("--quick", action="store_true", help="shorter cascade relaxation")
     ap.add_argument("--strong", action="store_true",
                     help="N>1: cut ONE size x size map into N stripes (cfg4: --size 16384 --particles 16777216) "

@@ -532,7 +532,8 @@ int colour_finish(swe_engine* e, int cycles, int k_done, uint64_t particles_befo
 
 // one cooperative launch for the whole particle phase; fully asynchronous (the kernel ends itself)
 int colour_launch_persistent(swe_engine* e, int cycles) {
-  long long blocks = ((long long)cycles / 3 + 255) / 256 + 1;
+  const int nt = colour_persistent_threads();
+  long long blocks = ((long long)cycles / 3 + nt - 1) / nt + 1;
   const bool stripe = e->st.enabled;
   long long cap = stripe ? (long long)e->sm_count * e->st.persist_blocks_per_sm / (e->st.colocated > 0 ? e->st.colocated : 1)
                          : (long long)e->sm_count * e->persist_blocks_per_sm;

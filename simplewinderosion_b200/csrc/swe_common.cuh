@@ -213,6 +213,7 @@ constexpr size_t SWE_PERSIST_BYTES = 4096;        // PersistCtl at 0, barrier ma
 constexpr size_t SWE_MAILBOX_OFFSET = 1024;
 int colour_persistent_blocks_per_sm(bool layered);
 int colour_persistent_blocks_per_sm_stripe();
+int colour_persistent_threads();
 cudaError_t launch_colour_persistent(const MapView& m, const swe_params& p, const ColourQueues& cq, int n_total,
                                      unsigned stagger, unsigned max_micro, uint64_t seed, uint32_t call,
                                      DevStats* stats, cudaStream_t st, int grid_blocks, const StripeQueues* stripe = nullptr,

@@ -409,6 +409,9 @@ __device__ __forceinline__ void st_peer(float* a, float v) {
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -425,15 +428,33 @@ __device__ __forceinline__ unsigned pin_mask(unsigned k) {
   return pin;
 }
 
-#ifndef SWE_PERSIST_BLOCKS
-#define SWE_PERSIST_BLOCKS 4   // resident 256-thread blocks per SM the register budget is tuned for (63 registers, no spills)
+#ifndef SWE_PERSIST_THREADS
+#define SWE_PERSIST_THREADS 256   // threads per block of the persistent kernel
 #endif
+#ifndef SWE_PERSIST_BLOCKS
+#define SWE_PERSIST_BLOCKS (1024 / SWE_PERSIST_THREADS)   // resident blocks per SM the register budget is tuned for (<= 64 registers)
+#endif
+#ifndef SWE_WARP_APPEND
+#define SWE_WARP_APPEND 1         // queue appends reserved per warp (no block barrier inside a micro-round)
+#endif
+#ifndef SWE_PREFETCH
+#define SWE_PREFETCH 1            // blocks waiting at the grid barrier prefetch the next micro-round's heights into L2
+#endif
+constexpr unsigned PNT = SWE_PERSIST_THREADS;
+__device__ __forceinline__ void prefetch_l2_keep(const void* a) {
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a));
+}
+__device__ __forceinline__ void prefetch_l2(const void* a) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+}
 template <bool LAYERED, bool STRIPE>
-__global__ void __launch_bounds__(256, SWE_PERSIST_BLOCKS)
+__global__ void __launch_bounds__(SWE_PERSIST_THREADS, SWE_PERSIST_BLOCKS)
 colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsigned* __restrict__ claim, uint2 key,
                          uint32_t call, int n_total, unsigned stagger, unsigned max_micro, PersistCtl* ctl,
                          DevStats* stats, const StripeQueues S) {
+#if !SWE_WARP_APPEND
   __shared__ unsigned s_cnt[18], s_base[18];
+#endif
   __shared__ unsigned s_stat[4];
   __shared__ float s_lost;
   __shared__ unsigned long long s_rel;
@@ -466,9 +487,11 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
     const float4* qb = Q.b + (size_t)tin * (size_t)Q.cap;
     int delta = 0;                                        // particles this thread added to / removed from the queues
 
-    for (unsigned j0 = blockIdx.x * 256u; j0 < total; j0 += gridDim.x * 256u) {
+    for (unsigned j0 = blockIdx.x * PNT; j0 < total; j0 += gridDim.x * PNT) {
+#if !SWE_WARP_APPEND
       if (tid < 18) s_cnt[tid] = 0u;
       __syncthreads();
+#endif
       const unsigned j = j0 + (unsigned)tid;
       int target = -1;
       float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -583,6 +606,17 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
         }
       }
       const unsigned has = __ballot_sync(0xffffffffu, target >= 0);
+#if SWE_WARP_APPEND
+      if (target >= 0) {
+        // one reservation per warp and target queue: the lanes going to the same queue elect a leader
+        const unsigned grp = __match_any_sync(has, target);
+        const int leader = __ffs(grp) - 1;
+        unsigned wb = 0u;
+        if ((int)lane == leader)
+          wb = STRIPE ? atomicAdd_system(Q.count + target * 32, (unsigned)__popc(grp)) : atomicAdd(Q.count + target * 32, (unsigned)__popc(grp));
+        wb = __shfl_sync(grp, wb, leader);
+        const unsigned slot = wb + (unsigned)__popc(grp & ((1u << lane) - 1u));
+#else
       unsigned rank = 0u;
       if (target >= 0) {
         const unsigned grp = __match_any_sync(has, target);
@@ -598,6 +632,7 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
       __syncthreads();
       if (target >= 0) {
         const unsigned slot = s_base[target] + rank;
+#endif
         if (slot < (unsigned)Q.cap) {
           const size_t o = (size_t)target * (size_t)Q.cap + slot;
           Q.a[o] = ra;
@@ -631,15 +666,16 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
           const unsigned long long seq = xseq0 + (unsigned long long)kn;
           const unsigned long long word = (seq << 32) | (unsigned long long)(unsigned)live;
           const int par = (int)(seq & 1ull);
-          __threadfence_system();
-          for (int i = 0; i < S.nranks; i++) st_release_sys_u64(S.mailbox[i] + (par * 8 + S.rank) * 16, word);
+          // ONE system-scope fence orders everything this GPU wrote in the micro-round (observed through the
+          // arrival word) before the mailbox words; the words themselves are then plain system-scope stores
+          asm volatile("fence.acq_rel.sys;" ::: "memory");
+          for (int i = 0; i < S.nranks; i++) st_relaxed_sys_u64(S.mailbox[i] + (par * 8 + S.rank) * 16, word);
           int total = 0;
           const long long t0 = clock64();
           for (int i = 0; i < S.nranks && !timed_out; i++) {
             unsigned long long w;
             unsigned spins = 0;
             while (((w = ld_acquire_sys_u64(S.mailbox[S.rank] + (par * 8 + i) * 16)) >> 32) != (seq & 0xffffffffull)) {
-              __nanosleep(60);
               if ((++spins & 1023u) == 0u && clock64() - t0 > 16000000000LL) { timed_out = true; break; }   // ~8 s
             }
             total += (int)(unsigned)(w & 0xffffffffull);
@@ -671,6 +707,30 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
       }
       s_rel = rel;
     }
+#if SWE_PREFETCH
+    else if (tid >= 32) {
+      // a block that waits at the grid barrier pulls the heights its threads will need in the NEXT micro-round into
+      // L2 (the entries already in that queue; addresses only -- nothing is consumed, so a record that is still
+      // being written by a slower block is harmless)
+      const unsigned kn = k + 1u, cn = kn % 9u;
+      const unsigned tn = cn * 2u + ((pin_mask(kn) >> cn) & 1u);
+      const unsigned jn = blockIdx.x * PNT + (unsigned)tid;
+      if (jn < min(__ldcg(Q.count + tn * 32u), (unsigned)Q.cap)) {
+        const size_t o = (size_t)tn * (size_t)Q.cap + jn;
+        const float4 pa = __ldcg(Q.a + o);
+        prefetch_l2(Q.b + o);
+        const int ix = __float2int_rd(pa.x + 0.5f), iz = __float2int_rd(pa.z + 0.5f);
+        const int x_lo = STRIPE ? S.own_lo : 0, x_hi = STRIPE ? S.own_hi : m.nx;
+        if (ix >= x_lo && ix < x_hi && iz >= 0 && iz < nz) {
+          const float* hp = m.height + m.idx(ix, iz);
+          prefetch_l2_keep(hp);
+          if (ix - 1 >= x_lo) prefetch_l2_keep(hp - nz);
+          if (ix + 1 < x_hi) prefetch_l2_keep(hp + nz);
+          prefetch_l2(m.track + m.idx(ix, iz));
+        }
+      }
+    }
+#endif
     __syncthreads();
     rel = s_rel;
     n_in = (unsigned)(rel & 0xffffffffull);
@@ -705,14 +765,14 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
 int colour_persistent_blocks_per_sm(bool layered) {
   int n = 0;
   const cudaError_t err = layered
-      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<true, false>, 256, 0)
-      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<false, false>, 256, 0);
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<true, false>, SWE_PERSIST_THREADS, 0)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<false, false>, SWE_PERSIST_THREADS, 0);
   return err == cudaSuccess ? n : 0;
 }
 
 int colour_persistent_blocks_per_sm_stripe() {
   int n = 0;
-  const cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<false, true>, 256, 0);
+  const cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, colour_persistent_kernel<false, true>, SWE_PERSIST_THREADS, 0);
   return err == cudaSuccess ? n : 0;
 }
 
@@ -740,8 +800,8 @@ cudaError_t launch_colour_persistent(const MapView& m, const swe_params& p, cons
                           : reinterpret_cast<const void*>(&colour_persistent_kernel<false, false>);
   // several logical stripes on ONE GPU (tests): their kernels must run side by side, which plain launches of
   // grids sized to a share of the device do; a cooperative launch is what guarantees co-residency otherwise
-  if (!cooperative) return cudaLaunchKernel(fn, dim3(grid_blocks), dim3(256), args, 0, st);
-  return cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(256), args, 0, st);
+  if (!cooperative) return cudaLaunchKernel(fn, dim3(grid_blocks), dim3(SWE_PERSIST_THREADS), args, 0, st);
+  return cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(SWE_PERSIST_THREADS), args, 0, st);
 }
 
 void launch_colour_round(const MapView& m, const swe_params& p, const ColourQueues& cq, const MicroRoundArgs& r,
@@ -765,6 +825,8 @@ void launch_colour_round(const MapView& m, const swe_params& p, const ColourQueu
     launch_chain(colour_round_kernel<false>, dim3(grid_blocks), dim3(256), 0, st, pdl, m, make_const(p), T, Q, R, cq.claim, key,
                  call, ctl, stats);
 }
+
+int colour_persistent_threads() { return SWE_PERSIST_THREADS; }
 
 void preload_queue() {
   cudaFuncAttributes a;
