@@ -435,10 +435,10 @@ __device__ __forceinline__ unsigned pin_mask(unsigned k) {
 #define SWE_PERSIST_BLOCKS (1024 / SWE_PERSIST_THREADS)   // resident blocks per SM the register budget is tuned for (<= 64 registers)
 #endif
 #ifndef SWE_WARP_APPEND
-#define SWE_WARP_APPEND 1         // queue appends reserved per warp (no block barrier inside a micro-round)
+#define SWE_WARP_APPEND 0         // 1 = queue appends reserved per warp instead of per block (measured on B200: 1.5x SLOWER, the 18 counters become hot)
 #endif
 #ifndef SWE_PREFETCH
-#define SWE_PREFETCH 1            // blocks waiting at the grid barrier prefetch the next micro-round's heights into L2
+#define SWE_PREFETCH 0            // 1 = blocks waiting at the grid barrier prefetch the next micro-round's heights into L2 (measured on B200: 8 % SLOWER)
 #endif
 constexpr unsigned PNT = SWE_PERSIST_THREADS;
 __device__ __forceinline__ void prefetch_l2_keep(const void* a) {
