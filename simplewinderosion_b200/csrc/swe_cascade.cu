@@ -489,8 +489,17 @@ cascade_commit_kernel(MapView m, RowWindow win, const float* __restrict__ stage,
 //           World::cascade to a shared-memory queue (warp-aggregated append);
 //   relax : the queue is processed densely, one entry per thread.
 // On a map close to the repose angle only a few per cent of the centres reach the queue.
+#ifndef SWE_TILE_MIN_BLOCKS
+#define SWE_TILE_MIN_BLOCKS 3     // 40 registers, three 512-thread CTAs per SM: the per-colour barriers of one CTA hide behind the others
+#endif
+#ifndef SWE_TILE_DIRECT
+#define SWE_TILE_DIRECT 1         // dense-direct path (see cascade_tile_kernel)
+#endif
+#ifndef SWE_TILE_DIRECT_PCT
+#define SWE_TILE_DIRECT_PCT 45u   // moved centres (per cent) above which the next sweep of the tile runs dense-direct
+#endif
 template <bool USE_TMA>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+__global__ void __launch_bounds__(TILE_THREADS, SWE_TILE_MIN_BLOCKS)
 cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float settling, CascadeThr thr,
                     RowWindow win, TileScratch scratch) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -665,6 +674,38 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
   // queue fills beyond 3/4 falls back to the coarse test for its remaining colours.
   bool refined = true;
   unsigned relaxed = 0u, centres = 0u;
+  // DENSE-DIRECT: while more than ~45 % of a tile's centres move (the first tens of sweeps of a relaxation from
+  // noise) testing every centre first costs more than it saves: every thread relaxes its centres in place in the
+  // scan's stride-3 mapping -- no early-out test, no queue, no ballots or atomics, one barrier per colour instead
+  // of two, perfectly balanced; a centre that needs nothing runs the chain with every transfer predicated off
+  // (same result). The moved centres are counted so that the hint can fall back to the scan path.
+  const bool direct = SWE_TILE_DIRECT && interior && !generic_only && !m.rock && scratch.hint != nullptr && scratch.hint[tile_id] == 2;
+  if (direct) {
+    const Valid8 all = centre_valid<true>(1, 1, 3, 3);
+    unsigned mine = 0u;
+#pragma unroll 1
+    for (int c = 0; c < 9; c++) {
+      const int cxc = c / 3;
+      const int ncx = TILE_TX / 3 + 2 - cxc, ncz = TILE_TZ / 3 + 8 - c;
+      if (ty < TILE_BY && tx < ncz) {
+        const int lz = c + 1 + 3 * tx;
+#pragma unroll 1
+        for (int cxi = ty; cxi < ncx; cxi += TILE_BY) {
+          float* tc = tile + (cxc + 1 + 3 * cxi) * TILE_PITCH + lz;
+          const float before = tc[0];
+          centre_relax<true>(tc, thr, lut, settling, hs, all, 1, 1, 3, 3);
+          mine += (tc[0] != before) ? 1u : 0u;    // (a transfer that ran without changing the centre in fp32 does not count)
+        }
+      }
+      centres += (unsigned)(ncx * ncz);
+      __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0 && mine) atomicAdd(&qcount[3], mine);
+    __syncthreads();
+    relaxed = qcount[3];
+    any_change = relaxed != 0u;
+  } else {
 #pragma unroll 1
   for (int c = 0; c < 9; c++) {
     const int cxc = c / 3;
@@ -725,8 +766,11 @@ cascade_tile_kernel(const __grid_constant__ CUtensorMap tmap, MapView m, float s
     }
     __syncthreads();
   }
-  // hint for the next sweep: skip the pair scan while most of this tile still moves
-  if (tid == 0 && scratch.hint != nullptr) scratch.hint[tile_id] = (relaxed * 100u > 26u * centres) ? 1 : 0;
+  }
+  // hint for the next sweep: 0 = pair-bitmap path, 1 = skip the pair scan while most of this tile still moves,
+  // 2 = dense-direct while nearly half of the centres move
+  if (tid == 0 && scratch.hint != nullptr)
+    scratch.hint[tile_id] = (relaxed * 100u > SWE_TILE_DIRECT_PCT * centres) ? 2 : ((relaxed * 100u > 26u * centres) ? 1 : 0);
   }
 
   // ---- store O if anything in this tile moved -----------------------------------------------
@@ -1078,6 +1122,7 @@ static void allow_smem(const void* kernel, int bytes) {
   cudaGetDevice(&dev);
   if (done.count({dev, kernel})) return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   done.insert({dev, kernel});
 }
 

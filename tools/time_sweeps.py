@@ -15,7 +15,7 @@ for k in range(1, 240):
     ex = w.cascade_sweep(1, want_excess=True)
     ms = w.stats().last_sweep_ms
     tot += ms
-    if k < 4 or k % 20 == 0:
+    if k < 4 or k % 20 == 0 or k in (5, 10):
         print(f"sweep {k:3d}: {ms:.3f} ms  ({8.0 * n * n / ms / 1e6:.0f} GB/s)  max excess {ex:.3g}", flush=True)
     if ex < 1e-4:
         print(f"converged after {k} sweeps, mean {tot / k:.3f} ms, last {ms:.3f} ms")
