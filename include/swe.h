@@ -176,6 +176,7 @@ int swe_set_params(swe_engine* e, const swe_params* params);   /* Wind::maxAge =
 int swe_get_params(const swe_engine* e, swe_params* out);
 int swe_get_size(const swe_engine* e, int* nx, int* nz);
 int swe_set_option(swe_engine* e, int option, int value);
+int swe_get_option(const swe_engine* e, int option, int* value);
 
 /* srand(seed) (SimpleWindErosion.cpp:29,33): seeds the deterministic mode's libc-rand
  * replica and the parallel mode's counter-based generator. */
@@ -287,6 +288,9 @@ int swe_normalize_height(swe_engine* e, float min, float max);
 /* ---- diagnostics ------------------------------------------------------------------- */
 int swe_get_stats(swe_engine* e, swe_stats* out);
 int swe_reset_stats(swe_engine* e);
+/* checkpoint / resume: make the counters of an earlier swe_get_stats the baseline again (particles, steps, exits,
+ * sediment_lost, cascade_cells, erode_calls; the timing fields are ignored) */
+int swe_import_stats(swe_engine* e, const swe_stats* in);
 int swe_sum_plane(swe_engine* e, int plane, double* out);   /* fp64 sum over the map */
 int swe_max_excess(swe_engine* e, float* out);
 int swe_hash_height(swe_engine* e, uint64_t* out);          /* FNV-1a-64 of fp32 words */

@@ -23,17 +23,21 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import os
 import struct
 
 import numpy as np
 
 from . import world as _world
-from ._capi import STATE_BYTES, Params, check, lib
+from ._capi import STATE_BYTES, Params, Stats, check, lib
 
 MAGIC = b"SWEB200\0"
 VERSION = 1
 PLANE_NAMES = ["height", "massflow", "momentumx", "momentumy", "momentumz",
                "massflow_track", "momentumx_track", "momentumy_track", "momentumz_track"]
+# engine options that change what a parallel run computes (swe_option values)
+_OPTIONS = {"cascade_interval": _world.OPT_CASCADE_INTERVAL, "call_batches": _world.OPT_CALL_BATCHES,
+            "schedule": _world.OPT_SCHEDULE, "stagger_rounds": _world.OPT_STAGGER_ROUNDS}
 _PARAM_FIELDS = ["max_age", "boundarylayer", "suspension", "gravity", "lrate", "maxdiff", "settling",
                  "mapscale", "abrasion"]
 
@@ -75,17 +79,24 @@ def save(w: "_world.World", path: str, user: dict | None = None, with_rock: bool
         "nx": w.nx, "nz": w.nz, "row0": w.row0, "global_nx": w.global_nx, "planes": names,
         "params": _params_to_dict(w.params), "state": bytes(state).hex(), "has_rock": rock is not None,
         "stats": {"particles": st.particles, "steps": st.steps, "exits_oob": st.exits_oob,
-                  "exits_age": st.exits_age, "sediment_lost": st.sediment_lost, "erode_calls": st.erode_calls},
+                  "exits_age": st.exits_age, "sediment_lost": st.sediment_lost, "erode_calls": st.erode_calls,
+                  "cascade_cells": st.cascade_cells},
+        "options": {name: w.get_option(opt) for name, opt in _OPTIONS.items()},
         "user": user or {},
     }
     blob = json.dumps(header, sort_keys=True).encode("utf-8")
-    with open(path, "wb") as f:
+    # written beside the target and renamed into place: a crash mid-write never destroys the previous checkpoint
+    tmp = f"{path}.tmp.{os.getpid()}"
+    with open(tmp, "wb") as f:
         f.write(MAGIC)
         f.write(struct.pack("<II", VERSION, len(blob)))
         f.write(blob)
         f.write(b"\0" * (-(16 + len(blob)) % 64))
         for a in planes:
             f.write(np.ascontiguousarray(a, dtype="<f4").tobytes())
+        f.flush()
+        os.fsync(f.fileno())
+    os.replace(tmp, path)
     return header
 
 
@@ -113,8 +124,12 @@ def read_planes(path: str) -> tuple[dict, dict]:
     return header, out
 
 
-def load(path: str, device: int = 0, into: "_world.World | None" = None) -> "_world.World":
-    """Recreate the engine of a checkpoint (or refill `into`, e.g. a connected stripe engine)."""
+def load(path: str, device: int = 0, into: "_world.World | None" = None, sync_halos: bool = False) -> "_world.World":
+    """Recreate the engine of a checkpoint (or refill `into`, e.g. a connected stripe engine): planes, rock,
+    run state, the options that change what a parallel run computes, and the counters (so that the mass balance
+    sum(height) + sediment_lost stays continuous across the resume). A stripe engine gets its owned rows only:
+    its ghost rows must be refreshed before the next erode -- pass sync_halos=True when every rank loads
+    collectively (one process per GPU), or call StripeGroup.sync_halos() for in-process stripes."""
     header, planes = read_planes(path)
     if into is None:
         if header["row0"] != 0 or header["global_nx"] != header["nx"]:
@@ -131,4 +146,15 @@ def load(path: str, device: int = 0, into: "_world.World | None" = None) -> "_wo
         w.upload_rock(np.ascontiguousarray(planes["rock"]))
     state = (C.c_ubyte * STATE_BYTES).from_buffer_copy(bytes.fromhex(header["state"]))
     check(lib.swe_import_state(w._h, state, STATE_BYTES))
+    for name, value in header.get("options", {}).items():
+        if name in _OPTIONS:
+            w.set_option(_OPTIONS[name], int(value))
+    hs = header.get("stats")
+    if hs:
+        st = Stats()
+        for k, v in hs.items():
+            setattr(st, k, v)
+        check(lib.swe_import_stats(w._h, C.byref(st)))
+    if sync_halos and hasattr(w, "sync_halos"):
+        w.sync_halos()
     return w

@@ -2,6 +2,7 @@
 // transfer with arbitrary host stride, stream plumbing, statistics. Host-only logic; all
 // arithmetic on map data happens in kernels. No CPU fallback anywhere: every entry point
 // that touches the map needs the CUDA device the engine was created on.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -38,6 +39,10 @@ int fail(int code, const char* fmt, ...) {
 
 bool params_ok(const swe_params& p, const char** why) {
   if (p.max_age < 0) { *why = "max_age < 0"; return false; }
+  if (p.max_age > (1 << 20)) { *why = "max_age > 2^20"; return false; }
+  for (float v : {p.boundarylayer, p.suspension, p.gravity, p.lrate, p.maxdiff, p.settling, p.abrasion, p.pspeed[0], p.pspeed[1],
+                  p.pspeed[2]})
+    if (!std::isfinite(v)) { *why = "a parameter is NaN or infinite"; return false; }
   if (!(p.boundarylayer > 0.0f)) { *why = "boundarylayer must be > 0"; return false; }
   if (p.mapscale <= 0) { *why = "mapscale must be > 0"; return false; }
   const float l2 = p.pspeed[0] * p.pspeed[0] + p.pspeed[1] * p.pspeed[1] + p.pspeed[2] * p.pspeed[2];
@@ -1073,6 +1078,8 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
     return fail(SWE_ERR_INVALID, "unknown mode %d", mode);
   if (e->st.enabled)
     if (int rc = stripe_erode_check(e, cycles, mode)) return rc;
+  if (mode == SWE_MODE_DETERMINISTIC && e->m.rock)   // (checked before anything is enqueued: a failed call leaves the engine untouched)
+    return fail(SWE_ERR_STATE, "deterministic mode reproduces the reference, which has no rock layer");
   if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_schedule == 0)
     return erode_colour(e, cycles);
   if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_cuda_graph && !e->opt_kernel_timing)
@@ -1096,7 +1103,6 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
         if (int rc = stripe_erode_round(e)) return rc;
     }
   } else if (mode == SWE_MODE_DETERMINISTIC) {
-    if (e->m.rock) return fail(SWE_ERR_STATE, "deterministic mode reproduces the reference, which has no rock layer");
     launch_det_erode(e->m, e->p, cycles, e->d_rng, e->d_stats, e->stream);
     if (int rc = check_launch(e, "det_erode")) return rc;
   } else if (cycles > 0) {
@@ -1434,6 +1440,20 @@ int swe_get_stats(swe_engine* e, swe_stats* out) {
   return SWE_OK;
 }
 
+// Restore the accumulated counters (checkpoint / resume): what swe_get_stats reported when the checkpoint was
+// written becomes the baseline again, so that the mass balance sum(height) + sediment_lost stays continuous.
+int swe_import_stats(swe_engine* e, const swe_stats* in) {
+  if (int rc = bind(e)) return rc;
+  if (!in) return fail(SWE_ERR_INVALID, "stats is NULL");
+  DevStats s{};
+  s.particles = in->particles; s.steps = in->steps; s.exits_oob = in->exits_oob; s.exits_age = in->exits_age;
+  s.sediment_lost = in->sediment_lost; s.cascade_cells = in->cascade_cells;
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  SWE_CUDA(cudaMemcpy(e->d_stats, &s, sizeof s, cudaMemcpyHostToDevice));
+  e->erode_calls = in->erode_calls;
+  return SWE_OK;
+}
+
 int swe_reset_stats(swe_engine* e) {
   if (int rc = bind(e)) return rc;
   SWE_CUDA(cudaMemsetAsync(e->d_stats, 0, sizeof(DevStats), e->stream));
@@ -1573,6 +1593,22 @@ int swe_stripe_rows(const swe_engine* e, int* own_lo, int* own_hi) {
   if (own_lo) *own_lo = e->own_lo();
   if (own_hi) *own_hi = e->own_hi();
   return SWE_OK;
+}
+
+int swe_get_option(const swe_engine* e, int option, int* value) {
+  if (!e || !value) return fail(SWE_ERR_INVALID, "NULL argument");
+  switch (option) {
+    case SWE_OPT_CASCADE_VARIANT: *value = e->opt_cascade_variant; return SWE_OK;
+    case SWE_OPT_CASCADE_INTERVAL: *value = e->opt_cascade_interval; return SWE_OK;
+    case SWE_OPT_KERNEL_TIMING: *value = e->opt_kernel_timing; return SWE_OK;
+    case SWE_OPT_CUDA_GRAPH: *value = e->opt_cuda_graph; return SWE_OK;
+    case SWE_OPT_PDL: *value = e->opt_pdl; return SWE_OK;
+    case SWE_OPT_CALL_BATCHES: *value = e->opt_call_batches; return SWE_OK;
+    case SWE_OPT_SCHEDULE: *value = e->opt_schedule; return SWE_OK;
+    case SWE_OPT_STAGGER_ROUNDS: *value = e->opt_stagger; return SWE_OK;
+    case SWE_OPT_PERSISTENT: *value = e->opt_persistent; return SWE_OK;
+    default: return fail(SWE_ERR_INVALID, "unknown option %d", option);
+  }
 }
 
 int swe_set_option(swe_engine* e, int option, int value) {

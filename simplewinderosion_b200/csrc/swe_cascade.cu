@@ -17,6 +17,7 @@
 // Compiled with -fmad=false; arithmetic through swe_exact.cuh.
 #include <cuda.h>
 #include <cstring>
+#include <mutex>
 #include <set>
 #include <utility>
 
@@ -1087,15 +1088,14 @@ bool make_height_tensor_map(const MapView& m, HeightTensorMap* out) {
   out->valid = false;
   if ((m.nz & 3) != 0) return false;                        // row pitch must be a multiple of 16 B
   static EncodeTiledFn encode = nullptr;
-  static bool looked = false;
-  if (!looked) {
-    looked = true;
+  static std::once_flag looked;           // engines may be created from several host threads (one per GPU)
+  std::call_once(looked, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
       encode = reinterpret_cast<EncodeTiledFn>(fn);
-  }
+  });
   if (!encode) return false;
   static_assert(sizeof(CUtensorMap) == sizeof(out->opaque), "tensor map size");
   const cuuint64_t dims[2] = {(cuuint64_t)m.nz, (cuuint64_t)m.rows};
@@ -1117,7 +1117,9 @@ bool make_height_tensor_map(const MapView& m, HeightTensorMap* out) {
 
 // dynamic shared memory above 48 KB needs an opt-in per function and per device
 static void allow_smem(const void* kernel, int bytes) {
-  static std::set<std::pair<int, const void*>> done;   // engines of one process share one host thread at a time
+  static std::set<std::pair<int, const void*>> done;
+  static std::mutex guard;                             // one host thread per GPU is the natural multi-GPU pattern
+  std::lock_guard<std::mutex> lock(guard);
   int dev = 0;
   cudaGetDevice(&dev);
   if (done.count({dev, kernel})) return;

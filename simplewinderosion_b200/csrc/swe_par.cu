@@ -121,7 +121,9 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
       // is a compare-and-swap loop that never takes the surface below the bedrock.
       const float rk = __ldcg(m.rock + ci);
       float take = dh;
-      if (hc - rk < 64.0f * dh) {
+      {
+        // always a compare-and-swap loop in layered mode: several particles may stand on one cell in the same
+        // round, and the sum of their takes must never bring the surface below the bedrock (sand >= 0)
         unsigned* hp = reinterpret_cast<unsigned*>(hc_ptr);
         unsigned old = __float_as_uint(hc), assumed;
         do {
@@ -130,8 +132,6 @@ __device__ __forceinline__ int par_step(const MapView& m, const ParConst& C, PSt
           if (!(take > 0.0f)) { take = 0.0f; break; }
           old = atomicCAS(hp, assumed, __float_as_uint(__uint_as_float(assumed) - take));
         } while (old != assumed);
-      } else {
-        red_add_f32(hc_ptr, -take);
       }
       const float ground = C.abrasion * (dh - take);
       if (ground > 0.0f) { red_add_f32(m.rock + ci, -ground); red_add_f32(hc_ptr, -ground); }

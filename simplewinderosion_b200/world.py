@@ -141,6 +141,11 @@ class World:
     def set_option(self, option: int, value: int) -> None:
         check(lib.swe_set_option(self._h, int(option), int(value)))
 
+    def get_option(self, option: int) -> int:
+        v = C.c_int()
+        check(lib.swe_get_option(self._h, int(option), C.byref(v)))
+        return v.value
+
     def srand(self, seed: int) -> None:
         """srand(SEED) (SimpleWindErosion.cpp:27-34)."""
         self.SEED = int(seed)

@@ -2,6 +2,8 @@
 fresh engine and continued must be BITWISE identical to the uninterrupted run and to the oracle
 (the libc-rand replica travels in the run state); a parallel run resumes with the same call
 counter, so its particle spawn sequence continues (statistical check: float atomics)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -74,8 +76,13 @@ def test_parallel_resume_continues_the_call_counter(tmp_path):
     c.erode(20000)
     # same spawn sequence (call index 1 after the resume) => same particle statistics up to atomics order
     sa, sc = a.stats(), c.stats()
-    assert sc.erode_calls == 1 and sa.erode_calls == 2          # stats restart with the new engine
-    assert abs(sa.steps / 2 - sc.steps) / sc.steps < 0.05
+    assert sc.erode_calls == 2 == sa.erode_calls                # the counters continue across the resume
+    assert sc.particles == sa.particles == 40000
+    assert abs(sa.steps - sc.steps) / sc.steps < 0.03
+    # ... and so does the mass balance: sum(height) + sediment carried away is still the initial mass
+    s0 = float(hm.astype(np.float64).sum())
+    assert abs(c.sum_plane() + sc.sediment_lost - s0) < 2e-5 * abs(s0)
+    assert c.get_option(swe.OPT_SCHEDULE) == swe.SCHEDULE_COLOUR_QUEUES
     ha, hc = a.download(), c.download()
     assert np.corrcoef((ha - hm).ravel(), (hc - hm).ravel())[0, 1] > 0.9
     d = fresh()
@@ -95,3 +102,51 @@ def test_layered_checkpoint_keeps_rock(tmp_path):
     assert h["has_rock"] and h["planes"][-1] == "rock"
     w2 = checkpoint.load(path)
     assert np.array_equal(bits(w2.download_rock()), bits(rock))
+
+
+def test_checkpoint_is_written_atomically_and_keeps_options(tmp_path):
+    n = 64
+    w = swe.World(n)
+    w.upload(generate.gaussian_hill(n))
+    w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_LOCKSTEP)
+    w.set_option(swe.OPT_CALL_BATCHES, 3)
+    w.set_option(swe.OPT_STAGGER_ROUNDS, 77)
+    path = str(tmp_path / "o.swe")
+    h = checkpoint.save(w, path)
+    assert h["options"] == {"cascade_interval": 1, "call_batches": 3, "schedule": 1, "stagger_rounds": 77}
+    assert os.listdir(str(tmp_path)) == ["o.swe"]               # no temporary file left behind
+    w2 = checkpoint.load(path)
+    assert (w2.get_option(swe.OPT_SCHEDULE), w2.get_option(swe.OPT_CALL_BATCHES), w2.get_option(swe.OPT_STAGGER_ROUNDS)) == (1, 3, 77)
+
+
+def test_stripe_checkpoint_resume(tmp_path):
+    """One file per stripe; after loading into connected stripe engines the ghost rows are refreshed and the run
+    continues with exact accounting."""
+    from simplewinderosion_b200 import stripes
+    n, world, cycles = 128, 2, 4096
+    hm = generate.gaussian_hill(n)
+
+    def make():
+        ws = [stripes.StripedWorld(n, n, r, world, cycles) for r in range(world)]
+        stripes.StripedWorld.connect_in_process(ws)
+        return stripes.StripeGroup(ws)
+
+    g = make()
+    for w in g.worlds:
+        w.upload_global(hm); w.srand(3)
+    g.sync_halos()
+    g.erode(cycles)
+    paths = [str(tmp_path / f"s{r}.swe") for r in range(world)]
+    for w, p in zip(g.worlds, paths):
+        checkpoint.save(w, p)
+    g2 = make()
+    for w, p in zip(g2.worlds, paths):
+        checkpoint.load(p, into=w)
+    g2.sync_halos()
+    assert np.array_equal(bits(g2.gather()), bits(g.gather()))
+    g2.erode(cycles)
+    sts = g2.stats()
+    assert sum(s.particles for s in sts) == 2 * cycles == sum(s.exits_oob + s.exits_age for s in sts)
+    s0 = float(hm.astype(np.float64).sum())
+    total = sum(w.sum_plane() for w in g2.worlds) + sum(s.sediment_lost for s in sts)
+    assert abs(total - s0) < 2e-5 * abs(s0)
