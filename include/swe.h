@@ -110,7 +110,15 @@ typedef enum swe_option {
    * call, the blocks meeting at a grid barrier between micro-rounds (~1.5 us instead of a ~6 us dependent
    * launch; the call ends on the device when the last particle dies); 0 = one launch per micro-round
    * (CUDA graph + programmatic dependent launches), with a host-side completion check. */
-  SWE_OPT_PERSISTENT = 9
+  SWE_OPT_PERSISTENT = 9,
+  /* 1 = periodic boundary, the variant the reference carries as comments beside its live closed boundary
+   * (cellpool.h:96-113 slice::oob/get, :447-465 map::oob/get): nothing is out of bounds, every cell access wraps,
+   * particles never leave the map (they die of age). Honoured by the deterministic mode (bitwise against the
+   * reference compiled with those blocks swapped in), swe_cascade / swe_height / swe_normal / the vertex and normal
+   * read-backs, whole-map sweeps (per-colour kernels) and the colour-queue parallel mode; sweeps and the parallel
+   * mode need map edges that are multiples of 3 (the nine-colour order on a torus). Single-GPU engines without a
+   * rock plane. Default 0. */
+  SWE_OPT_PERIODIC = 10
 } swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:

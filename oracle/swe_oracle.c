@@ -167,10 +167,21 @@ static inline v3 v3_mix(v3 x, v3 y, float a) {
   return v3_add(v3_scale_r(x, 1.0f - a), v3_scale_r(y, a));
 }
 
-static inline int oob(const swo_world* w, int x, int z) { /* cellpool.h:432-438 */
+static inline int oob(const swo_world* w, int x, int z) { /* cellpool.h:432-438; periodic variant :451-453 */
+  if (w->periodic) return 0;
   return x < 0 || z < 0 || x >= w->nx || z >= w->nz;
 }
-#define HGT(w, x, z) ((w)->plane[0][(size_t)(x) * (w)->nz + (z)])
+/* cell index; the periodic variant wraps (cellpool.h:102-110: while(p.x < 0) p.x += res.x; ...) */
+static inline size_t cidx(const swo_world* w, int x, int z) {
+  if (w->periodic) {
+    while (x < 0) x += w->nx;
+    while (z < 0) z += w->nz;
+    while (x >= w->nx) x -= w->nx;
+    while (z >= w->nz) z -= w->nz;
+  }
+  return (size_t)x * w->nz + z;
+}
+#define HGT(w, x, z) ((w)->plane[0][cidx((w), (x), (z))])
 
 /* quad::_normal, cellpool.h:200-223: up to four triangle normals, in the reference's
  * order; a triangle counts iff its DIAGONAL neighbour is in bounds. */
@@ -273,7 +284,7 @@ int swo_fly(swo_world* w, swo_particle* q) {
   const swo_params* P = &w->p;
   const int ix = (int)roundf(q->pos[0]), iz = (int)roundf(q->pos[2]);   /* :30 */
   if (oob(w, ix, iz)) return 0;                                          /* :32-38 */
-  const size_t ind = (size_t)ix * w->nz + iz;
+  const size_t ind = cidx(w, ix, iz);
   const float h = w->plane[0][ind];
   const v3 n = normal_v3(w, ix, iz);                                     /* :40 */
   v3 pos = v3_(q->pos[0], q->pos[1], q->pos[2]);

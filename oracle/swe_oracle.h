@@ -66,6 +66,11 @@ typedef struct swo_world {
    * Only swo_cascade / swo_cascade_sweep honour it: a transfer is capped by the giving
    * cell's sand max(height - rock, 0). */
   float* rock;
+  /* Periodic boundary: the variant the reference carries as comments (cellpool.h:96-113 slice::get,
+   * :447-465 map::get): oob() is never true and every cell access wraps its indices. 0 = the live
+   * closed boundary. Pinned against the reference compiled with those comment blocks swapped in
+   * (oracle/Makefile, libswe_ref_p<N>.so). */
+  int periodic;
 } swo_world;
 
 typedef struct swo_particle {  /* struct Wind, wind.hpp:4-21 */

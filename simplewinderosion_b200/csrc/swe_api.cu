@@ -998,6 +998,7 @@ int swe_download_frame(swe_engine* e, float* dst5) {
 
 int swe_upload_rock(swe_engine* e, const float* src, ptrdiff_t stride_bytes) {
   if (int rc = bind(e)) return rc;
+  if (e->m.periodic) return fail(SWE_ERR_STATE, "the layered extension is not available with the periodic boundary");
   if (e->st.enabled) return fail(SWE_ERR_STATE, "the layered extension is not available on stripe engines");
   if (!src) return fail(SWE_ERR_INVALID, "src is NULL");
   if (stride_bytes < 4 || stride_bytes % 4) return fail(SWE_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 4");
@@ -1078,6 +1079,13 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
     return fail(SWE_ERR_INVALID, "unknown mode %d", mode);
   if (e->st.enabled)
     if (int rc = stripe_erode_check(e, cycles, mode)) return rc;
+  if (e->m.periodic && mode == SWE_MODE_PARALLEL) {
+    // the nine-colour order is conflict-free on a torus only if both edges are multiples of 3
+    if (e->m.nx % 3 || e->m.nz % 3 || e->m.nx < 6 || e->m.nz < 6)
+      return fail(SWE_ERR_STATE, "periodic parallel mode needs map edges that are multiples of 3 (got %dx%d)", e->m.nx, e->m.nz);
+    if (e->opt_schedule != 0 || !e->opt_persistent || !e->coop_ok)
+      return fail(SWE_ERR_STATE, "periodic parallel mode runs the colour-queue schedule in its persistent form only");
+  }
   if (mode == SWE_MODE_DETERMINISTIC && e->m.rock)   // (checked before anything is enqueued: a failed call leaves the engine untouched)
     return fail(SWE_ERR_STATE, "deterministic mode reproduces the reference, which has no rock layer");
   if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_schedule == 0)
@@ -1207,6 +1215,8 @@ int swe_max_excess(swe_engine* e, float* out) {
 int swe_cascade_sweep(swe_engine* e, int sweeps, float* max_excess_out) {
   if (int rc = bind(e)) return rc;
   if (sweeps < 0) return fail(SWE_ERR_INVALID, "sweeps < 0");
+  if (e->m.periodic && (e->m.nx % 3 || e->m.nz % 3 || e->m.nx < 6 || e->m.nz < 6))
+    return fail(SWE_ERR_STATE, "a periodic cascade sweep needs map edges that are multiples of 3 (got %dx%d)", e->m.nx, e->m.nz);
   finish_timers(e);
   SWE_CUDA(cudaEventRecord(e->ev_c, e->stream));
   int n = 0;
@@ -1607,6 +1617,7 @@ int swe_get_option(const swe_engine* e, int option, int* value) {
     case SWE_OPT_SCHEDULE: *value = e->opt_schedule; return SWE_OK;
     case SWE_OPT_STAGGER_ROUNDS: *value = e->opt_stagger; return SWE_OK;
     case SWE_OPT_PERSISTENT: *value = e->opt_persistent; return SWE_OK;
+    case SWE_OPT_PERIODIC: *value = e->m.periodic; return SWE_OK;
     default: return fail(SWE_ERR_INVALID, "unknown option %d", option);
   }
 }
@@ -1634,6 +1645,14 @@ int swe_set_option(swe_engine* e, int option, int value) {
       e->opt_schedule = value; return SWE_OK;
     case SWE_OPT_PERSISTENT:
       e->opt_persistent = value ? 1 : 0; return SWE_OK;
+    case SWE_OPT_PERIODIC:
+      if (value && e->st.enabled) return fail(SWE_ERR_STATE, "the periodic boundary is not available on stripe engines");
+      if (value && e->m.rock) return fail(SWE_ERR_STATE, "the periodic boundary is not available with a rock plane");
+      if (cudaSetDevice(e->device) == cudaSuccess) cudaStreamSynchronize(e->stream);
+      e->m.periodic = value ? 1 : 0;
+      for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);   // captured launches carry the MapView by value
+      e->graphs.clear();
+      return SWE_OK;
     case SWE_OPT_STAGGER_ROUNDS:
       if (value < -1 || value > (1 << 20)) return fail(SWE_ERR_INVALID, "stagger rounds must be -1 (auto) or in [0, 2^20]");
       e->opt_stagger = value; return SWE_OK;

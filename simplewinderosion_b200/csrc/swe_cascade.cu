@@ -1062,6 +1062,13 @@ __global__ void max_excess_kernel(MapView m, swe_params P, float* out) {
        i += (size_t)gridDim.x * blockDim.x) {
     const int x = m.x0 + (int)(i / m.nz), z = (int)(i % m.nz);
     const float h = m.height[i];
+    if (m.periodic) {   // on a torus every cell has all four forward neighbours
+      best = fmaxf(best, fsub(fabsf(fsub(h, m.height[m.idx(x, z + 1)])), thr.ortho));
+      best = fmaxf(best, fsub(fabsf(fsub(h, m.height[m.idx(x + 1, z)])), thr.ortho));
+      best = fmaxf(best, fsub(fabsf(fsub(h, m.height[m.idx(x + 1, z - 1)])), thr.diag));
+      best = fmaxf(best, fsub(fabsf(fsub(h, m.height[m.idx(x + 1, z + 1)])), thr.diag));
+      continue;
+    }
     if (z + 1 < m.nz) best = fmaxf(best, fsub(fabsf(fsub(h, m.height[i + 1])), thr.ortho));
     if (x + 1 < m.nx && x + 1 < m.x0 + m.rows) {
       const size_t j = i + m.nz;
@@ -1189,6 +1196,7 @@ size_t tile_flag_count(const MapView& m) {
 int launch_cascade_sweep(const MapView& m, const swe_params& p, const HeightTensorMap* tmap, int sweeps,
                          DevStats* stats, cudaStream_t st, int variant, TileScratch scratch) {
   int launches = 0;
+  if (m.periodic) variant = 1;   // the tile kernels load their halo with TMA zero-fill / clipped loads: no wrap
   for (int s = 0; s < sweeps; s++) {
     if (variant == 0 || variant == 2) {
       launch_tile_sweep(m, p, variant == 2 ? nullptr : tmap, nullptr, 0, nullptr, 0, m.nx, scratch, st);

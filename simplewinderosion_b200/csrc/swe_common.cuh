@@ -25,10 +25,18 @@ struct MapView {
   int nx, nz;   // GLOBAL map extent (bounds tests use these: closed boundary, cellpool.h:432-438)
   int x0;       // global x of local row 0 (0 on a single GPU)
   int rows;     // rows stored locally (== nx on a single GPU)
+  int periodic; // 1 = the reference's commented periodic boundary (cellpool.h:96-113,447-465): nothing is out of
+                // bounds and every cell access wraps (single-GPU engines only)
+  __host__ __device__ __forceinline__ static int wrap(int v, int n) {
+    v %= n;
+    return v < 0 ? v + n : v;
+  }
   __host__ __device__ __forceinline__ size_t idx(int x, int z) const {
+    if (periodic) { x = wrap(x, nx); z = wrap(z, nz); }
     return (size_t)(x - x0) * (size_t)nz + (size_t)z;
   }
   __host__ __device__ __forceinline__ bool oob(int x, int z) const {
+    if (periodic) return false;
     return x < 0 || z < 0 || x >= nx || z >= nz;
   }
 };

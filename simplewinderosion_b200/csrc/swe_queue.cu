@@ -498,16 +498,22 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
       if (j < n_in) {
         ra = ld_l2(qa + j, stream);
         rb = ld_l2(qb + j, stream);
-        const int ix = __float2int_rd(ra.x + 0.5f), iz = __float2int_rd(ra.z + 0.5f);   // wind.hpp:30
+        int ix = __float2int_rd(ra.x + 0.5f), iz = __float2int_rd(ra.z + 0.5f);         // wind.hpp:30
+        if (m.periodic) { ix = MapView::wrap(ix, m.nx); iz = MapView::wrap(iz, nz); }     // cellpool.h:102-110 (positions keep growing)
         const size_t ci = m.idx(ix, iz);
         float* hp = m.height + ci;
-        const bool xm = ix > 0, xp = ix + 1 < m.nx, zm = iz > 0, zp = iz + 1 < nz;
+        const bool per = m.periodic != 0;
+        const bool xm = per || ix > 0, xp = per || ix + 1 < m.nx, zm = per || iz > 0, zp = per || iz + 1 < nz;
         const unsigned valid = (xm && zm ? 1u : 0u) | (xm ? 2u : 0u) | (xm && zp ? 4u : 0u) | (zm ? 8u : 0u) |
                                (zp ? 16u : 0u) | (xp && zm ? 32u : 0u) | (xp ? 64u : 0u) | (xp && zp ? 128u : 0u);
-        // rows of the 3x3 block: a stripe reads / writes a neighbour's row in the neighbour's memory
+        // rows / columns of the 3x3 block: a stripe reads / writes a neighbour's row in the neighbour's memory, a
+        // periodic map wraps at the seam
         const bool rem_m = STRIPE && xm && ix - 1 < S.own_lo, rem_p = STRIPE && xp && ix + 1 >= S.own_hi;
-        float* row_m = rem_m ? S.below_h + (size_t)(ix - 1 - S.below_x0) * (size_t)nz + iz : hp - nz;
-        float* row_p = rem_p ? S.above_h + (size_t)(ix + 1 - S.above_x0) * (size_t)nz + iz : hp + nz;
+        float* row_m = rem_m ? S.below_h + (size_t)(ix - 1 - S.below_x0) * (size_t)nz + iz
+                             : ((per && ix == 0) ? hp + (size_t)(m.nx - 1) * (size_t)nz : hp - nz);
+        float* row_p = rem_p ? S.above_h + (size_t)(ix + 1 - S.above_x0) * (size_t)nz + iz
+                             : ((per && ix == m.nx - 1) ? hp - (size_t)(m.nx - 1) * (size_t)nz : hp + nz);
+        const int zo_m = (per && iz == 0) ? nz - 1 : -1, zo_p = (per && iz == nz - 1) ? 1 - nz : 1;
         // one claim word per 3x3 lattice cell: the cells of the served colour map one-to-one onto it, the tags
         // grow with every micro-round, so the table (1/9 of a plane: L2-resident) serves all colours.
         // The block is loaded while the claim is in flight (harmless if the claim is lost).
@@ -517,7 +523,7 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
 #pragma unroll
         for (int q8 = 0; q8 < 8; q8++) {
           const int dx = block::slot_dx(q8), dz = block::slot_dz(q8);
-          const float* src = dx < 0 ? row_m + dz : (dx > 0 ? row_p + dz : hp + dz);
+          const float* src = (dx < 0 ? row_m : (dx > 0 ? row_p : hp)) + (dz < 0 ? zo_m : (dz > 0 ? zo_p : 0));
           h[q8] = ((valid >> q8) & 1u) ? ld_h(src, dx < 0 ? rem_m : (dx > 0 ? rem_p : false), keep) : hc;
         }
         if (seen >= tag) {
@@ -555,13 +561,14 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
           for (int i = 0; i < 8; i++)
             if ((moved >> i) & 1u) {
               const int dx = block::slot_dx(s[i]), dz = block::slot_dz(s[i]);
-              float* dst = dx < 0 ? row_m + dz : (dx > 0 ? row_p + dz : hp + dz);
+              float* dst = (dx < 0 ? row_m : (dx > 0 ? row_p : hp)) + (dz < 0 ? zo_m : (dz > 0 ? zo_p : 0));
               st_h(dst, v[i], dx < 0 ? rem_m : (dx > 0 ? rem_p : false), keep);
             }
           n_steps++;
           ra = make_float4(q.px, q.py, q.pz, q.sed);
           rb = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
-          const int jx = __float2int_rd(q.px + 0.5f), jz = __float2int_rd(q.pz + 0.5f);
+          int jx = __float2int_rd(q.px + 0.5f), jz = __float2int_rd(q.pz + 0.5f);
+          if (per) { jx = MapView::wrap(jx, m.nx); jz = MapView::wrap(jz, nz); }
           if (m.oob(jx, jz)) { n_oob++; lost += q.sed; delta--; }                 // :32-38 (the next fly() call)
           else if (q.age > C.max_age) { n_age++; lost += q.sed; delta--; }        // :45-46
           else {

@@ -28,7 +28,7 @@ class ORand(C.Structure):
 
 class OWorld(C.Structure):
     _fields_ = [("nx", C.c_int), ("nz", C.c_int), ("plane", C.POINTER(C.c_float) * 9),
-                ("p", OParams), ("rng", ORand), ("rock", C.POINTER(C.c_float))]
+                ("p", OParams), ("rng", ORand), ("rock", C.POINTER(C.c_float)), ("periodic", C.c_int)]
 
 
 class OStats(C.Structure):
@@ -90,12 +90,13 @@ def port():
 class PortWorld:
     """The plain-C restatement (oracle/swe_oracle.c)."""
 
-    def __init__(self, nx: int, nz: int | None = None):
+    def __init__(self, nx: int, nz: int | None = None, periodic: bool = False):
         nz = nx if nz is None else nz
         self.L = port()
         self.w = self.L.swo_create(nx, nz)
         assert self.w, "swo_create failed"
         self.nx, self.nz = nx, nz
+        self.w.contents.periodic = int(periodic)
 
     def __del__(self):
         try:
@@ -188,8 +189,8 @@ class PortWorld:
         return self.L.swo_fnl_getnoise(frequency, x, y, z)
 
 
-def ref_available(n: int) -> bool:
-    return os.path.exists(os.path.join(REF_DIR, f"libswe_ref_{n}.so"))
+def ref_available(n: int, periodic: bool = False) -> bool:
+    return os.path.exists(os.path.join(REF_DIR, f"libswe_ref_{'p' if periodic else ''}{n}.so"))
 
 
 class RefWorld:
@@ -197,9 +198,12 @@ class RefWorld:
     reference keeps its map in static globals (world.hpp:12-19)."""
     _libs: dict = {}
 
-    def __init__(self, n: int, seed: int = 1):
-        if n not in RefWorld._libs:
-            L = C.CDLL(os.path.join(REF_DIR, f"libswe_ref_{n}.so"))
+    def __init__(self, n: int, seed: int = 1, periodic: bool = False):
+        """periodic: the build with the reference's commented periodic-boundary blocks swapped in
+        (cellpool.h:96-113,447-465; oracle/Makefile)."""
+        key = ("p" if periodic else "") + str(n)
+        if key not in RefWorld._libs:
+            L = C.CDLL(os.path.join(REF_DIR, f"libswe_ref_{key}.so"))
             L.ref_hash.restype = C.c_ulonglong
             L.ref_sum_height.restype = C.c_double
             L.ref_set_plane.argtypes = [C.c_int, C.c_void_p]
@@ -214,8 +218,8 @@ class RefWorld:
                 L.ref_get_noise.argtypes = [C.c_float] * 4
                 L.ref_get_noise.restype = C.c_float
                 L.ref_noise_stack.argtypes = [C.c_int, C.c_int]
-            RefWorld._libs[n] = L
-        self.L = RefWorld._libs[n]
+            RefWorld._libs[key] = L
+        self.L = RefWorld._libs[key]
         assert self.L.ref_size() == n
         self.n = self.nx = self.nz = n
         self.L.ref_init(seed)  # srand(seed) + Gaussian-hill map (reset if already initialised)
