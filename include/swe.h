@@ -354,6 +354,9 @@ int swe_stripe_connect(swe_engine* e, const swe_stripe_link* below, const swe_st
 int swe_stripe_connect_ring(swe_engine* e, int rank, int n, const swe_stripe_link* links, int colocated);
 int swe_stripe_sync_halos(swe_engine* e);
 int swe_stripe_rows(const swe_engine* e, int* own_lo, int* own_hi);
+/* rows a stripe engine stores: [x0, x0 + rows) = its owned rows plus ghost rows. swe_upload_rock on a stripe engine
+ * takes exactly these rows (the layered extension needs the bedrock under the ghost rows too). */
+int swe_stripe_stored_rows(const swe_engine* e, int* x0, int* rows);
 /* One host thread driving several stripes (logical stripes on one GPU, or a process that owns
  * several GPUs): same effect as calling swe_erode(e, cycles, SWE_MODE_PARALLEL) /
  * swe_cascade_sweep(e, sweeps, NULL) / swe_stripe_sync_halos(e) on every engine, with the

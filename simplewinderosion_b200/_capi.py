@@ -100,6 +100,7 @@ PROTOTYPES = {
     "swe_stripe_export_ipc": (C.c_int, [_E, C.c_void_p, C.c_size_t]),
     "swe_stripe_open_ipc": (C.c_int, [_E, C.c_void_p, C.c_size_t, C.POINTER(StripeLink)]),
     "swe_stripe_connect": (C.c_int, [_E, C.POINTER(StripeLink), C.POINTER(StripeLink)]),
+    "swe_stripe_stored_rows": (C.c_int, [_E, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "swe_stripe_connect_ring": (C.c_int, [_E, C.c_int, C.c_int, C.POINTER(StripeLink), C.c_int]),
     "swe_stripe_sync_halos": (C.c_int, [_E]),
     "swe_stripe_rows": (C.c_int, [_E, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -32,9 +32,20 @@ def wind_spectrum(h: np.ndarray) -> np.ndarray:
     return (np.abs(f) ** 2).mean(axis=1) / h.shape[0]
 
 
-def dominant_wavelength(h: np.ndarray, kmin: int = 2) -> float:
-    """Wavelength (cells) of the strongest spectral peak along the wind, ignoring k < kmin."""
-    p = wind_spectrum(h)
+def detrend_along_wind(h: np.ndarray, degree: int = 3) -> np.ndarray:
+    """Remove the large-scale along-wind trend (a polynomial fitted to the z-averaged profile): on a closed
+    map sand piles up / drains along x, which otherwise puts all spectral power into the lowest bins."""
+    h = np.asarray(h, dtype=np.float64)
+    x = np.arange(h.shape[0], dtype=np.float64)
+    p = np.polyfit(x, h.mean(axis=1), degree)
+    return h - np.polyval(p, x)[:, None]
+
+
+def dominant_wavelength(h: np.ndarray, kmin: int = 4, detrend: bool = True) -> float:
+    """Wavelength (cells) of the strongest spectral peak along the wind. The profile is detrended first and the
+    bins k < kmin (map-scale structure, not dunes) are ignored -- without that the answer is just n/2 or n/3."""
+    p = wind_spectrum(detrend_along_wind(h) if detrend else h)
+    kmin = max(1, min(int(kmin), len(p) - 1))
     k = kmin + int(np.argmax(p[kmin:]))
     return h.shape[0] / k
 

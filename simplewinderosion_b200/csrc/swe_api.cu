@@ -431,7 +431,6 @@ int erode_parallel_graph(swe_engine* e, int cycles) {
   const uint64_t key = graph_key(e, cycles);
   cudaGraphExec_t exec = nullptr;
   for (auto& g : e->graphs) if (g.key == key) exec = g.exec;
-  finish_timers(e);
   const CallCtl ctl_host{(uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->call_index, 0u};
   SWE_CUDA(cudaMemcpyAsync(e->d_ctl, &ctl_host, sizeof ctl_host, cudaMemcpyHostToDevice, e->stream));
   if (!exec) {
@@ -591,7 +590,6 @@ int erode_colour(swe_engine* e, int cycles) {
   if (e->opt_persistent && e->coop_ok && e->persist_blocks_per_sm > 0 && !(e->m.rock && colour_persistent_blocks_per_sm(true) < 1))
     return erode_colour_persistent(e, cycles);
   if (int rc = need_queues(e, cycles)) return rc;
-  finish_timers(e);
   DevStats s0;
   SWE_CUDA(cudaMemcpyAsync(&s0, e->d_stats, sizeof s0, cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
@@ -638,8 +636,7 @@ int erode_colour(swe_engine* e, int cycles) {
   return erode_epilogue(e);
 }
 
-int erode_prologue(swe_engine* e) {
-  finish_timers(e);
+int erode_prologue(swe_engine* e) {   // (the timers of an earlier call are read at the next synchronising entry point)
   SWE_CUDA(cudaEventRecord(e->ev_a, e->stream));
   SWE_CUDA(cudaMemsetAsync(e->m.track, 0, e->cells() * sizeof(float4), e->stream));   // world.hpp:38-44
   SWE_CUDA(cudaEventRecord(e->ev_f0, e->stream));
@@ -657,7 +654,12 @@ int erode_epilogue(swe_engine* e) {
   return SWE_OK;
 }
 
+// Reads the event pairs of the last erode / sweep. Called from entry points that may run while that work is still
+// in flight (the next swe_erode is enqueued behind it): a pair whose closing event has not completed yet is left
+// for a later call instead of asking cudaEventElapsedTime for it (which would answer cudaErrorNotReady).
 void finish_timers(swe_engine* e) {
+  if (e->erode_timed && cudaEventQuery(e->ev_b) != cudaSuccess) { (void)cudaGetLastError(); return; }
+  if (e->sweep_timed && cudaEventQuery(e->ev_d) != cudaSuccess) { (void)cudaGetLastError(); return; }
   float ms = 0.0f;
   if (e->erode_timed && cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->last_erode_ms = ms;
   if (e->erode_timed && cudaEventElapsedTime(&ms, e->ev_f0, e->ev_f1) == cudaSuccess) e->last_fly_ms = ms;
@@ -999,7 +1001,10 @@ int swe_download_frame(swe_engine* e, float* dst5) {
 int swe_upload_rock(swe_engine* e, const float* src, ptrdiff_t stride_bytes) {
   if (int rc = bind(e)) return rc;
   if (e->m.periodic) return fail(SWE_ERR_STATE, "the layered extension is not available with the periodic boundary");
-  if (e->st.enabled) return fail(SWE_ERR_STATE, "the layered extension is not available on stripe engines");
+  // a stripe engine takes its STORED rows (swe_stripe_stored_rows: the owned rows plus the ghost rows either side):
+  // the bedrock under the ghost rows is needed by the sand-limited cascade at the stripe boundary and, unlike the
+  // heights, is not refreshed by the halo exchange (abrasion only ever lowers it, so a ghost copy can only
+  // underestimate the neighbour's sand: transfers stay within what the owner really has)
   if (!src) return fail(SWE_ERR_INVALID, "src is NULL");
   if (stride_bytes < 4 || stride_bytes % 4) return fail(SWE_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 4");
   const size_t n = e->cells(), bytes = n * sizeof(float);
@@ -1023,7 +1028,8 @@ int swe_download_rock(swe_engine* e, float* dst, ptrdiff_t stride_bytes) {
   if (int rc = bind(e)) return rc;
   if (!e->m.rock) return fail(SWE_ERR_STATE, "no rock plane: the engine is in single-layer mode");
   if (!dst || stride_bytes != 4) return fail(SWE_ERR_INVALID, "dst must be a packed fp32 plane (stride 4)");
-  SWE_CUDA(cudaMemcpyAsync(dst, e->m.rock, e->cells() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  const size_t off = (size_t)(e->own_lo() - e->m.x0) * (size_t)e->m.nz;     // owned rows only, like every download
+  SWE_CUDA(cudaMemcpyAsync(dst, e->m.rock + off, e->host_cells() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
   return SWE_OK;
 }
@@ -1079,6 +1085,10 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
     return fail(SWE_ERR_INVALID, "unknown mode %d", mode);
   if (e->st.enabled)
     if (int rc = stripe_erode_check(e, cycles, mode)) return rc;
+  if (e->st.enabled && e->m.rock && !stripe_uses_colour_queues(e))
+    // the lock-step stripe round recomputes its ghost rows instead of exchanging them, which needs bit-identical inputs
+    // on both sides; abrasion changes the bedrock under a neighbour's ghost copy
+    return fail(SWE_ERR_STATE, "the layered extension on stripes needs the colour-queue schedule (swe_stripe_connect_ring)");
   if (e->m.periodic && mode == SWE_MODE_PARALLEL) {
     // the nine-colour order is conflict-free on a torus only if both edges are multiples of 3
     if (e->m.nx % 3 || e->m.nz % 3 || e->m.nx < 6 || e->m.nz < 6)
@@ -1217,7 +1227,6 @@ int swe_cascade_sweep(swe_engine* e, int sweeps, float* max_excess_out) {
   if (sweeps < 0) return fail(SWE_ERR_INVALID, "sweeps < 0");
   if (e->m.periodic && (e->m.nx % 3 || e->m.nz % 3 || e->m.nx < 6 || e->m.nz < 6))
     return fail(SWE_ERR_STATE, "a periodic cascade sweep needs map edges that are multiples of 3 (got %dx%d)", e->m.nx, e->m.nz);
-  finish_timers(e);
   SWE_CUDA(cudaEventRecord(e->ev_c, e->stream));
   int n = 0;
   if (e->st.enabled) {
@@ -1596,6 +1605,13 @@ int swe_stripe_sync_halos(swe_engine* e) {
   const unsigned s = stripe_exchange_begin(e, false, &n);
   stripe_exchange_end(e, s, &n);
   return check_launch(e, "stripe halo sync", n);
+}
+
+int swe_stripe_stored_rows(const swe_engine* e, int* x0, int* rows) {
+  if (!e) return fail(SWE_ERR_INVALID, "engine is NULL");
+  if (x0) *x0 = e->m.x0;
+  if (rows) *rows = e->m.rows;
+  return SWE_OK;
 }
 
 int swe_stripe_rows(const swe_engine* e, int* own_lo, int* own_hi) {

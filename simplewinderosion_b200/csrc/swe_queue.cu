@@ -802,7 +802,8 @@ cudaError_t launch_colour_persistent(const MapView& m, const swe_params& p, cons
   StripeQueues sq{};
   if (stripe) sq = *stripe;
   void* args[] = {&mv, &C, &T, &Q, &claim, &key, &call, &n_total, &stagger, &max_micro, &ctl, &stats, &sq};
-  const void* fn = stripe ? reinterpret_cast<const void*>(&colour_persistent_kernel<false, true>)
+  const void* fn = stripe ? (m.rock ? reinterpret_cast<const void*>(&colour_persistent_kernel<true, true>)
+                                    : reinterpret_cast<const void*>(&colour_persistent_kernel<false, true>))
                  : m.rock ? reinterpret_cast<const void*>(&colour_persistent_kernel<true, false>)
                           : reinterpret_cast<const void*>(&colour_persistent_kernel<false, false>);
   // several logical stripes on ONE GPU (tests): their kernels must run side by side, which plain launches of
@@ -842,6 +843,7 @@ void preload_queue() {
   cudaFuncGetAttributes(&a, colour_persistent_kernel<false, false>);
   cudaFuncGetAttributes(&a, colour_persistent_kernel<true, false>);
   cudaFuncGetAttributes(&a, colour_persistent_kernel<false, true>);
+  cudaFuncGetAttributes(&a, colour_persistent_kernel<true, true>);
 }
 
 }  // namespace swe

@@ -171,6 +171,14 @@ class StripedWorld(_world.World):
         lo, hi = self.bounds[self.rank]
         self.upload(np.ascontiguousarray(height[lo:hi]), plane)
 
+    def upload_rock_global(self, rock: np.ndarray) -> None:
+        """Layered extension on a stripe: take this rank's STORED rows (owned + ghost rows) out of the global
+        (nx, nz) bedrock plane."""
+        x0, rows = C.c_int(), C.c_int()
+        check(lib.swe_stripe_stored_rows(self._h, C.byref(x0), C.byref(rows)))
+        a = np.ascontiguousarray(rock[x0.value:x0.value + rows.value], dtype=np.float32)
+        check(lib.swe_upload_rock(self._h, a.ctypes.data, 4))
+
     def sync_halos(self) -> None:
         check(lib.swe_stripe_sync_halos(self._h))
 

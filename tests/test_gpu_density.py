@@ -135,3 +135,22 @@ def test_stagger_option_and_sparse_calls():
     st = w.stats()
     assert st.exits_oob + st.exits_age == st.particles == 16 * n
     w.close()
+
+
+def test_cfg2_dune_wavelength_matches_sequential_reference():
+    """Dune formation from flat sand at cfg2's density (1.0 particle per cell per call), six calls: the dominant
+    along-wind wavelength (detrended spectrum, k >= 4: analysis.dominant_wavelength) of the parallel run must sit in
+    the same or an adjacent spectral bin as the sequential oracle's, and the spectra must correlate."""
+    n, cycles, calls = 256, 1 << 16, 6
+    hm = generate.flat_sand(n, seed=42)
+    ora = PortWorld(n); ora.set_plane(0, hm); ora.srand(1)
+    w = swe.World(n); w.upload(hm); w.srand(1)
+    for _ in range(calls):
+        ora.erode(cycles)
+        w.erode(cycles, swe.MODE_PARALLEL)
+    ho, hg = np.array(ora.plane(0)), w.download()
+    ko, kg = n / analysis.dominant_wavelength(ho), n / analysis.dominant_wavelength(hg)
+    assert abs(ko - kg) <= 1.0, (ko, kg)
+    assert analysis.spectrum_similarity(ho, hg, 1, n // 4) > 0.99
+    assert analysis.histogram_distance(ho, hg) < 0.12
+    assert abs(float(ho.std()) / float(hg.std()) - 1.0) < 0.1

@@ -35,6 +35,10 @@ def test_spectrum_finds_a_planted_dune_wavelength():
     rs = np.random.RandomState(0)
     h = (0.1 * np.sin(2 * np.pi * x / 32.0) + 0.01 * rs.standard_normal((n, n))).astype(np.float32)
     assert analysis.dominant_wavelength(h) == 32.0
+    # a strong along-wind trend (sand draining towards the downwind edge) must not hide the dunes
+    trend = (h + 8.0 * (x / n) ** 2 - 3.0 * x / n).astype(np.float32)
+    assert analysis.dominant_wavelength(trend) == 32.0
+    assert analysis.dominant_wavelength(trend, kmin=1, detrend=False) > 64.0       # what round 1 reported: n/2, n/3
     p = analysis.wind_spectrum(h)
     assert int(np.argmax(p[1:])) + 1 == n // 32
     shifted = np.roll(h, 5, axis=0)

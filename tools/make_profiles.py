@@ -14,7 +14,7 @@ def launches(path, out):
     tot = sum(sum(v) for v in d.values())
     with open(out, "w") as f:
         f.write(f"# ncu launch list summary ({os.path.basename(path)}): `ncu --metrics gpu__time_duration.sum --clock-control none` "
-                f"over `python bench.py --steps 1 --warmup 3 --skip-cpu --skip-cascade` (first {sum(len(v) for v in d.values())} launches; "
+                f"over `python bench.py --steps 1 --warmup 3 --skip-cpu --skip-cascade --skip-layered --skip-cfg4` (first {sum(len(v) for v in d.values())} launches; "
                 f"cold-cache, serialised: compare SHARES)\n\n| kernel | launches | total ms | share | mean us |\n|---|---|---|---|---|\n")
         for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"| {k} | {len(v)} | {sum(v)/1e6:.3f} | {100*sum(v)/tot:.1f} % | {sum(v)/len(v)/1e3:.1f} |\n")
@@ -28,7 +28,8 @@ def ncu_summary(rep, out, title):
 if os.path.exists(os.path.join(G, f"launches_{tag}.csv")):
     launches(os.path.join(G, f"launches_{tag}.csv"), os.path.join(P, f"{tag}_launches_summary.md"))
 traffic = {}
-for name, title in (("par_round", "par_round_kernel, 4096^2 FBm map, 4,194,304 particles, one round (step ~150 of a call)"),
+for name, title in (("colour_persistent", "colour_persistent_kernel (Wind::fly + erosion + World::cascade per particle step, all micro-rounds of one World::erode), 4096^2 FBm map, 4,194,304 particles"),
+                    ("par_round", "par_round_kernel, 4096^2 FBm map, 4,194,304 particles, one round (step ~150 of a call)"),
                     ("cascade_stamped", "cascade_tile_kernel<stamped,TMA>, same run: World::cascade at the cells touched in the round"),
                     ("cascade_sweep8192", "cascade_tile_kernel<plain,TMA>, 8192^2 U(0,1) map, one whole-map sweep (sweep 3: dense path, everything moves)"),
                     ("noise_stack", "noise_stack_kernel, 4096^2, eight layers of FastNoiseLite OpenSimplex2 FBm (map::init generate on the device)"),
@@ -43,6 +44,12 @@ for name, title in (("par_round", "par_round_kernel, 4096^2 FBm map, 4,194,304 p
             if len(f) >= 3 and f[0] == "dram__bytes_read.sum": rd = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[f[2]]
             if len(f) >= 3 and f[0] == "dram__bytes_write.sum": wr = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[f[2]]
         if rd is not None and wr is not None: traffic[name] = rd + wr
-json.dump({"source": f"profiles/{tag}_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)", "bytes_per_launch": traffic},
-          open(os.path.join(P, "traffic.json"), "w"), indent=1)
+old = {}
+try:
+    old = json.load(open(os.path.join(P, "traffic.json")))["bytes_per_launch"]
+except Exception:
+    pass
+old.update(traffic)
+json.dump({"source": "profiles/r*_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch; latest round per kernel)",
+           "bytes_per_launch": old}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(traffic)
