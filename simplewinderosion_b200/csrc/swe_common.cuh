@@ -214,7 +214,7 @@ struct StripeQueues {
   float* above_h; int above_x0;
   float4* below_a; float4* below_b; unsigned* below_count; int below_cap;
   float4* above_a; float4* above_b; unsigned* above_count; int above_cap;
-  unsigned long long* mailbox[8];      // [rank] -> that rank's mailbox: slot (parity * 8 + source rank), 128 B apart
+  unsigned long long* mailbox[8];      // [rank] -> that rank's mailbox ring: word (micro-round % 16) * 8 + source rank
 };
 constexpr int SWE_MAX_STRIPE_RANKS = 8;
 constexpr size_t SWE_PERSIST_BYTES = 4096;        // PersistCtl at 0, barrier mailbox at 1024

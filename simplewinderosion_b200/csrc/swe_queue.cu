@@ -668,31 +668,48 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
         const unsigned kn = k + 1u;
         bool timed_out = false;
         if (STRIPE) {
-          // cross-GPU barrier: publish (sequence number, local live count) into every rank's mailbox, wait for all
-          // ranks' words of this micro-round (two slots per rank by parity: a rank can be one barrier ahead)
+          // Cross-GPU barrier. Every rank publishes (sequence number, local live count) of the micro-round it has
+          // finished into every rank's mailbox ring (16 micro-rounds deep, 8 ranks per slot: one 64-byte line) and
+          // then waits for its two NEIGHBOURS only -- they are the only ranks whose boundary rows and queue
+          // appends it depends on, so a slow rank delays the others one hop per micro-round instead of at once.
+          // Ranks can therefore drift up to nranks - 1 micro-rounds apart; the decision "every particle is dead"
+          // is taken from the words of micro-round kn - nranks, which have all arrived by then (no waiting), so
+          // every rank leaves the loop at the same micro-round.
           const unsigned long long seq = xseq0 + (unsigned long long)kn;
           const unsigned long long word = (seq << 32) | (unsigned long long)(unsigned)live;
-          const int par = (int)(seq & 1ull);
+          const int slot = (int)(seq & 15ull);
           // ONE system-scope fence orders everything this GPU wrote in the micro-round (observed through the
           // arrival word) before the mailbox words; the words themselves are then plain system-scope stores
           asm volatile("fence.acq_rel.sys;" ::: "memory");
-          for (int i = 0; i < S.nranks; i++) st_relaxed_sys_u64(S.mailbox[i] + (par * 8 + S.rank) * 16, word);
-          int total = 0;
+          for (int i = 0; i < S.nranks; i++) st_relaxed_sys_u64(S.mailbox[i] + slot * 8 + S.rank, word);
+          const unsigned long long* mine = S.mailbox[S.rank];
           const long long t0 = clock64();
-          for (int i = 0; i < S.nranks && !timed_out; i++) {
-            unsigned long long w;
+          for (int nb = S.rank - 1; nb <= S.rank + 1 && !timed_out; nb += 2) {
+            if (nb < 0 || nb >= S.nranks) continue;
             unsigned spins = 0;
-            while (((w = ld_acquire_sys_u64(S.mailbox[S.rank] + (par * 8 + i) * 16)) >> 32) != (seq & 0xffffffffull)) {
+            while ((ld_acquire_sys_u64(mine + slot * 8 + nb) >> 32) != (seq & 0xffffffffull))
               if ((++spins & 1023u) == 0u && clock64() - t0 > 16000000000LL) { timed_out = true; break; }   // ~8 s
-            }
-            total += (int)(unsigned)(w & 0xffffffffull);
           }
-          live = total;
+          live = 1;                                          // not decided yet
+          if (kn > (unsigned)S.nranks) {
+            const unsigned long long seq_t = seq - (unsigned long long)S.nranks;
+            const int slot_t = (int)(seq_t & 15ull);
+            int total = 0;
+            for (int i = 0; i < S.nranks && !timed_out; i++) {
+              unsigned long long w;
+              unsigned spins = 0;
+              while (((w = ld_acquire_sys_u64(mine + slot_t * 8 + i)) >> 32) != (seq_t & 0xffffffffull))   // (already there)
+                if ((++spins & 1023u) == 0u && clock64() - t0 > 16000000000LL) { timed_out = true; break; }
+              total += (int)(unsigned)(w & 0xffffffffull);
+            }
+            // all particles were dead nranks micro-rounds ago (and all had been injected): nothing has moved since
+            live = (total == 0 && kn - (unsigned)S.nranks >= stagger) ? 0 : 1;
+          }
         }
         const unsigned cn = kn % 9u;
         const unsigned tn = cn * 2u + ((pin_mask(kn) >> cn) & 1u);
         const unsigned next_n = tn == tin ? 0u : min(__ldcg(Q.count + tn * 32u), (unsigned)Q.cap);
-        unsigned done = (live == 0 && kn >= stagger) ? 1u : 0u;
+        unsigned done = (live == 0 && (STRIPE || kn >= stagger)) ? 1u : 0u;
         if (!done && kn >= max_micro) { done = 1u; ctl->error = 2u; }
         if (timed_out) { done = 1u; ctl->error = 1u; }
         if (done) { ctl->micro = kn; ctl->tag_base = tag0 + kn + 2u; if (STRIPE) ctl->xseq = xseq0 + (unsigned long long)kn; }
