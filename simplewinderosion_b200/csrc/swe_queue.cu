@@ -437,6 +437,9 @@ __device__ __forceinline__ unsigned pin_mask(unsigned k) {
 #ifndef SWE_WARP_APPEND
 #define SWE_WARP_APPEND 0         // 1 = queue appends reserved per warp instead of per block (measured on B200: 1.5x SLOWER, the 18 counters become hot)
 #endif
+#ifndef SWE_STRIPE_SYS_ATOMICS
+#define SWE_STRIPE_SYS_ATOMICS 1  // stripes: a rank reserves slots in its OWN queues with system-scope atomics too (the neighbours' hand-offs are)
+#endif
 #ifndef SWE_PREFETCH
 #define SWE_PREFETCH 0            // 1 = blocks waiting at the grid barrier prefetch the next micro-round's heights into L2 (measured on B200: 8 % SLOWER)
 #endif
@@ -635,7 +638,7 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
       }
       __syncthreads();
       if (tid < 18 && s_cnt[tid] != 0u)
-        s_base[tid] = STRIPE ? atomicAdd_system(Q.count + tid * 32, s_cnt[tid]) : atomicAdd(Q.count + tid * 32, s_cnt[tid]);
+        s_base[tid] = (STRIPE && SWE_STRIPE_SYS_ATOMICS) ? atomicAdd_system(Q.count + tid * 32, s_cnt[tid]) : atomicAdd(Q.count + tid * 32, s_cnt[tid]);
       __syncthreads();
       if (target >= 0) {
         const unsigned slot = s_base[target] + rank;
@@ -680,7 +683,9 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
           const int slot = (int)(seq & 15ull);
           // ONE system-scope fence orders everything this GPU wrote in the micro-round (observed through the
           // arrival word) before the mailbox words; the words themselves are then plain system-scope stores
+#ifndef SWE_EXPERIMENT_NO_SYS_FENCE   // (measurement only: how much of the cross-GPU barrier is the fence)
           asm volatile("fence.acq_rel.sys;" ::: "memory");
+#endif
           for (int i = 0; i < S.nranks; i++) st_relaxed_sys_u64(S.mailbox[i] + slot * 8 + S.rank, word);
           const unsigned long long* mine = S.mailbox[S.rank];
           const long long t0 = clock64();
@@ -691,19 +696,27 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
               if ((++spins & 1023u) == 0u && clock64() - t0 > 16000000000LL) { timed_out = true; break; }   // ~8 s
           }
           live = 1;                                          // not decided yet
-          if (kn > (unsigned)S.nranks) {
+          if (kn > (unsigned)S.nranks && kn - (unsigned)S.nranks >= stagger) {     // (nothing to decide while particles are still injected)
             const unsigned long long seq_t = seq - (unsigned long long)S.nranks;
             const int slot_t = (int)(seq_t & 15ull);
             int total = 0;
-            for (int i = 0; i < S.nranks && !timed_out; i++) {
-              unsigned long long w;
+            // the eight words of a ring slot share one 64-byte line: four independent 16-byte loads, one latency
+            unsigned long long w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2)
+              asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i]), "=l"(w[i + 1]) : "l"(mine + slot_t * 8 + i) : "memory");
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if (i >= S.nranks) break;
               unsigned spins = 0;
-              while (((w = ld_acquire_sys_u64(mine + slot_t * 8 + i)) >> 32) != (seq_t & 0xffffffffull))   // (already there)
+              while ((w[i] >> 32) != (seq_t & 0xffffffffull)) {                     // (cannot happen: ranks drift < nranks)
+                w[i] = ld_acquire_sys_u64(mine + slot_t * 8 + i);
                 if ((++spins & 1023u) == 0u && clock64() - t0 > 16000000000LL) { timed_out = true; break; }
-              total += (int)(unsigned)(w & 0xffffffffull);
+              }
+              total += (int)(unsigned)(w[i] & 0xffffffffull);
             }
             // all particles were dead nranks micro-rounds ago (and all had been injected): nothing has moved since
-            live = (total == 0 && kn - (unsigned)S.nranks >= stagger) ? 0 : 1;
+            live = total == 0 ? 0 : 1;
           }
         }
         const unsigned cn = kn % 9u;
