@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -543,6 +544,10 @@ int colour_launch_persistent(swe_engine* e, int cycles) {
                          : (long long)e->sm_count * e->persist_blocks_per_sm;
   if (cap < 1) cap = 1;
   if (blocks > cap) blocks = cap;
+  if (const char* dbg = std::getenv("SWE_DEBUG_GRID")) {   // measurement aid: force the grid (barrier cost vs block count)
+    const long long g = std::atoll(dbg);
+    if (g >= 1 && g <= cap) blocks = g;
+  }
   const unsigned stagger = (unsigned)colour_stagger_micro(e, cycles);
   const unsigned max_micro = 64u * (unsigned)colour_main_micro(e, cycles);
   // claim tags grow by at most max_micro + 2 per call: clear the lattice before they could wrap

@@ -219,6 +219,7 @@ struct StripeQueues {
 constexpr int SWE_MAX_STRIPE_RANKS = 8;
 constexpr size_t SWE_PERSIST_BYTES = 4096;        // PersistCtl at 0, barrier mailbox at 1024
 constexpr size_t SWE_MAILBOX_OFFSET = 1024;
+constexpr size_t SWE_GROUP_OFFSET = 2048;         // copies 1..15 of the grid barrier's release word, 128 B apart
 int colour_persistent_blocks_per_sm(bool layered);
 int colour_persistent_blocks_per_sm_stripe();
 int colour_persistent_threads();

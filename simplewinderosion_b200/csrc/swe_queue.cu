@@ -336,6 +336,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   return v;
 }
 
+#ifndef SWE_RELEASE_COPIES
+#define SWE_RELEASE_COPIES 16u
+#endif
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// copy 0 is PersistCtl::release itself; copies 1.. live 128 bytes apart behind the stripe mailbox
+__device__ __forceinline__ unsigned long long* release_copy(PersistCtl* ctl, unsigned g) {
+  return g == 0u ? &ctl->release
+                 : reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ctl) + SWE_GROUP_OFFSET) + g * 16u;
+}
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -728,13 +739,18 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
         if (done) { ctl->micro = kn; ctl->tag_base = tag0 + kn + 2u; if (STRIPE) ctl->xseq = xseq0 + (unsigned long long)kn; }
         const unsigned long long gen = (rel >> 34) + 1ull;
         rel = (gen << 34) | ((unsigned long long)done << 32) | (unsigned long long)next_n;
+        // the release word is fanned out to 16 copies on separate 128-byte lines (separate L2 slices): hundreds of
+        // blocks polling ONE address saturate its slice and delay the very store they are waiting for
+        __threadfence();
+        for (unsigned g = 1; g < SWE_RELEASE_COPIES; g++) st_relaxed_u64(release_copy(ctl, g), rel);
         st_release_u64(&ctl->release, rel);
       } else {
         const unsigned long long gen = rel >> 34;
         const long long t0 = clock64();
         unsigned long long now;
         unsigned spins = 0;
-        while (((now = ld_acquire_u64(&ctl->release)) >> 34) == gen) {
+        const unsigned long long* my_rel = release_copy(ctl, blockIdx.x % SWE_RELEASE_COPIES);
+        while (((now = ld_acquire_u64(my_rel)) >> 34) == gen) {
           __nanosleep(40);
           if ((++spins & 1023u) == 0u && clock64() - t0 > 8000000000LL) {   // ~4 s watchdog: never hang the device
             ctl->error = 1u; now = ((gen + 1ull) << 34) | (3ull << 32); break;
