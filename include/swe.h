@@ -167,6 +167,12 @@ typedef struct swe_stats {
   uint64_t queue_dropped;  /* colour-queue scheduler: particles lost to a full queue (must be 0) */
 } swe_stats;
 
+/* Threading contract. An engine is not re-entrant: calls on ONE engine must come from one host thread at a time
+ * (like the reference, whose World is all statics: world.hpp:12-19,100). Different engines may be driven from
+ * different host threads concurrently (one thread per GPU is the natural in-process multi-GPU pattern); the
+ * library's one-time set-up is guarded. Work is enqueued on the engine's stream; swe_last_error() is per thread.
+ * Logical stripes sharing ONE GPU must be driven through swe_stripe_group_* from one thread (their kernels wait for
+ * each other on the device); keep them to at most 8 per device (CUDA_DEVICE_MAX_CONNECTIONS hardware queues). */
 typedef struct swe_engine swe_engine;
 
 /* ---- lifecycle -------------------------------------------------------------------- */
