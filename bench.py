@@ -422,6 +422,7 @@ def cfg4_strong(swe, rank: int, world: int, device: int, barrier, max_over_ranks
         for _ in range(steps):
             w.erode(particles, swe.MODE_PARALLEL)
         ev1.record(stream)
+    stream.synchronize()          # (see run_ours: never an NCCL barrier while stripe erodes are in flight)
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     st = w.stats()
@@ -562,6 +563,10 @@ def run_ours(args) -> None:
         for _ in range(args.steps):
             w.erode(particles_call, swe.MODE_PARALLEL)
         ev1.record(stream)
+    # the erodes are asynchronous and, on stripes, their persistent kernels wait for the other ranks ON THE DEVICE while
+    # holding every SM: drain them before the NCCL barrier, whose kernel could otherwise be scheduled between two ranks'
+    # launches and wait for a peer that is itself waiting for this GPU (the engine's watchdog would turn that into an error)
+    stream.synchronize()
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if rank == 0 else None

@@ -318,7 +318,11 @@ int swe_sync(swe_engine* e);
  * flags -- no host round trip per exchange. Every rank must issue the same sequence of
  * swe_erode / swe_cascade_sweep / swe_stripe_sync_halos calls with the same arguments
  * (swe_max_excess on a stripe wants a swe_stripe_sync_halos first: it reads one ghost row);
- * `cycles` of swe_erode is the GLOBAL particle count of the call. Host transfers
+ * `cycles` of swe_erode is the GLOBAL particle count of the call. With the colour-queue schedule (swe_stripe_connect_ring)
+ * a stripe's swe_erode is ONE persistent kernel that holds the whole GPU and waits for the other ranks' kernels on the
+ * device: do not enqueue another inter-GPU blocking operation (an NCCL collective, ...) on any stream while such calls
+ * are in flight -- synchronise the engine's stream first, or the two can wait for each other (the engine's watchdog then
+ * ends the call with SWE_ERR_STATE after a few seconds instead of hanging). Host transfers
  * (swe_upload_plane, swe_download_plane, swe_sum_plane, ...) act on the owned rows only. Parallel mode only.
  *   1. swe_stripe_create on every rank (max_particles >= the largest global `cycles`; the same
  *      value on every rank)
