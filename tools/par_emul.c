@@ -267,7 +267,7 @@ long long emul_erode_queues(swo_world* w, int cycles, int stagger, int order_kin
   int live = n;
   static const int ord0[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};      /* z fastest */
   static const int ord1[9] = {0, 3, 6, 1, 4, 7, 2, 5, 8};      /* x fastest: a +x mover is served again at once */
-  const int* order = order_kind ? ord1 : ord0;
+  const int* order = (order_kind & 1) ? ord1 : ord0;
   while (live > 0) {
     const int c = order[k % 9];
     const int stamp = (int)(k + 1);
@@ -280,10 +280,16 @@ long long emul_erode_queues(swo_world* w, int cycles, int stagger, int order_kin
       const size_t ind = (size_t)ix * nz + iz;
       if (claim[ind] == stamp) continue;
       claim[ind] = stamp;
-      int cell;
-      if (!fly_nc(w, &q[i], NULL, &cell)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
-      steps++;
-      swo_cascade(w, ix, iz);
+      /* order_kind >= 16: a particle that stays on its cell keeps its claim and steps again at once, up to
+       * (order_kind >> 4) steps per micro-round (it owns the cell and its 3x3 block for the whole micro-round) */
+      const int reps = order_kind >= 16 ? (order_kind >> 4) : 1;
+      for (int rep = 0; rep < reps; rep++) {
+        int cell;
+        if (!fly_nc(w, &q[i], NULL, &cell)) { alive[i] = 0; live--; lost += (double)q[i].sediment; break; }
+        steps++;
+        swo_cascade(w, ix, iz);
+        if ((int)roundf(q[i].pos[0]) != ix || (int)roundf(q[i].pos[2]) != iz) break;
+      }
     }
     k++;
   }

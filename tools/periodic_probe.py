@@ -1,5 +1,11 @@
-import sys, numpy as np
-sys.path.insert(0, "/root/repo")
+"""GPU probe: parallel mode on a torus (SWE_OPT_PERIODIC) against the periodic oracle port, for several staggers.
+    python tools/periodic_probe.py"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import simplewinderosion_b200 as swe
 from simplewinderosion_b200 import analysis, generate
 from tests.oracle_lib import PortWorld
