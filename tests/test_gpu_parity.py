@@ -295,6 +295,14 @@ def test_strided_aos_roundtrip():
     w2.upload_cells(cells)
     assert w2.download_cells().tobytes() == cells.tobytes()
     assert np.array_equal(w2.download(swe.MOMENTUMY_TRACK), cells["momentumy_track"])
+    # the per-frame read-back of the render loop in one call (SimpleWindErosion.cpp:219-230)
+    frame = w2.download_frame()
+    for i, name in enumerate(("height", "massflow", "momentumx", "momentumy", "momentumz")):
+        assert np.array_equal(frame[i], cells[name]), name
+    # options read back what was set
+    for opt, val in ((swe.OPT_SCHEDULE, 1), (swe.OPT_STAGGER_ROUNDS, 33), (swe.OPT_PERSISTENT, 0), (swe.OPT_CALL_BATCHES, 5)):
+        w2.set_option(opt, val)
+        assert w2.get_option(opt) == val
 
 
 def test_error_paths():
