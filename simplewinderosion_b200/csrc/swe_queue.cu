@@ -494,13 +494,15 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
   const int claim_pitch = (nz + 2) / 3;
   const unsigned long long keep = l2_policy_keep(), stream = l2_policy_stream();
   unsigned n_in = 0u;                                     // micro-round 0: all queues are empty
+  // per-call uniforms kept out of the micro-round loop (they showed up as ~130 instructions per particle step)
+  const long long seam_rows = (long long)(m.nx - 1) * (long long)nz;     // periodic: offset from the first to the last row
+  const unsigned inj_q = stagger ? (unsigned)n_total / stagger : 0u, inj_r = stagger ? (unsigned)n_total % stagger : 0u;
+  unsigned pin = 0u, colour = 0u;                          // parity bits of the queues' input sides; colour served = k % 9
 
   for (unsigned k = 0;; k++) {
-    const unsigned colour = k % 9u;
-    const unsigned pin = pin_mask(k);
     const unsigned tin = colour * 2u + ((pin >> colour) & 1u);
     const unsigned tag = tag0 + k + 1u;
-    const unsigned inj_count = k < stagger ? ((unsigned)n_total - k + stagger - 1u) / stagger : 0u;
+    const unsigned inj_count = k < stagger ? inj_q + (k < inj_r ? 1u : 0u) : 0u;   // ids k + j * stagger < n_total
     const unsigned total = n_in + inj_count;
     const float4* qa = Q.a + (size_t)tin * (size_t)Q.cap;
     const float4* qb = Q.b + (size_t)tin * (size_t)Q.cap;
@@ -529,9 +531,9 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
         // periodic map wraps at the seam
         const bool rem_m = STRIPE && xm && ix - 1 < S.own_lo, rem_p = STRIPE && xp && ix + 1 >= S.own_hi;
         float* row_m = rem_m ? S.below_h + (size_t)(ix - 1 - S.below_x0) * (size_t)nz + iz
-                             : ((per && ix == 0) ? hp + (size_t)(m.nx - 1) * (size_t)nz : hp - nz);
+                             : ((per && ix == 0) ? hp + seam_rows : hp - nz);
         float* row_p = rem_p ? S.above_h + (size_t)(ix + 1 - S.above_x0) * (size_t)nz + iz
-                             : ((per && ix == m.nx - 1) ? hp - (size_t)(m.nx - 1) * (size_t)nz : hp + nz);
+                             : ((per && ix == m.nx - 1) ? hp - seam_rows : hp + nz);
         const int zo_m = (per && iz == 0) ? nz - 1 : -1, zo_p = (per && iz == nz - 1) ? 1 - nz : 1;
         // one claim word per 3x3 lattice cell: the cells of the served colour map one-to-one onto it, the tags
         // grow with every micro-round, so the table (1/9 of a plane: L2-resident) serves all colours.
@@ -752,8 +754,8 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
             live = total == 0 ? 0 : 1;
           }
         }
-        const unsigned cn = kn % 9u;
-        const unsigned tn = cn * 2u + ((pin_mask(kn) >> cn) & 1u);
+        const unsigned cn = colour == 8u ? 0u : colour + 1u;
+        const unsigned tn = cn * 2u + (((pin ^ (1u << colour)) >> cn) & 1u);
         const unsigned next_n = tn == tin ? 0u : min(__ldcg(Q.count + tn * 32u), (unsigned)Q.cap);
         unsigned done = (live == 0 && (STRIPE || kn >= stagger)) ? 1u : 0u;
         if (!done && kn >= max_micro) { done = 1u; ctl->error = 2u; }
@@ -787,8 +789,8 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
       // a block that waits at the grid barrier pulls the heights its threads will need in the NEXT micro-round into
       // L2 (the entries already in that queue; addresses only -- nothing is consumed, so a record that is still
       // being written by a slower block is harmless)
-      const unsigned kn = k + 1u, cn = kn % 9u;
-      const unsigned tn = cn * 2u + ((pin_mask(kn) >> cn) & 1u);
+      const unsigned cn = colour == 8u ? 0u : colour + 1u;
+      const unsigned tn = cn * 2u + (((pin ^ (1u << colour)) >> cn) & 1u);
       const unsigned jn = blockIdx.x * PNT + (unsigned)tid;
       if (jn < min(__ldcg(Q.count + tn * 32u), (unsigned)Q.cap)) {
         const size_t o = (size_t)tn * (size_t)Q.cap + jn;
@@ -810,6 +812,8 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
     rel = s_rel;
     n_in = (unsigned)(rel & 0xffffffffull);
     if ((rel >> 32) & 1ull) break;
+    pin ^= 1u << colour;                                   // the served colour's input side flips
+    colour = colour == 8u ? 0u : colour + 1u;
   }
 
   for (int o = 16; o > 0; o >>= 1) {
