@@ -451,6 +451,9 @@ __device__ __forceinline__ unsigned pin_mask(unsigned k) {
 #ifndef SWE_STRIPE_SYS_ATOMICS
 #define SWE_STRIPE_SYS_ATOMICS 1  // stripes: a rank reserves slots in its OWN queues with system-scope atomics too (the neighbours' hand-offs are)
 #endif
+#ifndef SWE_PREFETCH_NEXT
+#define SWE_PREFETCH_NEXT 0       // 1 = a particle prefetches the rows of its NEXT cell into L2 when its step ends (measured: no gain)
+#endif
 #ifndef SWE_MULTI_STEP
 #define SWE_MULTI_STEP 1u         // steps a particle may take per turn while it stays on its cell (4: 32 % fewer micro-rounds and a better
                                   // match with the oracle, but 1.3-1.6x SLOWER on B200: one repeating lane holds its warp, and every
@@ -611,6 +614,16 @@ colour_persistent_kernel(MapView m, ParConst C, block::Thr T, QueueView Q, unsig
             rb = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
             const unsigned cn = (unsigned)cell_colour(jx, jz);
             target = (int)(cn * 2u + (((pin >> cn) & 1u) ^ (cn == colour ? 1u : 0u)));
+#if SWE_PREFETCH_NEXT
+            // the particle knows where it will stand at its next turn (3-9 micro-rounds from now): pull that cell's
+            // rows into L2 now, off the critical path of that micro-round (no load, no register: prefetch only)
+            if (!STRIPE || (jx > S.own_lo && jx + 1 < S.own_hi)) {
+              const float* nh = m.height + m.idx(jx, jz);
+              prefetch_l2_keep(nh);
+              if (jx > 0) prefetch_l2_keep(nh - nz);
+              if (jx + 1 < m.nx) prefetch_l2_keep(nh + nz);
+            }
+#endif
             if (STRIPE && (jx < S.own_lo || jx >= S.own_hi)) {
               // hand the particle to the owner of its next cell: append to the neighbour's queue of that colour
               const bool dn = jx < S.own_lo;
