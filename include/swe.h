@@ -118,7 +118,10 @@ typedef enum swe_option {
    * read-backs, whole-map sweeps (per-colour kernels) and the colour-queue parallel mode; sweeps and the parallel
    * mode need map edges that are multiples of 3 (the nine-colour order on a torus). Single-GPU engines without a
    * rock plane. Default 0. */
-  SWE_OPT_PERIODIC = 10
+  SWE_OPT_PERIODIC = 10,
+  /* Tile-resident schedule (SWE_OPT_SCHEDULE = 2): rounds (nine micro-rounds each) a CTA keeps its tile in shared
+   * memory before the particles are re-sorted into the next, shifted tiling. Default 16, range [1, 64]. */
+  SWE_OPT_TILE_ROUNDS = 11
 } swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:

@@ -95,6 +95,10 @@ struct swe_engine {
   int coop_ok = 0;                    // device supports cooperative launches
   uint64_t claim_tags_used = 0;       // upper bound of the claim tags handed out since the last clearing
   int persist_blocks_per_sm = 0;
+  TileSched ts{};                     // tile-resident scheduler (swe_tile.cu): records sorted by tile
+  int opt_tile_rounds = 16;           // rounds (nine micro-rounds each) a CTA keeps its tile per super-round
+  int tile_pcap[2] = {0, 0};          // shared-memory record capacity the fly kernel is configured for [layered]
+  int smem_optin = 0;
   CallCtl* d_ctl = nullptr;           // seed / call index of the current call (read by graph-replayed kernels)
   struct CachedGraph { uint64_t key; cudaGraphExec_t exec; };
   std::vector<CachedGraph> graphs;
@@ -316,7 +320,7 @@ StripeRound stripe_round_ctx(swe_engine* e) {
 }
 
 bool stripe_uses_colour_queues(const swe_engine* e) {
-  return e->st.enabled && e->st.ring && e->opt_schedule == 0 && e->coop_ok && e->st.persist_blocks_per_sm > 0;
+  return e->st.enabled && e->st.ring && e->opt_schedule != 1 && e->coop_ok && e->st.persist_blocks_per_sm > 0;
 }
 
 int stripe_erode_begin(swe_engine* e, int cycles) {
@@ -641,6 +645,84 @@ int erode_colour(swe_engine* e, int cycles) {
   return erode_epilogue(e);
 }
 
+// ---- tile-resident scheduler (swe_tile.cu) -----------------------------------------------------------
+int need_tiles(swe_engine* e, int cycles) {
+  const int cap = ((cycles > 1024 ? cycles : 1024) + 255) / 256 * 256;
+  if (!e->ts.count) {
+    const int mt = tile_max_tiles(e->m.nx, e->m.nz);
+    const size_t words = (size_t)mt + 1;
+    SWE_CUDA(cudaMalloc(&e->ts.count, 4 * words * sizeof(unsigned) + 64));
+    SWE_CUDA(cudaMemsetAsync(e->ts.count, 0, 4 * words * sizeof(unsigned) + 64, e->stream));
+    e->ts.base[0] = e->ts.count + words; e->ts.base[1] = e->ts.count + 2 * words;
+    e->ts.cursor = e->ts.count + 3 * words; e->ts.info = e->ts.count + 4 * words;
+    e->ts.max_tiles = mt;
+  }
+  if (e->ts.cap >= cap) return SWE_OK;
+  SWE_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(e->ts.pa[0]);
+  e->ts.pa[0] = nullptr; e->ts.cap = 0;
+  SWE_CUDA(cudaMalloc(&e->ts.pa[0], 4 * (size_t)cap * sizeof(float4)));
+  e->ts.pa[1] = e->ts.pa[0] + cap; e->ts.pb[0] = e->ts.pa[0] + 2 * (size_t)cap; e->ts.pb[1] = e->ts.pa[0] + 3 * (size_t)cap;
+  e->ts.cap = cap;
+  return SWE_OK;
+}
+
+// Whole particle phase on the tile-resident schedule: particle i becomes active at round i * S / n (S = the
+// stagger of the colour-queue scheduler), at the granularity of a super-round; super-rounds are enqueued until
+// the device reports that no record is left (checked every few super-rounds once the injection is over).
+int erode_tile(swe_engine* e, int cycles) {
+  if (int rc = need_tiles(e, cycles)) return rc;
+  const bool layered = e->m.rock != nullptr;
+  const int K = e->opt_tile_rounds;
+  const int life = e->p.max_age + 2;
+  long long S = colour_stagger_micro(e, cycles) / 9;      // rounds
+  const int TE = tile_edge();
+  // expected particles per tile while the injection runs (Poisson): mean + 5 sigma + slack stays on chip; a tile
+  // with more than that parks the excess for a super-round (never lost)
+  const double density = (double)cycles / ((double)e->m.nx * (double)e->m.nz);
+  const double lam = density * TE * TE * (S > 0 ? (double)life / (double)(S + life) : 1.0);
+  int pcap = ((int)(lam + 5.0 * std::sqrt(lam) + 64.0) + 63) / 64 * 64;
+  if (const char* dbg = std::getenv("SWE_DEBUG_TILE_PCAP")) { const int v = std::atoi(dbg); if (v >= 64) pcap = v / 64 * 64; }
+  const int pmax = tile_max_pcap(layered, e->smem_optin > 0 ? e->smem_optin : 49152);
+  if (pmax < 64) return fail(SWE_ERR_STATE, "tile scheduler: not enough shared memory per block");
+  if (pcap < 128) pcap = 128;
+  if (pcap > pmax) pcap = pmax;
+  if (e->tile_pcap[layered] != pcap) {
+    const cudaError_t err = tile_configure(layered, pcap);
+    if (err != cudaSuccess) return fail(SWE_ERR_CUDA, "tile kernel configuration failed: %s", cudaGetErrorString(err));
+    e->tile_pcap[layered] = pcap;
+  }
+  if (int rc = erode_prologue(e)) return rc;
+  const long long n = cycles;
+  auto started_before = [&](long long round) -> int {     // particles with start round floor(i S / n) < round
+    if (S <= 0) return round > 0 ? (int)n : 0;
+    const long long v = (round * n + S - 1) / S;
+    return (int)(v > n ? n : v);
+  };
+  const int inj_srs = S > 0 ? (int)((S + K - 1) / K) : 1;  // super-rounds that receive new particles
+  int nl = launch_tile_super_round(e->m, e->p, e->ts, -1, K, pcap, 0, started_before(K), e->seed, e->call_index,
+                                   e->d_stats, e->stream);
+  int first_check = inj_srs + (life * 6 / 10 + K - 1) / K;
+  const int max_srs = inj_srs + 64 * ((life + K - 1) / K) + 64;
+  int s = 0;
+  for (;; s++) {
+    if (s >= max_srs) return fail(SWE_ERR_STATE, "tile scheduler: particles still alive after %d super-rounds", s);
+    const int lo = started_before((long long)(s + 1) * K), hi = started_before((long long)(s + 2) * K);
+    nl += launch_tile_super_round(e->m, e->p, e->ts, s, K, pcap, lo, hi, e->seed, e->call_index, e->d_stats, e->stream);
+    if (s + 1 >= first_check && (s + 1 - first_check) % 4 == 0) {
+      if (int rc = check_launch(e, "tile super-round", nl)) return rc;
+      nl = 0;
+      unsigned info[2];
+      SWE_CUDA(cudaMemcpyAsync(info, e->ts.info, sizeof info, cudaMemcpyDeviceToHost, e->stream));
+      SWE_CUDA(cudaStreamSynchronize(e->stream));
+      if (info[1] != 0u) return fail(SWE_ERR_STATE, "tile scheduler dropped %u particle records", info[1]);
+      if (info[0] == 0u && s + 1 >= inj_srs) { s++; break; }
+    }
+  }
+  e->last_micro_rounds = s * 9 * K;
+  return erode_epilogue(e);
+}
+
 int erode_prologue(swe_engine* e) {   // (the timers of an earlier call are read at the next synchronising entry point)
   SWE_CUDA(cudaEventRecord(e->ev_a, e->stream));
   SWE_CUDA(cudaMemsetAsync(e->m.track, 0, e->cells() * sizeof(float4), e->stream));   // world.hpp:38-44
@@ -802,10 +884,11 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
     }
   }
   make_height_tensor_map(e->m, &e->tmap);   // optional: plain-load kernels are used when it fails
-  preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe(); preload_noise(); preload_queue();
+  preload_det(); preload_cascade(); preload_fields(); preload_par(); preload_stripe(); preload_noise(); preload_queue(); preload_tile();
   if (cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || e->sm_count < 1) e->sm_count = 148;
   if (cudaDeviceGetAttribute(&e->coop_ok, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) e->coop_ok = 0;
   e->persist_blocks_per_sm = colour_persistent_blocks_per_sm(false);
+  if (cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) e->smem_optin = 49152;
   (void)cudaGetLastError();
   (void)cudaGetLastError();
   launch_det_srand(e->d_rng, 1u, e->stream);
@@ -846,6 +929,7 @@ void swe_destroy(swe_engine* e) {
   cudaFree(e->tsc.stage); cudaFree(e->tsc.flags); cudaFree(e->d_rock); cudaFree(e->d_ctl);
   cudaFree(e->cq.a); cudaFree(e->cq.b); cudaFree(e->cq.count); cudaFree(e->cq.claim);
   cudaFree(e->cq.claim32); cudaFree(e->cq.persist);
+  cudaFree(e->ts.count); cudaFree(e->ts.pa[0]);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : e->st.ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1098,13 +1182,15 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
     // the nine-colour order is conflict-free on a torus only if both edges are multiples of 3
     if (e->m.nx % 3 || e->m.nz % 3 || e->m.nx < 6 || e->m.nz < 6)
       return fail(SWE_ERR_STATE, "periodic parallel mode needs map edges that are multiples of 3 (got %dx%d)", e->m.nx, e->m.nz);
-    if (e->opt_schedule != 0 || !e->opt_persistent || !e->coop_ok)
+    if (e->opt_schedule == 1 || !e->opt_persistent || !e->coop_ok)
       return fail(SWE_ERR_STATE, "periodic parallel mode runs the colour-queue schedule in its persistent form only");
   }
   if (mode == SWE_MODE_DETERMINISTIC && e->m.rock)   // (checked before anything is enqueued: a failed call leaves the engine untouched)
     return fail(SWE_ERR_STATE, "deterministic mode reproduces the reference, which has no rock layer");
-  if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_schedule == 0)
-    return erode_colour(e, cycles);
+  if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_schedule == 2 && !e->m.periodic)
+    return erode_tile(e, cycles);
+  if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_schedule != 1)
+    return erode_colour(e, cycles);   // (also the tile schedule on a torus: tiles do not wrap)
   if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_cuda_graph && !e->opt_kernel_timing)
     return erode_parallel_graph(e, cycles);
   // world.hpp:38-44: reset the four track members of every cell
@@ -1639,6 +1725,7 @@ int swe_get_option(const swe_engine* e, int option, int* value) {
     case SWE_OPT_STAGGER_ROUNDS: *value = e->opt_stagger; return SWE_OK;
     case SWE_OPT_PERSISTENT: *value = e->opt_persistent; return SWE_OK;
     case SWE_OPT_PERIODIC: *value = e->m.periodic; return SWE_OK;
+    case SWE_OPT_TILE_ROUNDS: *value = e->opt_tile_rounds; return SWE_OK;
     default: return fail(SWE_ERR_INVALID, "unknown option %d", option);
   }
 }
@@ -1662,7 +1749,7 @@ int swe_set_option(swe_engine* e, int option, int value) {
       if (value < 1 || value > 64) return fail(SWE_ERR_INVALID, "call batches must be in [1, 64]");
       e->opt_call_batches = value; return SWE_OK;
     case SWE_OPT_SCHEDULE:
-      if (value < 0 || value > 1) return fail(SWE_ERR_INVALID, "schedule must be 0 (colour queues) or 1 (lock-step rounds)");
+      if (value < 0 || value > 2) return fail(SWE_ERR_INVALID, "schedule must be 0 (colour queues), 1 (lock-step rounds) or 2 (tile-resident)");
       e->opt_schedule = value; return SWE_OK;
     case SWE_OPT_PERSISTENT:
       e->opt_persistent = value ? 1 : 0; return SWE_OK;
@@ -1674,6 +1761,9 @@ int swe_set_option(swe_engine* e, int option, int value) {
       for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);   // captured launches carry the MapView by value
       e->graphs.clear();
       return SWE_OK;
+    case SWE_OPT_TILE_ROUNDS:
+      if (value < 1 || value > 64) return fail(SWE_ERR_INVALID, "tile rounds must be in [1, 64]");
+      e->opt_tile_rounds = value; return SWE_OK;
     case SWE_OPT_STAGGER_ROUNDS:
       if (value < -1 || value > (1 << 20)) return fail(SWE_ERR_INVALID, "stagger rounds must be -1 (auto) or in [0, 2^20]");
       e->opt_stagger = value; return SWE_OK;

@@ -229,6 +229,27 @@ cudaError_t launch_colour_persistent(const MapView& m, const swe_params& p, cons
                                      bool cooperative = true);
 void preload_queue();
 
+// tile-resident scheduler of the single-GPU parallel erode: swe_tile.cu
+// Particle records sorted by tile (one contiguous segment per tile of the current tiling), ping-pong.
+struct TileSched {
+  float4* pa[2];            // records {pos.x, pos.y, pos.z, sediment}
+  float4* pb[2];            // records {speed.x, speed.y, speed.z, age (int bits; < 0 = dead)}
+  unsigned* count;          // [max_tiles + 1] particles per tile of the NEXT tiling (cleared by the scan)
+  unsigned* base[2];        // [max_tiles + 1] segment bases (exclusive prefix sums); base[nt] = records in the segments
+  unsigned* cursor;         // [max_tiles] scatter cursors
+  unsigned* info;           // [0] records placed for the next super-round, [1] records dropped (must stay 0)
+  int cap;                  // records per array
+  int max_tiles;
+};
+int tile_edge();
+int tile_threads();
+int tile_max_tiles(int nx, int nz);
+int tile_max_pcap(bool layered, int smem_optin);
+cudaError_t tile_configure(bool layered, int pcap);
+int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSched& S, int s, int K, int pcap,
+                            int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st);
+void preload_tile();
+
 // stripe exchange primitives: swe_stripe.cu
 void launch_stripe_push(const float* src_h, float* dst_h, const unsigned char* src_s, unsigned char* dst_s,
                         size_t cells, cudaStream_t st);

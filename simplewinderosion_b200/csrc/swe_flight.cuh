@@ -1,6 +1,7 @@
 // swe_flight.cuh -- pieces shared by the parallel flight kernels (swe_par.cu: round-synchronous
-// pipeline of the stripe engines; swe_queue.cu: colour-queue scheduler of the single-GPU engine):
-// constants, counter-based RNG, atomic scatter helpers, the stratified spawn.
+// pipeline; swe_queue.cu: colour-queue scheduler; swe_tile.cu: tile-resident scheduler):
+// constants, counter-based RNG, atomic scatter helpers, the spawn, and Wind::fly for a particle
+// that owns its cell (fly_owned).
 #pragma once
 #include <math.h>
 
@@ -72,6 +73,78 @@ __device__ __forceinline__ void spawn_position_iid(int i, int nx, int nz, uint2 
   const uint4 r = philox4x32_10(make_uint4((uint32_t)i, call, 0u, 0x6u), key);
   px = (float)__umulhi(r.x, (unsigned)nx) + (float)__umulhi(r.z, 1000u) / 1000.0f;
   pz = (float)__umulhi(r.y, (unsigned)nz) + (float)__umulhi(r.w, 1000u) / 1000.0f;
+}
+
+__device__ __forceinline__ int cell_colour(int x, int z) { return (x % 3) * 3 + (z % 3); }
+
+// Wind::fly (wind.hpp:28-112) for a particle that owns its cell: heights come in registers, the
+// erosion amount goes out. Returns dh: the centre cell loses dh (wind.hpp:110-111).
+__device__ __forceinline__ float fly_owned(const ParConst& C, PState& q, float hc, float hxm, float hxp, float hzm,
+                                           float hzp, bool xm, bool xp, bool zm, bool zp, uint4 rng_ctr, uint2 key,
+                                           float& collision_out, float& tx, float& ty, float& tz, float& tsed) {
+  float nxv, nyv, nzv;   // quad::_normal, closed form (cellpool.h:200-223; see swe_par.cu)
+  {
+    const float S = C.mapscale;
+    const float cz = (zp ? 1.0f : 0.0f) + (zm ? 1.0f : 0.0f);
+    const float cx = (xp ? 1.0f : 0.0f) + (xm ? 1.0f : 0.0f);
+    nxv = S * cz * ((hxm - hc) - (hxp - hc));
+    nyv = cx * cz;
+    nzv = S * cx * ((hzm - hc) - (hzp - hc));
+    const float l2 = nxv * nxv + nyv * nyv + nzv * nzv;
+    if (l2 > 0.0f) { const float il = rsqrtf(l2); nxv *= il; nyv *= il; nzv *= il; }
+  }
+  if (q.age == 0 || q.py < hc) q.py = hc;                                         // :42-43
+  q.age++;                                                                        // :45 (age limit: caller)
+  const float hfac = __expf(-(q.py - hc) * C.inv_boundarylayer);                 // :50
+  float shadow = C.pnx * nxv + C.pny * nyv + C.pnz * nzv;                         // :56-59
+  shadow = 1.0f - fmaxf(shadow, 0.0f);
+  float sx = q.sx, sy = q.sy, sz = q.sz;
+  {
+    const float k = 0.1f + 0.9f * shadow;                                         // :61
+    sx += 0.05f * (k * C.px - sx);
+    sy += 0.05f * (k * C.py - sy);
+    sz += 0.05f * (k * C.pz - sz);
+  }
+  if (q.py > hc) sy -= C.gravity * q.sed;                                         // :65-66
+  float collision;
+  {
+    const float il = rsqrtf(sx * sx + sy * sy + sz * sz);                         // :70-71
+    collision = fmaxf(-(sx * nxv + sy * nyv + sz * nzv) * il, 0.0f);
+  }
+  {
+    const float k = 1.0f - collision;                                             // :75  n x (a x n)
+    const float ax = k * sx, ay = k * sy, az = k * sz;
+    const float nn = nxv * nxv + nyv * nyv + nzv * nzv;
+    const float na = nxv * ax + nyv * ay + nzv * az;
+    const float rx = ax * nn - nxv * na, ry = ay * nn - nyv * na, rz = az * nn - nzv * na;
+    const float w = shadow * hfac;                                                // :79
+    sx += 0.9f * (shadow * (C.px * (1.0f - w) + rx * w) - sx);
+    sy += 0.9f * (shadow * (C.py * (1.0f - w) + ry * w) - sy);
+    sz += 0.9f * (shadow * (C.pz * (1.0f - w) + rz * w) - sz);
+  }
+  {
+    const float amp = 0.1f * hfac * collision;                                    // :83
+    if (amp > 0.0f) {
+      const uint4 r = philox4x32_10(rng_ctr, key);
+      const float s = amp * (1.0f / 500.0f);
+      sx += s * ((float)__umulhi(r.x, 1001u) - 500.0f);
+      sy += s * ((float)__umulhi(r.y, 1001u) - 500.0f);
+      sz += s * ((float)__umulhi(r.z, 1001u) - 500.0f);
+    }
+  }
+  {
+    const float f = 1.0f - 0.3f * q.sed;                                          // :87
+    sx *= f; sy *= f; sz *= f;
+  }
+  q.px += sx; q.py += sy; q.pz += sz;                                             // :91
+  q.sx = sx; q.sy = sy; q.sz = sz;
+  tx = sx; ty = sy; tz = sz; tsed = q.sed;                                        // :93-96
+  const float len = sqrtf(sx * sx + sy * sy + sz * sz);
+  const float force = fmaxf(-(sx * nxv + sy * nyv + sz * nzv), 0.0f);             // :100-102
+  const float lift = (1.0f - collision) * len;                                    // :104
+  const float capacity = hfac * (force + 0.02f * lift);                           // :106
+  collision_out = collision;
+  return C.suspension * (capacity - q.sed);                                       // :110
 }
 
 static inline ParConst make_const(const swe_params& p) {

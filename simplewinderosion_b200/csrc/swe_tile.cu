@@ -1,0 +1,482 @@
+// swe_tile.cu -- parallel World::erode of a single-GPU engine: the TILE-RESIDENT scheduler.
+//
+// Same per-particle semantics as the colour-queue scheduler (swe_queue.cu): a particle claims its cell for a
+// micro-round of its cell's colour, flies ONE Wind::fly step (wind.hpp:28-112) against the current heights,
+// erodes / deposits, and runs World::cascade on its 3x3 block at once (wind.hpp:114) -- the reference's order of
+// operations -- and the call's particles are injected staggered over S rounds. What changes is WHERE a
+// micro-round is synchronised. The colour-queue kernel meets at a grid barrier after every micro-round (13,500
+// dependent ~21 us steps per headline call: latency-bound, 2.5x the algorithmic DRAM traffic in scattered
+// 32-byte sectors). Here the map is cut into T x T tiles and ONE CTA owns one tile for a SUPER-ROUND of K rounds
+// (9 K micro-rounds behind __syncthreads): the tile's heights and its particles live in shared memory, the
+// height plane is read and written once per super-round with coalesced rows, a particle record makes one
+// round trip to HBM per super-round instead of one per step, and independent CTAs hide each other's latency.
+//
+// Conflict-freedom without halos or atomics: a particle is served only while its cell lies in the INTERIOR of
+// the tile (>= 1 cell from the tile's edges; map edges excepted), so the 3x3 block it reads and writes never
+// leaves the tile and tiles never touch each other's cells. A particle that reaches the border ring -- or
+// leaves the tile in one step -- is PARKED until the next super-round, whose tiling is shifted by T/3 in both
+// directions. Three tilings take turns; a cell lies on the x-ring of at most one of them and on the z-ring of
+// at most one, so every cell is interior at least every third super-round. T and the shifts are multiples of
+// 3: the tile-local colouring is the global one and one claim word per 3x3 lattice cell serves all colours.
+// Every schedule this produces is a sequentially consistent interleaving of whole particle steps, like the
+// colour queues'. tools/par_emul.c (mode D) runs this schedule on the oracle's physics on the CPU: against
+// the one-after-another reference it is statistically as close as the colour queues.
+//
+// Per super-round s (host loop, three launches):
+//   tile_fly_kernel   one CTA per tile of tiling s: load tile + its particle segment, 9 K micro-rounds, store;
+//                     counts, per tile of tiling s+1, the surviving particles (and, in extra CTAs, the
+//                     particles injected for s+1)
+//   tile_scan_kernel  exclusive prefix sum of those counts = segment bases of tiling s+1
+//   tile_scatter_kernel  moves every surviving record (and the new particles) into its tile's segment
+#include "swe_block.cuh"
+#include "swe_flight.cuh"
+
+namespace swe {
+
+#ifndef SWE_TILE_T
+#define SWE_TILE_T 60              // tile edge in cells (multiple of 3)
+#endif
+#ifndef SWE_TILE_THREADS
+#define SWE_TILE_THREADS 128
+#endif
+#ifndef SWE_TILE_RECORDS_L2
+#define SWE_TILE_RECORDS_L2 0      // 1 = the particle records stay in global memory (L2) during a super-round instead of
+                                   // shared memory: 3 instead of 35 bytes of shared memory per particle, more CTAs per SM
+#endif
+static_assert(SWE_TILE_T % 3 == 0 && SWE_TILE_T >= 12, "tile edge: multiple of 3");
+constexpr bool RL2 = SWE_TILE_RECORDS_L2 != 0;
+constexpr unsigned DEAD = 0x0eu;     // pcol value of a particle that died in this super-round
+constexpr int TT = SWE_TILE_T;
+constexpr int TNT = SWE_TILE_THREADS;
+constexpr int TLAT = TT / 3;
+constexpr unsigned PARKED = 0x0fu;   // pcol value of a particle that is not served (parked, dead, not loaded)
+
+int tile_edge() { return TT; }
+int tile_threads() { return TNT; }
+
+__device__ __forceinline__ int tile_of(int ix, int iz, int off, int ntz) { return ((ix + off) / TT) * ntz + (iz + off) / TT; }
+
+// one atomic per warp and destination tile
+__device__ __forceinline__ void count_dest(unsigned* count, int dest, bool active) {
+  const unsigned has = __ballot_sync(0xffffffffu, active);
+  if (active) {
+    const unsigned grp = __match_any_sync(has, dest);
+    if ((int)(threadIdx.x & 31u) == __ffs(grp) - 1) atomicAdd(count + dest, (unsigned)__popc(grp));
+  }
+}
+
+// colour under which the particle standing on (ix, iz) is served by the tile with origin (x0, z0), or PARKED
+__device__ __forceinline__ unsigned service_colour(int ix, int iz, int x0, int z0, int nx, int nz) {
+  const int lx = ix - x0, lz = iz - z0;
+  if ((unsigned)lx >= (unsigned)TT || (unsigned)lz >= (unsigned)TT) return PARKED;          // left the tile
+  if ((lx == 0 && ix != 0) || (lx == TT - 1 && ix != nx - 1) || (lz == 0 && iz != 0) || (lz == TT - 1 && iz != nz - 1))
+    return PARKED;                                                                         // border ring
+  return (unsigned)((lx % 3) * 3 + lz % 3);
+}
+
+struct TileGeom {
+  int off_cur, ntx_cur, ntz_cur;     // tiling served now: tile (a, b) covers [a T - off, (a + 1) T - off) x [b T - off, ...)
+  int off_next, ntx_next, ntz_next;  // tiling of the next super-round
+  int cur;                           // index of the record arrays / base array that hold the current segments
+  int inj_lo, inj_hi;                // particle ids injected for the NEXT super-round
+  unsigned micro0;                   // number of the super-round's first micro-round within the call (RNG counter)
+  int K;                             // rounds per super-round
+  int pcap;                          // particles a tile keeps in shared memory (the rest of its segment stays parked)
+};
+
+template <bool LAYERED>
+__global__ void __launch_bounds__(SWE_TILE_THREADS)
+tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, uint2 key, uint32_t call, DevStats* stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = (int)threadIdx.x;
+  const unsigned lane = (unsigned)tid & 31u;
+  const int ntiles = G.ntx_cur * G.ntz_cur;
+  const int nx = m.nx, nz = m.nz;
+
+  if ((int)blockIdx.x >= ntiles) {
+    // ---- extra CTAs: count the particles injected for the next super-round per tile of its tiling ----
+    const int per_block = TNT * 8;
+    const int lo = G.inj_lo + ((int)blockIdx.x - ntiles) * per_block;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      const int id = lo + j * TNT + tid;
+      bool active = id < G.inj_hi;
+      int dest = 0;
+      if (active) {
+        float px, pz;
+        spawn_position_iid(id, nx, nz, key, call, px, pz);
+        const int ix = __float2int_rd(px + 0.5f), iz = __float2int_rd(pz + 0.5f);
+        active = !m.oob(ix, iz);                                     // (dies in its first fly() call: never stored)
+        if (active) dest = tile_of(ix, iz, G.off_next, G.ntz_next);
+      }
+      count_dest(S.count, dest, active);
+    }
+    return;
+  }
+
+  const unsigned* base_cur = G.cur ? S.base[1] : S.base[0];
+  const unsigned seg = base_cur[blockIdx.x];
+  const int n = (int)(base_cur[blockIdx.x + 1] - seg);
+  if (n == 0) return;
+  const int np = min(n, G.pcap);
+  float4* ga = (G.cur ? S.pa[1] : S.pa[0]) + seg;
+  float4* gb = (G.cur ? S.pb[1] : S.pb[0]) + seg;
+  const int x0 = ((int)blockIdx.x / G.ntz_cur) * TT - G.off_cur, z0 = ((int)blockIdx.x % G.ntz_cur) * TT - G.off_cur;
+
+  // ---- shared memory: heights [rock] | records a | records b | claim lattice | list | pcol | counters ----
+  float* hs = reinterpret_cast<float*>(smem_raw);
+  float* rs = hs + (LAYERED ? TT * TT : 0);
+  float4* ra = RL2 ? ga : reinterpret_cast<float4*>(rs + TT * TT);
+  float4* rb = RL2 ? gb : ra + G.pcap;
+  unsigned* claim = RL2 ? reinterpret_cast<unsigned*>(rs + TT * TT) : reinterpret_cast<unsigned*>(rb + G.pcap);
+  unsigned short* list = reinterpret_cast<unsigned short*>(claim + TLAT * TLAT);
+  unsigned* pcol32 = reinterpret_cast<unsigned*>(list + G.pcap);          // pcap is a multiple of 4
+  unsigned char* pcol = reinterpret_cast<unsigned char*>(pcol32);
+  __shared__ unsigned s_n[2];
+  __shared__ unsigned s_dirty, s_dirty_rock;
+  __shared__ unsigned s_stat[3];
+  __shared__ float s_lost;
+
+  if (tid < 2) s_n[tid] = 0u;
+  if (tid == 2) { s_dirty = 0u; s_dirty_rock = 0u; s_lost = 0.0f; }
+  if (tid < 3) s_stat[tid] = 0u;
+  for (int i = tid; i < TT * TT; i += TNT) {
+    const int gx = x0 + i / TT, gz = z0 + i % TT;
+    const bool in = gx >= 0 && gx < nx && gz >= 0 && gz < nz;
+    hs[i] = in ? __ldcg(m.height + (size_t)gx * (size_t)nz + gz) : 0.0f;
+    if (LAYERED) rs[i] = in ? __ldcg(m.rock + (size_t)gx * (size_t)nz + gz) : 0.0f;
+  }
+  for (int i = tid; i < TLAT * TLAT; i += TNT) claim[i] = 0u;
+  for (int p = tid; p < G.pcap; p += TNT) {
+    unsigned col = PARKED;
+    if (p < np) {
+      const float4 a = RL2 ? __ldcg(ga + p) : __ldcs(ga + p);
+      if (!RL2) { ra[p] = a; rb[p] = __ldcs(gb + p); }
+      col = service_colour(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), x0, z0, nx, nz);
+    }
+    pcol[p] = (unsigned char)col;
+  }
+  __syncthreads();
+
+  unsigned n_steps = 0, n_oob = 0, n_age = 0;
+  float lost = 0.0f;
+  unsigned tag = 0u;
+  const int nwords = (np + 3) >> 2;
+#pragma unroll 1
+  for (int r = 0; r < G.K; r++) {
+    unsigned served = 0u;
+#pragma unroll 1
+    for (unsigned c = 0; c < 9u; c++) {
+      tag++;
+      unsigned* cnt = &s_n[tag & 1u];
+      // ---- collect the particles standing on interior cells of colour c ----
+      const unsigned pat = c * 0x01010101u;
+      for (int w0 = 0; w0 < nwords; w0 += TNT) {           // (uniform trip count: warp-aggregated append, one atomic per warp)
+        const int w = w0 + tid;
+        const unsigned eq = w < nwords ? __vcmpeq4(pcol32[w], pat) : 0u;
+        const unsigned k = (unsigned)__popc(eq) >> 3;
+        if (__ballot_sync(0xffffffffu, k != 0u) == 0u) continue;
+        unsigned incl = k;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+          if ((int)lane >= o) incl += t;
+        }
+        unsigned wbase = 0u;
+        if (lane == 31u) wbase = atomicAdd(cnt, incl);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        unsigned slot = wbase + incl - k;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if ((eq >> (8 * b)) & 1u) list[slot++] = (unsigned short)(4 * w + b);
+      }
+      if (tid == 0) s_n[(tag + 1u) & 1u] = 0u;
+      __syncthreads();
+      const unsigned cntv = *cnt;
+      served += cntv;
+      for (unsigned i = (unsigned)tid; i < cntv; i += TNT) {
+        const int p = (int)list[i];
+        const float4 a = RL2 ? __ldcg(ra + p) : ra[p], b = RL2 ? __ldcg(rb + p) : rb[p];
+        const int ix = __float2int_rd(a.x + 0.5f), iz = __float2int_rd(a.z + 0.5f);               // wind.hpp:30
+        const int lx = ix - x0, lz = iz - z0;
+        // one particle per cell per micro-round; the others wait for the colour's next turn
+        if (atomicMax(&claim[(lx / 3) * TLAT + lz / 3], tag) >= tag) continue;
+        const int li = lx * TT + lz;
+        const bool xm = ix > 0, xp = ix + 1 < nx, zm = iz > 0, zp = iz + 1 < nz;
+        const unsigned valid = (xm && zm ? 1u : 0u) | (xm ? 2u : 0u) | (xm && zp ? 4u : 0u) | (zm ? 8u : 0u) |
+                               (zp ? 16u : 0u) | (xp && zm ? 32u : 0u) | (xp ? 64u : 0u) | (xp && zp ? 128u : 0u);
+        const float hc = hs[li];
+        float h[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          h[k] = ((valid >> k) & 1u) ? hs[li + block::slot_dx(k) * TT + block::slot_dz(k)] : hc;
+        float rock_c = 0.0f, rk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (LAYERED) {
+          rock_c = rs[li];
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if ((valid >> k) & 1u) rk[k] = rs[li + block::slot_dx(k) * TT + block::slot_dz(k)];
+        }
+        PState q;
+        q.px = a.x; q.py = a.y; q.pz = a.z; q.sed = a.w;
+        q.sx = b.x; q.sy = b.y; q.sz = b.z; q.age = __float_as_int(b.w);
+        const size_t ci = (size_t)ix * (size_t)nz + (size_t)iz;
+        float collision, tx, ty, tz, tsed;
+        float dh = fly_owned(C, q, hc, h[1], h[6], h[3], h[4], xm, xp, zm, zp,
+                             make_uint4((uint32_t)ci, call, G.micro0 + tag - 1u, 0xAu), key, collision, tx, ty, tz, tsed);
+        red_add_v4(m.track + ci, tsed, tx, ty, tz);                                              // wind.hpp:93-96
+        if (LAYERED && dh > 0.0f) {
+          // layered extension: only the sand above the bedrock is picked up; the unmet demand grinds the rock
+          // at `abrasion` efficiency (rock -> suspended sediment). The cell is owned: plain updates.
+          const float take = fminf(dh, fmaxf(hc - rock_c, 0.0f));
+          const float ground = C.abrasion * (dh - take);
+          if (ground > 0.0f) { rock_c -= ground; rs[li] = rock_c; s_dirty_rock = 1u; }
+          dh = take + ground;
+        }
+        float c1 = hc - dh;                                                                      // :110-112
+        q.sed += dh;
+        float v[8];
+        int s[8];
+        const unsigned moved = LAYERED ? block::cascade_sorted<true>(c1, h, valid, T, v, s, rock_c, rk)   // :114
+                                       : block::cascade_sorted<false>(c1, h, valid, T, v, s, rock_c, rk);
+        if (moved != 0u || dh != 0.0f) { hs[li] = c1; s_dirty = 1u; }
+        // slot -> (dx + 1, dz + 1) packed four bits per slot (world.hpp:83-92): two shifts instead of the branches of slot_dx / slot_dz
+#pragma unroll
+        for (int i8 = 0; i8 < 8; i8++)
+          if ((moved >> i8) & 1u) {
+            const unsigned code = (0xa9864210u >> (4 * s[i8])) & 15u;
+            hs[li + (int)(code >> 2) * TT + (int)(code & 3u) - (TT + 1)] = v[i8];
+          }
+        n_steps++;
+        const int jx = __float2int_rd(q.px + 0.5f), jz = __float2int_rd(q.pz + 0.5f);
+        unsigned col;
+        if (m.oob(jx, jz)) { n_oob++; lost += q.sed; q.age = -1; col = DEAD; }                   // :32-38 (the next fly() call)
+        else if (q.age > C.max_age) { n_age++; lost += q.sed; q.age = -1; col = DEAD; }          // :45-46
+        else col = service_colour(jx, jz, x0, z0, nx, nz);
+        if (RL2) {
+          __stcg(ra + p, make_float4(q.px, q.py, q.pz, q.sed));
+          __stcg(rb + p, make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age)));
+        } else {
+          ra[p] = make_float4(q.px, q.py, q.pz, q.sed);
+          rb[p] = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
+        }
+        pcol[p] = (unsigned char)col;
+      }
+      __syncthreads();
+    }
+    if (served == 0u) break;          // everything left in the tile is parked or dead (uniform over the CTA)
+  }
+
+  // ---- store: heights if anything moved, every record (dead ones marked by age < 0), destination counts ----
+  if (s_dirty) {
+    for (int i = tid; i < TT * TT; i += TNT) {
+      const int gx = x0 + i / TT, gz = z0 + i % TT;
+      if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) m.height[(size_t)gx * (size_t)nz + gz] = hs[i];
+    }
+  }
+  if (LAYERED && s_dirty_rock) {
+    for (int i = tid; i < TT * TT; i += TNT) {
+      const int gx = x0 + i / TT, gz = z0 + i % TT;
+      if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) m.rock[(size_t)gx * (size_t)nz + gz] = rs[i];
+    }
+  }
+  for (int p0 = 0; p0 < n; p0 += TNT) {
+    const int p = p0 + tid;
+    bool alive = false;
+    int dest = 0;
+    if (p < n) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < np) {
+        alive = pcol[p] != DEAD;
+        if (RL2) { if (alive) a = __ldcg(ga + p); }
+        else { a = ra[p]; ga[p] = a; gb[p] = rb[p]; }
+      } else {
+        a = __ldcs(ga + p);             // beyond the shared-memory capacity: parked for this super-round
+        alive = true;
+      }
+      if (alive) dest = tile_of(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), G.off_next, G.ntz_next);
+    }
+    count_dest(S.count, dest, alive);
+  }
+
+  for (int o = 16; o > 0; o >>= 1) {
+    n_steps += __shfl_xor_sync(0xffffffffu, n_steps, o);
+    n_oob += __shfl_xor_sync(0xffffffffu, n_oob, o);
+    n_age += __shfl_xor_sync(0xffffffffu, n_age, o);
+    lost += __shfl_xor_sync(0xffffffffu, lost, o);
+  }
+  if (lane == 0u) {
+    if (n_steps) atomicAdd(&s_stat[0], n_steps);
+    if (n_oob) atomicAdd(&s_stat[1], n_oob);
+    if (n_age) atomicAdd(&s_stat[2], n_age);
+    if (lost != 0.0f) atomicAdd(&s_lost, lost);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (s_stat[0]) atomicAdd(&stats->steps, (unsigned long long)s_stat[0]);
+    if (s_stat[1]) atomicAdd(&stats->exits_oob, (unsigned long long)s_stat[1]);
+    if (s_stat[2]) atomicAdd(&stats->exits_age, (unsigned long long)s_stat[2]);
+    if (s_lost != 0.0f) atomicAdd(&stats->sediment_lost, (double)s_lost);
+  }
+}
+
+// Exclusive prefix sum of the per-tile counts (one CTA; a thread sums a contiguous run, the CTA scans the 1024
+// partial sums); clears the counts and the scatter cursors for the next super-round.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(TileSched S, int nt, int nxt) {
+  __shared__ unsigned part[1024];
+  const int tid = (int)threadIdx.x;
+  const int run = (nt + 1023) / 1024;
+  const int lo = min(tid * run, nt), hi = min(lo + run, nt);
+  unsigned sum = 0u;
+  for (int i = lo; i < hi; i++) sum += S.count[i];
+  part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned v = tid >= o ? part[tid - o] : 0u;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  unsigned acc = part[tid] - sum;
+  unsigned* base = nxt ? S.base[1] : S.base[0];
+  for (int i = lo; i < hi; i++) {
+    base[i] = acc;
+    acc += S.count[i];
+    S.count[i] = 0u;
+    S.cursor[i] = 0u;
+  }
+  if (tid == 1023) { base[nt] = part[1023]; S.info[0] = part[1023]; }
+}
+
+// Moves every surviving record of the current segments, and the particles injected for the next super-round,
+// into the segment of the tile (next tiling) its cell belongs to.
+__global__ void __launch_bounds__(256) tile_scatter_kernel(MapView m, TileSched S, TileGeom G, uint2 key, uint32_t call,
+                                                           DevStats* stats) {
+  const unsigned total = (G.cur ? S.base[1] : S.base[0])[G.ntx_cur * G.ntz_cur];
+  const unsigned ninj = (unsigned)(G.inj_hi - G.inj_lo);
+  const unsigned all = total + ninj;
+  const float4* ga = G.cur ? S.pa[1] : S.pa[0];
+  const float4* gb = G.cur ? S.pb[1] : S.pb[0];
+  float4* da = G.cur ? S.pa[0] : S.pa[1];
+  float4* db = G.cur ? S.pb[0] : S.pb[1];
+  const unsigned* base = G.cur ? S.base[0] : S.base[1];
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned n_new = 0, n_oob = 0;
+  for (unsigned j0 = blockIdx.x * 256u; j0 < all; j0 += gridDim.x * 256u) {
+    const unsigned j = j0 + threadIdx.x;
+    bool active = false;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < total) {
+      a = __ldcs(ga + j); b = __ldcs(gb + j);
+      active = __float_as_int(b.w) >= 0;
+    } else if (j < all) {
+      float px, pz;                                                  // Wind ctor + spawn (world.hpp:52-54)
+      spawn_position_iid(G.inj_lo + (int)(j - total), m.nx, m.nz, key, call, px, pz);
+      a = make_float4(px, 0.0f, pz, 0.0f);
+      b = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
+      n_new++;
+      active = !m.oob(__float2int_rd(px + 0.5f), __float2int_rd(pz + 0.5f));
+      if (!active) n_oob++;                                          // dies in its first fly() call
+    }
+    int dest = 0;
+    if (active) dest = tile_of(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), G.off_next, G.ntz_next);
+    const unsigned has = __ballot_sync(0xffffffffu, active);
+    if (active) {
+      const unsigned grp = __match_any_sync(has, dest);
+      const int leader = __ffs(grp) - 1;
+      unsigned wb = 0u;
+      if ((int)lane == leader) wb = atomicAdd(S.cursor + dest, (unsigned)__popc(grp));
+      wb = __shfl_sync(grp, wb, leader);
+      const unsigned slot = base[dest] + wb + (unsigned)__popc(grp & ((1u << lane) - 1u));
+      if (slot < (unsigned)S.cap) { da[slot] = a; db[slot] = b; }
+      else atomicAdd(S.info + 1, 1u);                                // cannot happen: cap >= particles per call
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_new += __shfl_xor_sync(0xffffffffu, n_new, o);
+    n_oob += __shfl_xor_sync(0xffffffffu, n_oob, o);
+  }
+  if (lane == 0u) {
+    if (n_new) atomicAdd(&stats->particles, (unsigned long long)n_new);
+    if (n_oob) atomicAdd(&stats->exits_oob, (unsigned long long)n_oob);
+  }
+}
+
+static size_t tile_smem_bytes(bool layered, int pcap) {
+  return (size_t)(layered ? 2 : 1) * TT * TT * sizeof(float) + (size_t)pcap * ((RL2 ? 0 : 2 * sizeof(float4)) + sizeof(unsigned short) + 1) +
+         (size_t)TLAT * TLAT * sizeof(unsigned) + 16;
+}
+
+// largest pcap (multiple of 64) the device can give one CTA
+int tile_max_pcap(bool layered, int smem_optin) {
+  const long long fixed = (long long)tile_smem_bytes(layered, 0) + 1024;
+  long long p = ((long long)smem_optin - fixed) / (RL2 ? 3 : 35);
+  p = p / 64 * 64;
+  return p < 64 ? 0 : (int)(p > 8192 ? 8192 : p);
+}
+
+static TileGeom tile_geom(const MapView& m, int s) {
+  TileGeom G{};
+  G.off_cur = (s % 3) * (TT / 3);
+  G.ntx_cur = (m.nx + G.off_cur + TT - 1) / TT; G.ntz_cur = (m.nz + G.off_cur + TT - 1) / TT;
+  G.off_next = ((s + 1) % 3) * (TT / 3);
+  G.ntx_next = (m.nx + G.off_next + TT - 1) / TT; G.ntz_next = (m.nz + G.off_next + TT - 1) / TT;
+  G.cur = s & 1;
+  return G;
+}
+
+int tile_max_tiles(int nx, int nz) {
+  const int off = 2 * (TT / 3);
+  return ((nx + off + TT - 1) / TT) * ((nz + off + TT - 1) / TT);
+}
+
+// Super-round s of a call (s = -1: only the injection of super-round 0's particles). Returns the launches made.
+int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSched& S, int s, int K, int pcap,
+                            int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  block::Thr T;
+  T.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;   // host IEEE fp32: the values exact::cascade_thresholds computes
+  T.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
+  T.settling = p.settling;
+  TileGeom G;
+  if (s >= 0) G = tile_geom(m, s);
+  else {                                      // no tiles yet: cur = 1 holds an empty segment table (base[1][0] = 0)
+    G = tile_geom(m, 2);                      // (s + 1) % 3 == 0  -> next tiling is tiling 0
+    G.ntx_cur = 0; G.ntz_cur = 0; G.cur = 1;
+  }
+  G.inj_lo = inj_lo; G.inj_hi = inj_hi;
+  G.micro0 = s >= 0 ? (unsigned)s * 9u * (unsigned)K : 0u;
+  G.K = K; G.pcap = pcap;
+  const int ntiles = G.ntx_cur * G.ntz_cur;
+  const int inj_blocks = (inj_hi - inj_lo + TNT * 8 - 1) / (TNT * 8);
+  const bool layered = m.rock != nullptr;
+  const size_t smem = tile_smem_bytes(layered, pcap);
+  int launches = 0;
+  if (ntiles + inj_blocks > 0) {
+    if (layered) tile_fly_kernel<true><<<ntiles + inj_blocks, TNT, smem, st>>>(m, make_const(p), T, S, G, key, call, stats);
+    else tile_fly_kernel<false><<<ntiles + inj_blocks, TNT, smem, st>>>(m, make_const(p), T, S, G, key, call, stats);
+    launches++;
+  }
+  tile_scan_kernel<<<1, 1024, 0, st>>>(S, G.ntx_next * G.ntz_next, G.cur ^ 1);
+  const long long work = (long long)S.cap;
+  long long blocks = (work + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tile_scatter_kernel<<<(int)blocks, 256, 0, st>>>(m, S, G, key, call, stats);
+  return launches + 2;
+}
+
+cudaError_t tile_configure(bool layered, int pcap) {
+  const size_t smem = tile_smem_bytes(layered, pcap);
+  return layered ? cudaFuncSetAttribute(tile_fly_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                 : cudaFuncSetAttribute(tile_fly_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+void preload_tile() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, tile_fly_kernel<false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<true>);
+  cudaFuncGetAttributes(&a, tile_scan_kernel);
+  cudaFuncGetAttributes(&a, tile_scatter_kernel);
+}
+
+}  // namespace swe

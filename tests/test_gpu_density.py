@@ -131,7 +131,7 @@ def test_stagger_option_and_sparse_calls():
     with pytest.raises(swe.SweError):
         w.set_option(swe.OPT_STAGGER_ROUNDS, -2)
     with pytest.raises(swe.SweError):
-        w.set_option(swe.OPT_SCHEDULE, 2)
+        w.set_option(swe.OPT_SCHEDULE, 3)
     st = w.stats()
     assert st.exits_oob + st.exits_age == st.particles == 16 * n
     w.close()

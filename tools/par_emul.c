@@ -4,6 +4,7 @@
  * within a round / where the cascade runs). Not part of the product; design input for DESIGN.md 3.
  *   gcc -O2 -ffp-contract=off -shared -fPIC tools/par_emul.c -o /tmp/libpar_emul.so -lm
  */
+#include <stdio.h>
 #include "../oracle/swe_oracle.c"
 
 /* Wind::fly (wind.hpp:28-112) without the cascade; erosion goes to hd[] when given (frozen
@@ -301,5 +302,80 @@ long long emul_erode_queues(swo_world* w, int cycles, int stagger, int order_kin
   free(claim); free(q); free(alive);
   if (lost_out) *lost_out = lost;
   if (rounds_out) *rounds_out = k;
+  return steps;
+}
+
+/* Option D: TILE-RESIDENT super-rounds (what csrc/swe_tile.cu does). The map is cut into T x T tiles; a
+ * super-round runs K rounds of nine colour micro-rounds INSIDE every tile independently (one CTA per tile,
+ * heights and particles in shared memory). A particle is served only while its cell lies in the INTERIOR of
+ * the tile it started the super-round in (>= 1 cell from the tile's edges, map edges excepted), so that its
+ * 3x3 block never leaves the tile: tiles are conflict-free, no staleness, no atomics on heights. A particle
+ * that reaches the border ring (or jumps out of the tile) is parked until the next super-round, whose tiling
+ * is shifted by T/3 in both directions (three tilings in turn: a cell lies on the x-ring of at most one of
+ * them and on the z-ring of at most one, so it is interior in at least one).
+ * Particle i becomes active at round i * stagger / n (flags & 1: at that round inside the super-round;
+ * else at the start of the super-round that contains it). */
+long long emul_erode_tiles(swo_world* w, int cycles, int stagger, int T, int K, int flags, double* lost_out,
+                           long long* rounds_out) {
+  const int nx = w->nx, nz = w->nz;
+  const size_t area = (size_t)nx * nz;
+  for (int k = 5; k < 9; k++) memset(w->plane[k], 0, sizeof(float) * area);
+  long long steps = 0, sr = 0;
+  double lost = 0.0;
+  int* claim = (int*)calloc(area, sizeof(int));
+  const int n = cycles;
+  swo_particle* q = (swo_particle*)malloc(sizeof(swo_particle) * (size_t)(n + 1));
+  char* alive = (char*)malloc((size_t)n + 1);
+  int* home = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+  for (int i = 0; i < n; i++) { swo_spawn(w, &q[i]); alive[i] = 1; }
+  int live = n, stamp = 0;
+  const int ntz = nz / T + 2;
+  while (live > 0) {
+    const int off = (int)(sr % 3) * (T / 3);   /* three tilings: a cell lies on the x-ring of at most one and on the z-ring of at most one */
+    for (int i = 0; i < n; i++) {
+      home[i] = -1;
+      if (!alive[i]) continue;
+      const int ix = (int)roundf(q[i].pos[0]), iz = (int)roundf(q[i].pos[2]);
+      if (oob(w, ix, iz)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
+      home[i] = ((ix + off) / T) * ntz + (iz + off) / T;
+    }
+    for (int r = 0; r < K; r++) {
+      const long long round = sr * K + r;
+      for (int c = 0; c < 9; c++) {
+        stamp++;
+        for (int i = 0; i < n; i++) {
+          if (!alive[i] || home[i] < 0) continue;
+          if (stagger > 0) {
+            const long long start = ((long long)i * stagger) / n;
+            if ((flags & 1) ? start > round : start >= (sr + 1) * K) continue;
+          }
+          const int ix = (int)roundf(q[i].pos[0]), iz = (int)roundf(q[i].pos[2]);
+          if (oob(w, ix, iz)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
+          if ((ix % 3) * 3 + iz % 3 != c) continue;
+          if (((ix + off) / T) * ntz + (iz + off) / T != home[i]) continue;            /* left its tile: parked */
+          const int lx = (ix + off) % T, lz = (iz + off) % T;
+          if ((lx == 0 && ix != 0) || (lx == T - 1 && ix != nx - 1) || (lz == 0 && iz != 0) || (lz == T - 1 && iz != nz - 1))
+            continue;                                                                 /* border ring: parked */
+          const size_t ind = (size_t)ix * nz + iz;
+          if (claim[ind] == stamp) continue;
+          claim[ind] = stamp;
+          int cell;
+          if (!fly_nc(w, &q[i], NULL, &cell)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
+          steps++;
+          swo_cascade(w, ix, iz);
+        }
+      }
+    }
+    sr++;
+    if (getenv("EMUL_DBG")) fprintf(stderr, "sr %lld live %d steps %lld\n", sr, live, steps);
+  }
+  const float lr = w->p.lrate;
+  for (int kk = 1; kk < 5; kk++) {
+    float* f = w->plane[kk]; const float* t = w->plane[kk + 4];
+    for (size_t i = 0; i < area; i++) f[i] = (1.0f - lr) * f[i] + lr * t[i];
+  }
+  free(claim); free(q); free(alive); free(home);
+  if (lost_out) *lost_out = lost;
+  if (rounds_out) *rounds_out = sr * K;
   return steps;
 }

@@ -10,6 +10,11 @@ if what == "fly4096":
     w = swe.World(4096); w.generate_noise(1, 8); w.normalize(); w.srand(1)   # bench.py's dune field
     for _ in range(2): w.erode(1 << 22, swe.MODE_PARALLEL)
     w.sync(); print(w.stats().last_fly_ms)
+elif what == "fly4096tile1":
+    w = swe.World(4096); w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_TILES)
+    w.generate_noise(1, 8); w.normalize(); w.srand(1)
+    w.erode(1 << 22, swe.MODE_PARALLEL)
+    w.sync(); print(w.stats().last_fly_ms)
 elif what == "fly1024flat":
     w = swe.World(1024); w.upload(generate.flat_sand(1024)); w.srand(1)
     for _ in range(2): w.erode(1 << 20, swe.MODE_PARALLEL)
