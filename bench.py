@@ -15,15 +15,17 @@ the reference snapshot). One JSON line is printed by rank 0.
   e2e       the same metric through the host-buffer C-ABI: every step uploads the height
             plane from pinned host memory, erodes, and downloads height + the four flow
             fields (what the reference's renderer reads each frame)
-  roofline  the flight kernel (colour_persistent_kernel: Wind::fly + erosion + World::cascade of
-            every particle step, one cooperative launch per call): 104 algorithmic B/step
-            (3x3 heights read + written, four tracks read + written) / its device
-            time, against MEASURED_PEAKS.json hbm_gbs; cascade_roofline is the same for the
-            whole-map cascade sweep (8 B/cell/sweep) on the 8192^2 random-slope workload
-  schedule  the headline runs the colour-queue scheduler (parity-green against the sequential
-            oracle at this density, tests/test_gpu_density.py); round 1's lock-step schedule,
-            which is faster but exports +24 % more sand than the reference, is timed beside it
-            as `lockstep_all_at_once`
+  roofline  the flight kernel (single GPU: tile_fly_kernel, one launch per super-round; stripes:
+            colour_persistent_kernel, one cooperative launch per call -- Wind::fly + erosion +
+            World::cascade of every particle step): 104 algorithmic B/step (SURVEY.md 8d: 3x3
+            heights read + written, four tracks read + written) / its device time, against
+            MEASURED_PEAKS.json hbm_gbs; cascade_roofline is the same for the whole-map cascade
+            sweep (8 B/cell/sweep) on the 8192^2 random-slope workload
+  schedule  the single-GPU headline runs the tile-resident scheduler (SWE_OPT_SCHEDULE = 2,
+            parity-green against the sequential oracle at this density, tests/test_gpu_tiles.py);
+            the colour-queue scheduler (the stripes' schedule, equally parity-green) and round 1's
+            lock-step schedule, which exports +24 % more sand than the reference, are timed
+            beside it as `colour_queue_schedule` and `lockstep_all_at_once`
   cpu_baseline  the unmodified reference (oracle/_ref) timed on one host core on a bounded
             sample of the same workload (the reference is single-threaded, world.hpp:100)
 """
@@ -436,6 +438,29 @@ def cfg4_strong(swe, rank: int, world: int, device: int, barrier, max_over_ranks
     return out
 
 
+def colour_queue_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> dict:
+    """The colour-queue scheduler (SWE_OPT_SCHEDULE = 0; the schedule of the multi-GPU stripes and of periodic maps)
+    on the headline call, timed beside the tile-resident headline."""
+    w = swe.World(n, device=device)
+    w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_COLOUR_QUEUES)
+    w.upload(hm)
+    w.srand(1)
+    for _ in range(2):
+        w.erode(particles, swe.MODE_PARALLEL)
+    w.sync()
+    s0 = w.stats().steps
+    ms = 0.0
+    for _ in range(steps):
+        w.erode(particles, swe.MODE_PARALLEL)
+        ms += w.stats().last_erode_ms
+    out = {"schedule": "colour queues: one persistent cooperative kernel, grid barrier per micro-round (parity-green, "
+                       "tests/test_gpu_density.py)",
+           "value": (w.stats().steps - s0) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "micro_rounds_per_step": w.stats().last_micro_rounds}
+    w.close()
+    return out
+
+
 def lockstep_extra(swe, device: int, n: int, particles: int, hm, steps: int) -> dict:
     """Round 1's schedule (SWE_OPT_SCHEDULE = 1): every particle of the call steps once per round, then one
     stamped cascade over the touched cells. Timed beside the headline because it is what round 1 reported;
@@ -505,6 +530,8 @@ def run_ours(args) -> None:
 
     if world == 1:
         w = swe.World(n, device=local)
+        w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_TILES)
+        tile_rounds = w.get_option(swe.OPT_TILE_ROUNDS)
     else:
         # weak scaling: every GPU owns one n x n stripe of an (n*world) x n map (copies of the
         # single-GPU map stacked along the wind axis) and the call flies particles*world particles.
@@ -672,6 +699,23 @@ def run_ours(args) -> None:
                 "result_check_mean_height": mean_h},
         "gpu_launches": int(launches),
         "roofline": ({
+            "bound": "hbm", "kernel": "tile_fly_kernel (Wind::fly + erosion + World::cascade per particle step; one CTA per 60x60 tile, "
+                                      "heights and particles in shared memory)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic("tile_fly"), "peak_source": peak_src,
+            "algorithmic_bytes_per_step": BYTES_PER_STEP,
+            "launches_per_step": micro_rounds / args.steps / (9.0 * tile_rounds),
+            "kernel_ms_per_launch": fly_ms / max(1.0, micro_rounds / (9.0 * tile_rounds)),
+            "algorithmic_bytes_per_launch": BYTES_PER_STEP * fly_steps / max(1.0, micro_rounds / (9.0 * tile_rounds)),
+            "share_of_step": {"tile_fly_kernel + scan + scatter (one super-round each)": fly_ms / erode_ms,
+                              "track reset + EMA": 1.0 - fly_ms / erode_ms},
+            "super_rounds_per_step": micro_rounds / args.steps / (9.0 * tile_rounds),
+            "note": "104 B/step is SURVEY 8(d)'s figure for flight + cascade, which this one kernel does. `traffic` is the DRAM "
+                    "traffic of ONE mid-call launch under ncu (the launches of a call differ in size: the injection ramps "
+                    "up and down); per particle step it is ~4x BELOW the algorithmic bytes because a tile's heights are "
+                    "read and written once per super-round, not per step. The kernel is bound by instruction issue and "
+                    "the dependent chain of a step, not by HBM (DESIGN.md 4)"}
+            if world == 1 else {
             "bound": "hbm", "kernel": "colour_persistent_kernel (Wind::fly + erosion + World::cascade per particle step)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic("colour_persistent"), "peak_source": peak_src,
@@ -691,6 +735,10 @@ def run_ours(args) -> None:
     }
     line["config"]["schedule"] = (
         "lock-step rounds (stripe engines; round 1's schedule: NOT parity-green at this density, DESIGN.md 6)" if lockstep else
+        f"tile-resident: 60x60-cell tiles, one CTA per tile for {tile_rounds} rounds of nine colour micro-rounds per launch, three "
+        f"shifted tilings, interior-only service, in-register cascade, automatic stagger "
+        f"({int(8 * particles / (n * n) * rounds_per_call + 0.5)} rounds); parity-green at this density "
+        f"(tests/test_gpu_tiles.py)" if world == 1 else
         f"colour queues: 9-colour micro-rounds, one particle per cell, in-register cascade, automatic stagger "
         f"({int(8 * particles / (n * n) * rounds_per_call + 0.5)} rounds); parity-green at this density "
         f"(tests/test_gpu_density.py)")
@@ -699,6 +747,7 @@ def run_ours(args) -> None:
     if cfg4 is not None:
         line["cfg4_strong"] = cfg4
     if world == 1:
+        line["colour_queue_schedule"] = colour_queue_extra(swe, local, n, particles, hm, args.steps)
         line["lockstep_all_at_once"] = lockstep_extra(swe, local, n, particles, hm, args.steps)
     if world == 1 and not args.skip_layered:
         line["layered_extension"] = layered_extra(swe, local, n, particles, hm, args.steps)

@@ -120,8 +120,12 @@ typedef enum swe_option {
    * rock plane. Default 0. */
   SWE_OPT_PERIODIC = 10,
   /* Tile-resident schedule (SWE_OPT_SCHEDULE = 2): rounds (nine micro-rounds each) a CTA keeps its tile in shared
-   * memory before the particles are re-sorted into the next, shifted tiling. Default 16, range [1, 64]. */
-  SWE_OPT_TILE_ROUNDS = 11
+   * memory before the particles are re-sorted into the next, shifted tiling. 0 (default) = auto: tile edge / 5
+   * (12 for 60 x 60 tiles, 24 for 120 x 120); range [0, 64]. */
+  SWE_OPT_TILE_ROUNDS = 11,
+  /* Tile-resident schedule: tile geometry. -1 (default) = by map size (120 x 120 cells / 256 threads when that
+   * still gives every SM three tiles, else 60 x 60 / 128 threads), 0 = 60 x 60, 1 = 120 x 120. */
+  SWE_OPT_TILE_SHAPE = 12
 } swe_option;
 
 /* Tunables. Defaults (swe_params_default) are the reference's statics and constants:

@@ -96,8 +96,9 @@ struct swe_engine {
   uint64_t claim_tags_used = 0;       // upper bound of the claim tags handed out since the last clearing
   int persist_blocks_per_sm = 0;
   TileSched ts{};                     // tile-resident scheduler (swe_tile.cu): records sorted by tile
-  int opt_tile_rounds = 16;           // rounds (nine micro-rounds each) a CTA keeps its tile per super-round
-  int tile_pcap[2] = {0, 0};          // shared-memory record capacity the fly kernel is configured for [layered]
+  int opt_tile_rounds = 0;            // rounds (nine micro-rounds each) a CTA keeps its tile per super-round (0 = auto: edge / 5)
+  int opt_tile_shape = -1;            // -1 = by map size (tile_pick), else the index of a compiled tile geometry
+  int tile_pcap[2][2] = {{0, 0}, {0, 0}};   // particle capacity the fly kernel is configured for [shape][layered]
   int smem_optin = 0;
   CallCtl* d_ctl = nullptr;           // seed / call index of the current call (read by graph-replayed kernels)
   struct CachedGraph { uint64_t key; cudaGraphExec_t exec; };
@@ -673,24 +674,25 @@ int need_tiles(swe_engine* e, int cycles) {
 int erode_tile(swe_engine* e, int cycles) {
   if (int rc = need_tiles(e, cycles)) return rc;
   const bool layered = e->m.rock != nullptr;
-  const int K = e->opt_tile_rounds;
+  const int shape = e->opt_tile_shape >= 0 ? e->opt_tile_shape : tile_pick(e->m.nx, e->m.nz, e->sm_count);
+  const int TE = tile_edge(shape);
+  const int K = e->opt_tile_rounds > 0 ? e->opt_tile_rounds : TE / 5;
   const int life = e->p.max_age + 2;
   long long S = colour_stagger_micro(e, cycles) / 9;      // rounds
-  const int TE = tile_edge();
   // expected particles per tile while the injection runs (Poisson): mean + 5 sigma + slack stays on chip; a tile
   // with more than that parks the excess for a super-round (never lost)
   const double density = (double)cycles / ((double)e->m.nx * (double)e->m.nz);
   const double lam = density * TE * TE * (S > 0 ? (double)life / (double)(S + life) : 1.0);
   int pcap = ((int)(lam + 5.0 * std::sqrt(lam) + 64.0) + 63) / 64 * 64;
   if (const char* dbg = std::getenv("SWE_DEBUG_TILE_PCAP")) { const int v = std::atoi(dbg); if (v >= 64) pcap = v / 64 * 64; }
-  const int pmax = tile_max_pcap(layered, e->smem_optin > 0 ? e->smem_optin : 49152);
+  const int pmax = tile_max_pcap(shape, layered, e->smem_optin > 0 ? e->smem_optin : 49152);
   if (pmax < 64) return fail(SWE_ERR_STATE, "tile scheduler: not enough shared memory per block");
   if (pcap < 128) pcap = 128;
   if (pcap > pmax) pcap = pmax;
-  if (e->tile_pcap[layered] != pcap) {
-    const cudaError_t err = tile_configure(layered, pcap);
+  if (e->tile_pcap[shape][layered] != pcap) {
+    const cudaError_t err = tile_configure(shape, layered, pcap);
     if (err != cudaSuccess) return fail(SWE_ERR_CUDA, "tile kernel configuration failed: %s", cudaGetErrorString(err));
-    e->tile_pcap[layered] = pcap;
+    e->tile_pcap[shape][layered] = pcap;
   }
   if (int rc = erode_prologue(e)) return rc;
   const long long n = cycles;
@@ -700,7 +702,7 @@ int erode_tile(swe_engine* e, int cycles) {
     return (int)(v > n ? n : v);
   };
   const int inj_srs = S > 0 ? (int)((S + K - 1) / K) : 1;  // super-rounds that receive new particles
-  int nl = launch_tile_super_round(e->m, e->p, e->ts, -1, K, pcap, 0, started_before(K), e->seed, e->call_index,
+  int nl = launch_tile_super_round(e->m, e->p, e->ts, shape, -1, K, pcap, 0, started_before(K), e->seed, e->call_index,
                                    e->d_stats, e->stream);
   int first_check = inj_srs + (life * 6 / 10 + K - 1) / K;
   const int max_srs = inj_srs + 64 * ((life + K - 1) / K) + 64;
@@ -708,7 +710,7 @@ int erode_tile(swe_engine* e, int cycles) {
   for (;; s++) {
     if (s >= max_srs) return fail(SWE_ERR_STATE, "tile scheduler: particles still alive after %d super-rounds", s);
     const int lo = started_before((long long)(s + 1) * K), hi = started_before((long long)(s + 2) * K);
-    nl += launch_tile_super_round(e->m, e->p, e->ts, s, K, pcap, lo, hi, e->seed, e->call_index, e->d_stats, e->stream);
+    nl += launch_tile_super_round(e->m, e->p, e->ts, shape, s, K, pcap, lo, hi, e->seed, e->call_index, e->d_stats, e->stream);
     if (s + 1 >= first_check && (s + 1 - first_check) % 4 == 0) {
       if (int rc = check_launch(e, "tile super-round", nl)) return rc;
       nl = 0;
@@ -1726,6 +1728,7 @@ int swe_get_option(const swe_engine* e, int option, int* value) {
     case SWE_OPT_PERSISTENT: *value = e->opt_persistent; return SWE_OK;
     case SWE_OPT_PERIODIC: *value = e->m.periodic; return SWE_OK;
     case SWE_OPT_TILE_ROUNDS: *value = e->opt_tile_rounds; return SWE_OK;
+    case SWE_OPT_TILE_SHAPE: *value = e->opt_tile_shape; return SWE_OK;
     default: return fail(SWE_ERR_INVALID, "unknown option %d", option);
   }
 }
@@ -1762,8 +1765,11 @@ int swe_set_option(swe_engine* e, int option, int value) {
       e->graphs.clear();
       return SWE_OK;
     case SWE_OPT_TILE_ROUNDS:
-      if (value < 1 || value > 64) return fail(SWE_ERR_INVALID, "tile rounds must be in [1, 64]");
+      if (value < 0 || value > 64) return fail(SWE_ERR_INVALID, "tile rounds must be in [0, 64] (0 = auto)");
       e->opt_tile_rounds = value; return SWE_OK;
+    case SWE_OPT_TILE_SHAPE:
+      if (value < -1 || value >= tile_shapes()) return fail(SWE_ERR_INVALID, "tile shape must be -1 (auto) or in [0, %d)", tile_shapes());
+      e->opt_tile_shape = value; return SWE_OK;
     case SWE_OPT_STAGGER_ROUNDS:
       if (value < -1 || value > (1 << 20)) return fail(SWE_ERR_INVALID, "stagger rounds must be -1 (auto) or in [0, 2^20]");
       e->opt_stagger = value; return SWE_OK;

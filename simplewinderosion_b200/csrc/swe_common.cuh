@@ -241,12 +241,14 @@ struct TileSched {
   int cap;                  // records per array
   int max_tiles;
 };
-int tile_edge();
-int tile_threads();
+int tile_shapes();                   // tile geometries compiled in (0 = 60 x 60 cells / 128 threads, 1 = 120 x 120 / 256)
+int tile_edge(int shape);
+int tile_threads(int shape);
+int tile_pick(int nx, int nz, int sm_count);
 int tile_max_tiles(int nx, int nz);
-int tile_max_pcap(bool layered, int smem_optin);
-cudaError_t tile_configure(bool layered, int pcap);
-int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSched& S, int s, int K, int pcap,
+int tile_max_pcap(int shape, bool layered, int smem_optin);
+cudaError_t tile_configure(int shape, bool layered, int pcap);
+int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSched& S, int shape, int s, int K, int pcap,
                             int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st);
 void preload_tile();
 

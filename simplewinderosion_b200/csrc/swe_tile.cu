@@ -7,9 +7,11 @@
 // micro-round is synchronised. The colour-queue kernel meets at a grid barrier after every micro-round (13,500
 // dependent ~21 us steps per headline call: latency-bound, 2.5x the algorithmic DRAM traffic in scattered
 // 32-byte sectors). Here the map is cut into T x T tiles and ONE CTA owns one tile for a SUPER-ROUND of K rounds
-// (9 K micro-rounds behind __syncthreads): the tile's heights and its particles live in shared memory, the
-// height plane is read and written once per super-round with coalesced rows, a particle record makes one
-// round trip to HBM per super-round instead of one per step, and independent CTAs hide each other's latency.
+// (9 K micro-rounds behind __syncthreads): the tile's heights live in shared memory and are read from / written
+// to the height plane once per super-round with coalesced rows; the tile's particle records are one contiguous
+// segment that only this CTA touches (L2-resident for the super-round; measured on B200: keeping them in shared
+// memory costs 35 bytes per particle and lowers the number of resident CTAs -- 4-7 % slower); independent CTAs
+// hide each other's latency.
 //
 // Conflict-freedom without halos or atomics: a particle is served only while its cell lies in the INTERIOR of
 // the tile (>= 1 cell from the tile's edges; map edges excepted), so the 3x3 block it reads and writes never
@@ -33,28 +35,19 @@
 
 namespace swe {
 
-#ifndef SWE_TILE_T
-#define SWE_TILE_T 60              // tile edge in cells (multiple of 3)
-#endif
-#ifndef SWE_TILE_THREADS
-#define SWE_TILE_THREADS 128
-#endif
-#ifndef SWE_TILE_RECORDS_L2
-#define SWE_TILE_RECORDS_L2 0      // 1 = the particle records stay in global memory (L2) during a super-round instead of
-                                   // shared memory: 3 instead of 35 bytes of shared memory per particle, more CTAs per SM
-#endif
-static_assert(SWE_TILE_T % 3 == 0 && SWE_TILE_T >= 12, "tile edge: multiple of 3");
-constexpr bool RL2 = SWE_TILE_RECORDS_L2 != 0;
 constexpr unsigned DEAD = 0x0eu;     // pcol value of a particle that died in this super-round
-constexpr int TT = SWE_TILE_T;
-constexpr int TNT = SWE_TILE_THREADS;
-constexpr int TLAT = TT / 3;
-constexpr unsigned PARKED = 0x0fu;   // pcol value of a particle that is not served (parked, dead, not loaded)
+constexpr unsigned PARKED = 0x0fu;   // pcol value of a particle that is not served (parked, not loaded)
 
-int tile_edge() { return TT; }
-int tile_threads() { return TNT; }
+// Two tile geometries (host picks per call: tile_pick): 120 x 120 cells / 256 threads for big maps (more particles per
+// micro-round and CTA: fuller warps; measured on the 4096^2 headline: 170 ms against 200 ms with 60 x 60), 60 x 60 /
+// 128 threads for maps that would not fill the GPU with 120 x 120 tiles.
+struct TileShape { int edge, threads; };
+static const TileShape kShapes[2] = {{60, 128}, {120, 256}};
+int tile_shapes() { return 2; }
+int tile_edge(int shape) { return kShapes[shape].edge; }
+int tile_threads(int shape) { return kShapes[shape].threads; }
 
-__device__ __forceinline__ int tile_of(int ix, int iz, int off, int ntz) { return ((ix + off) / TT) * ntz + (iz + off) / TT; }
+__device__ __forceinline__ int tile_of(int ix, int iz, int off, int ntz, int tt) { return ((ix + off) / tt) * ntz + (iz + off) / tt; }
 
 // one atomic per warp and destination tile
 __device__ __forceinline__ void count_dest(unsigned* count, int dest, bool active) {
@@ -66,6 +59,7 @@ __device__ __forceinline__ void count_dest(unsigned* count, int dest, bool activ
 }
 
 // colour under which the particle standing on (ix, iz) is served by the tile with origin (x0, z0), or PARKED
+template <int TT>
 __device__ __forceinline__ unsigned service_colour(int ix, int iz, int x0, int z0, int nx, int nz) {
   const int lx = ix - x0, lz = iz - z0;
   if ((unsigned)lx >= (unsigned)TT || (unsigned)lz >= (unsigned)TT) return PARKED;          // left the tile
@@ -75,18 +69,21 @@ __device__ __forceinline__ unsigned service_colour(int ix, int iz, int x0, int z
 }
 
 struct TileGeom {
+  int edge;                          // tile edge T (multiple of 3)
   int off_cur, ntx_cur, ntz_cur;     // tiling served now: tile (a, b) covers [a T - off, (a + 1) T - off) x [b T - off, ...)
   int off_next, ntx_next, ntz_next;  // tiling of the next super-round
   int cur;                           // index of the record arrays / base array that hold the current segments
   int inj_lo, inj_hi;                // particle ids injected for the NEXT super-round
   unsigned micro0;                   // number of the super-round's first micro-round within the call (RNG counter)
   int K;                             // rounds per super-round
-  int pcap;                          // particles a tile keeps in shared memory (the rest of its segment stays parked)
+  int pcap;                          // particles of a tile that take part (the rest of its segment stays parked); multiple of 64
 };
 
-template <bool LAYERED>
-__global__ void __launch_bounds__(SWE_TILE_THREADS)
+template <int TT, int TNT, bool LAYERED>
+__global__ void __launch_bounds__(TNT)
 tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, uint2 key, uint32_t call, DevStats* stats) {
+  constexpr int TLAT = TT / 3;
+  static_assert(TT % 3 == 0 && TNT % 32 == 0, "tile edge: multiple of 3");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = (int)threadIdx.x;
   const unsigned lane = (unsigned)tid & 31u;
@@ -107,7 +104,7 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         spawn_position_iid(id, nx, nz, key, call, px, pz);
         const int ix = __float2int_rd(px + 0.5f), iz = __float2int_rd(pz + 0.5f);
         active = !m.oob(ix, iz);                                     // (dies in its first fly() call: never stored)
-        if (active) dest = tile_of(ix, iz, G.off_next, G.ntz_next);
+        if (active) dest = tile_of(ix, iz, G.off_next, G.ntz_next, TT);
       }
       count_dest(S.count, dest, active);
     }
@@ -119,26 +116,25 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
   const int n = (int)(base_cur[blockIdx.x + 1] - seg);
   if (n == 0) return;
   const int np = min(n, G.pcap);
-  float4* ga = (G.cur ? S.pa[1] : S.pa[0]) + seg;
+  float4* ga = (G.cur ? S.pa[1] : S.pa[0]) + seg;      // this tile's records: nobody else touches them in this launch
   float4* gb = (G.cur ? S.pb[1] : S.pb[0]) + seg;
   const int x0 = ((int)blockIdx.x / G.ntz_cur) * TT - G.off_cur, z0 = ((int)blockIdx.x % G.ntz_cur) * TT - G.off_cur;
+  // a tile that does not touch the map's edge: every neighbour of a served cell exists
+  const bool inner = x0 > 0 && z0 > 0 && x0 + TT < nx && z0 + TT < nz;
 
-  // ---- shared memory: heights [rock] | records a | records b | claim lattice | list | pcol | counters ----
+  // ---- shared memory: heights [rock] | claim lattice | list | pcol ----
   float* hs = reinterpret_cast<float*>(smem_raw);
   float* rs = hs + (LAYERED ? TT * TT : 0);
-  float4* ra = RL2 ? ga : reinterpret_cast<float4*>(rs + TT * TT);
-  float4* rb = RL2 ? gb : ra + G.pcap;
-  unsigned* claim = RL2 ? reinterpret_cast<unsigned*>(rs + TT * TT) : reinterpret_cast<unsigned*>(rb + G.pcap);
+  unsigned* claim = reinterpret_cast<unsigned*>(rs + TT * TT);
   unsigned short* list = reinterpret_cast<unsigned short*>(claim + TLAT * TLAT);
-  unsigned* pcol32 = reinterpret_cast<unsigned*>(list + G.pcap);          // pcap is a multiple of 4
-  unsigned char* pcol = reinterpret_cast<unsigned char*>(pcol32);
+  uint4* pcol128 = reinterpret_cast<uint4*>(list + G.pcap);               // pcap is a multiple of 64
+  unsigned char* pcol = reinterpret_cast<unsigned char*>(pcol128);
   __shared__ unsigned s_n[2];
-  __shared__ unsigned s_dirty, s_dirty_rock;
   __shared__ unsigned s_stat[3];
   __shared__ float s_lost;
 
   if (tid < 2) s_n[tid] = 0u;
-  if (tid == 2) { s_dirty = 0u; s_dirty_rock = 0u; s_lost = 0.0f; }
+  if (tid == 2) s_lost = 0.0f;
   if (tid < 3) s_stat[tid] = 0u;
   for (int i = tid; i < TT * TT; i += TNT) {
     const int gx = x0 + i / TT, gz = z0 + i % TT;
@@ -147,12 +143,12 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
     if (LAYERED) rs[i] = in ? __ldcg(m.rock + (size_t)gx * (size_t)nz + gz) : 0.0f;
   }
   for (int i = tid; i < TLAT * TLAT; i += TNT) claim[i] = 0u;
-  for (int p = tid; p < G.pcap; p += TNT) {
+  const int npad = (np + 15) & ~15;
+  for (int p = tid; p < npad; p += TNT) {
     unsigned col = PARKED;
     if (p < np) {
-      const float4 a = RL2 ? __ldcg(ga + p) : __ldcs(ga + p);
-      if (!RL2) { ra[p] = a; rb[p] = __ldcs(gb + p); }
-      col = service_colour(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), x0, z0, nx, nz);
+      const float4 a = __ldcg(ga + p);
+      col = service_colour<TT>(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), x0, z0, nx, nz);
     }
     pcol[p] = (unsigned char)col;
   }
@@ -161,7 +157,8 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
   unsigned n_steps = 0, n_oob = 0, n_age = 0;
   float lost = 0.0f;
   unsigned tag = 0u;
-  const int nwords = (np + 3) >> 2;
+  int dirty = 0, dirty_rock = 0;          // this thread changed a height / a bedrock height
+  const int nvec = npad >> 4;                        // 16 particles per 128-bit word of colour bytes
 #pragma unroll 1
   for (int r = 0; r < G.K; r++) {
     unsigned served = 0u;
@@ -169,12 +166,21 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
     for (unsigned c = 0; c < 9u; c++) {
       tag++;
       unsigned* cnt = &s_n[tag & 1u];
-      // ---- collect the particles standing on interior cells of colour c ----
+      // ---- collect the particles standing on interior cells of colour c: a thread scans 16 colour bytes, a warp
+      //      reserves its entries with one atomic; warps beyond the tile's particle count skip the scan ----
       const unsigned pat = c * 0x01010101u;
-      for (int w0 = 0; w0 < nwords; w0 += TNT) {           // (uniform trip count: warp-aggregated append, one atomic per warp)
+      for (int w0 = 0; w0 < nvec; w0 += TNT) {
+        if (w0 + (tid & ~31) >= nvec) break;         // (warp-uniform)
         const int w = w0 + tid;
-        const unsigned eq = w < nwords ? __vcmpeq4(pcol32[w], pat) : 0u;
-        const unsigned k = (unsigned)__popc(eq) >> 3;
+        uint4 q = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (w < nvec) q = pcol128[w];
+        // bit b of byte j of e{0..3}: 0x01 per matching byte
+        const unsigned e0 = __vcmpeq4(q.x, pat) & 0x01010101u, e1 = __vcmpeq4(q.y, pat) & 0x01010101u;
+        const unsigned e2 = __vcmpeq4(q.z, pat) & 0x01010101u, e3 = __vcmpeq4(q.w, pat) & 0x01010101u;
+        // 16-bit match mask: particle 16 w + i  (multiply gathers the four byte flags of a word into one nibble)
+        const unsigned m16 = ((e0 * 0x10204080u) >> 28) | (((e1 * 0x10204080u) >> 28) << 4) |
+                             (((e2 * 0x10204080u) >> 28) << 8) | (((e3 * 0x10204080u) >> 28) << 12);
+        const unsigned k = (unsigned)__popc(m16);
         if (__ballot_sync(0xffffffffu, k != 0u) == 0u) continue;
         unsigned incl = k;
 #pragma unroll
@@ -186,9 +192,8 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         if (lane == 31u) wbase = atomicAdd(cnt, incl);
         wbase = __shfl_sync(0xffffffffu, wbase, 31);
         unsigned slot = wbase + incl - k;
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-          if ((eq >> (8 * b)) & 1u) list[slot++] = (unsigned short)(4 * w + b);
+        for (unsigned mm = m16; mm != 0u; mm &= mm - 1u)
+          list[slot++] = (unsigned short)(16 * w + __ffs(mm) - 1);
       }
       if (tid == 0) s_n[(tag + 1u) & 1u] = 0u;
       __syncthreads();
@@ -196,15 +201,16 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
       served += cntv;
       for (unsigned i = (unsigned)tid; i < cntv; i += TNT) {
         const int p = (int)list[i];
-        const float4 a = RL2 ? __ldcg(ra + p) : ra[p], b = RL2 ? __ldcg(rb + p) : rb[p];
+        const float4 a = __ldcg(ga + p), b = __ldcg(gb + p);
         const int ix = __float2int_rd(a.x + 0.5f), iz = __float2int_rd(a.z + 0.5f);               // wind.hpp:30
         const int lx = ix - x0, lz = iz - z0;
         // one particle per cell per micro-round; the others wait for the colour's next turn
         if (atomicMax(&claim[(lx / 3) * TLAT + lz / 3], tag) >= tag) continue;
         const int li = lx * TT + lz;
-        const bool xm = ix > 0, xp = ix + 1 < nx, zm = iz > 0, zp = iz + 1 < nz;
-        const unsigned valid = (xm && zm ? 1u : 0u) | (xm ? 2u : 0u) | (xm && zp ? 4u : 0u) | (zm ? 8u : 0u) |
-                               (zp ? 16u : 0u) | (xp && zm ? 32u : 0u) | (xp ? 64u : 0u) | (xp && zp ? 128u : 0u);
+        const bool xm = inner || ix > 0, xp = inner || ix + 1 < nx, zm = inner || iz > 0, zp = inner || iz + 1 < nz;
+        const unsigned valid = inner ? 0xffu :
+                               ((xm && zm ? 1u : 0u) | (xm ? 2u : 0u) | (xm && zp ? 4u : 0u) | (zm ? 8u : 0u) |
+                                (zp ? 16u : 0u) | (xp && zm ? 32u : 0u) | (xp ? 64u : 0u) | (xp && zp ? 128u : 0u));
         const float hc = hs[li];
         float h[8];
 #pragma unroll
@@ -230,7 +236,7 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
           // at `abrasion` efficiency (rock -> suspended sediment). The cell is owned: plain updates.
           const float take = fminf(dh, fmaxf(hc - rock_c, 0.0f));
           const float ground = C.abrasion * (dh - take);
-          if (ground > 0.0f) { rock_c -= ground; rs[li] = rock_c; s_dirty_rock = 1u; }
+          if (ground > 0.0f) { rock_c -= ground; rs[li] = rock_c; dirty_rock = 1; }
           dh = take + ground;
         }
         float c1 = hc - dh;                                                                      // :110-112
@@ -239,7 +245,7 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         int s[8];
         const unsigned moved = LAYERED ? block::cascade_sorted<true>(c1, h, valid, T, v, s, rock_c, rk)   // :114
                                        : block::cascade_sorted<false>(c1, h, valid, T, v, s, rock_c, rk);
-        if (moved != 0u || dh != 0.0f) { hs[li] = c1; s_dirty = 1u; }
+        if (moved != 0u || dh != 0.0f) { hs[li] = c1; dirty = 1; }
         // slot -> (dx + 1, dz + 1) packed four bits per slot (world.hpp:83-92): two shifts instead of the branches of slot_dx / slot_dz
 #pragma unroll
         for (int i8 = 0; i8 < 8; i8++)
@@ -252,14 +258,9 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         unsigned col;
         if (m.oob(jx, jz)) { n_oob++; lost += q.sed; q.age = -1; col = DEAD; }                   // :32-38 (the next fly() call)
         else if (q.age > C.max_age) { n_age++; lost += q.sed; q.age = -1; col = DEAD; }          // :45-46
-        else col = service_colour(jx, jz, x0, z0, nx, nz);
-        if (RL2) {
-          __stcg(ra + p, make_float4(q.px, q.py, q.pz, q.sed));
-          __stcg(rb + p, make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age)));
-        } else {
-          ra[p] = make_float4(q.px, q.py, q.pz, q.sed);
-          rb[p] = make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age));
-        }
+        else col = service_colour<TT>(jx, jz, x0, z0, nx, nz);
+        __stcg(ga + p, make_float4(q.px, q.py, q.pz, q.sed));
+        __stcg(gb + p, make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age)));
         pcol[p] = (unsigned char)col;
       }
       __syncthreads();
@@ -267,14 +268,14 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
     if (served == 0u) break;          // everything left in the tile is parked or dead (uniform over the CTA)
   }
 
-  // ---- store: heights if anything moved, every record (dead ones marked by age < 0), destination counts ----
-  if (s_dirty) {
+  // ---- store: heights if anything moved; destination counts of the survivors (dead records carry age < 0) ----
+  if (__syncthreads_or(dirty)) {
     for (int i = tid; i < TT * TT; i += TNT) {
       const int gx = x0 + i / TT, gz = z0 + i % TT;
       if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) m.height[(size_t)gx * (size_t)nz + gz] = hs[i];
     }
   }
-  if (LAYERED && s_dirty_rock) {
+  if (LAYERED && __syncthreads_or(dirty_rock)) {
     for (int i = tid; i < TT * TT; i += TNT) {
       const int gx = x0 + i / TT, gz = z0 + i % TT;
       if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) m.rock[(size_t)gx * (size_t)nz + gz] = rs[i];
@@ -285,16 +286,11 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
     bool alive = false;
     int dest = 0;
     if (p < n) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p < np) {
-        alive = pcol[p] != DEAD;
-        if (RL2) { if (alive) a = __ldcg(ga + p); }
-        else { a = ra[p]; ga[p] = a; gb[p] = rb[p]; }
-      } else {
-        a = __ldcs(ga + p);             // beyond the shared-memory capacity: parked for this super-round
-        alive = true;
+      alive = p >= np || pcol[p] != DEAD;              // (beyond pcap: parked for this super-round)
+      if (alive) {
+        const float4 a = __ldcg(ga + p);
+        dest = tile_of(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), G.off_next, G.ntz_next, TT);
       }
-      if (alive) dest = tile_of(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), G.off_next, G.ntz_next);
     }
     count_dest(S.count, dest, alive);
   }
@@ -379,7 +375,7 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(MapView m, TileSched 
       if (!active) n_oob++;                                          // dies in its first fly() call
     }
     int dest = 0;
-    if (active) dest = tile_of(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), G.off_next, G.ntz_next);
+    if (active) dest = tile_of(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), G.off_next, G.ntz_next, G.edge);
     const unsigned has = __ballot_sync(0xffffffffu, active);
     if (active) {
       const unsigned grp = __match_any_sync(has, dest);
@@ -402,79 +398,105 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(MapView m, TileSched 
   }
 }
 
-static size_t tile_smem_bytes(bool layered, int pcap) {
-  return (size_t)(layered ? 2 : 1) * TT * TT * sizeof(float) + (size_t)pcap * ((RL2 ? 0 : 2 * sizeof(float4)) + sizeof(unsigned short) + 1) +
-         (size_t)TLAT * TLAT * sizeof(unsigned) + 16;
+static size_t tile_smem_bytes(int shape, bool layered, int pcap) {
+  const int tt = kShapes[shape].edge;
+  return (size_t)(layered ? 2 : 1) * tt * tt * sizeof(float) + (size_t)pcap * (sizeof(unsigned short) + 1) +
+         (size_t)(tt / 3) * (tt / 3) * sizeof(unsigned) + 16;
 }
 
-// largest pcap (multiple of 64) the device can give one CTA
-int tile_max_pcap(bool layered, int smem_optin) {
-  const long long fixed = (long long)tile_smem_bytes(layered, 0) + 1024;
-  long long p = ((long long)smem_optin - fixed) / (RL2 ? 3 : 35);
+// largest pcap (multiple of 64) the device can give one CTA; the list holds 16-bit particle indices
+int tile_max_pcap(int shape, bool layered, int smem_optin) {
+  const long long fixed = (long long)tile_smem_bytes(shape, layered, 0) + 1024;
+  long long p = ((long long)smem_optin - fixed) / 3;
   p = p / 64 * 64;
-  return p < 64 ? 0 : (int)(p > 8192 ? 8192 : p);
+  return p < 64 ? 0 : (int)(p > 32768 ? 32768 : p);
 }
 
-static TileGeom tile_geom(const MapView& m, int s) {
+static TileGeom tile_geom(const MapView& m, int tt, int s) {
   TileGeom G{};
-  G.off_cur = (s % 3) * (TT / 3);
-  G.ntx_cur = (m.nx + G.off_cur + TT - 1) / TT; G.ntz_cur = (m.nz + G.off_cur + TT - 1) / TT;
-  G.off_next = ((s + 1) % 3) * (TT / 3);
-  G.ntx_next = (m.nx + G.off_next + TT - 1) / TT; G.ntz_next = (m.nz + G.off_next + TT - 1) / TT;
+  G.edge = tt;
+  G.off_cur = (s % 3) * (tt / 3);
+  G.ntx_cur = (m.nx + G.off_cur + tt - 1) / tt; G.ntz_cur = (m.nz + G.off_cur + tt - 1) / tt;
+  G.off_next = ((s + 1) % 3) * (tt / 3);
+  G.ntx_next = (m.nx + G.off_next + tt - 1) / tt; G.ntz_next = (m.nz + G.off_next + tt - 1) / tt;
   G.cur = s & 1;
   return G;
 }
 
+// tiles of the tiling with the most tiles (allocation size of the per-tile arrays: the smallest edge, the largest shift)
 int tile_max_tiles(int nx, int nz) {
-  const int off = 2 * (TT / 3);
-  return ((nx + off + TT - 1) / TT) * ((nz + off + TT - 1) / TT);
+  int best = 0;
+  for (const TileShape& sh : kShapes) {
+    const int off = 2 * (sh.edge / 3);
+    const int t = ((nx + off + sh.edge - 1) / sh.edge) * ((nz + off + sh.edge - 1) / sh.edge);
+    if (t > best) best = t;
+  }
+  return best;
+}
+
+// Shape for a map: the big tiles when they still give every SM a few CTAs
+int tile_pick(int nx, int nz, int sm_count) {
+  const int big = kShapes[1].edge;
+  const long long tiles = (long long)((nx + big - 1) / big) * ((nz + big - 1) / big);
+  return tiles >= 3LL * sm_count ? 1 : 0;
+}
+
+template <int TT, int TNT>
+static void launch_fly(bool layered, int grid, size_t smem, cudaStream_t st, const MapView& m, const ParConst& C, const block::Thr& T,
+                       const TileSched& S, const TileGeom& G, uint2 key, uint32_t call, DevStats* stats) {
+  if (layered) tile_fly_kernel<TT, TNT, true><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats);
+  else tile_fly_kernel<TT, TNT, false><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats);
 }
 
 // Super-round s of a call (s = -1: only the injection of super-round 0's particles). Returns the launches made.
-int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSched& S, int s, int K, int pcap,
+int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSched& S, int shape, int s, int K, int pcap,
                             int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   block::Thr T;
   T.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;   // host IEEE fp32: the values exact::cascade_thresholds computes
   T.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
   T.settling = p.settling;
+  const int tt = kShapes[shape].edge, nt = kShapes[shape].threads;
   TileGeom G;
-  if (s >= 0) G = tile_geom(m, s);
+  if (s >= 0) G = tile_geom(m, tt, s);
   else {                                      // no tiles yet: cur = 1 holds an empty segment table (base[1][0] = 0)
-    G = tile_geom(m, 2);                      // (s + 1) % 3 == 0  -> next tiling is tiling 0
+    G = tile_geom(m, tt, 2);                  // (s + 1) % 3 == 0  -> next tiling is tiling 0
     G.ntx_cur = 0; G.ntz_cur = 0; G.cur = 1;
   }
   G.inj_lo = inj_lo; G.inj_hi = inj_hi;
   G.micro0 = s >= 0 ? (unsigned)s * 9u * (unsigned)K : 0u;
   G.K = K; G.pcap = pcap;
   const int ntiles = G.ntx_cur * G.ntz_cur;
-  const int inj_blocks = (inj_hi - inj_lo + TNT * 8 - 1) / (TNT * 8);
+  const int inj_blocks = (inj_hi - inj_lo + nt * 8 - 1) / (nt * 8);
   const bool layered = m.rock != nullptr;
-  const size_t smem = tile_smem_bytes(layered, pcap);
+  const size_t smem = tile_smem_bytes(shape, layered, pcap);
   int launches = 0;
   if (ntiles + inj_blocks > 0) {
-    if (layered) tile_fly_kernel<true><<<ntiles + inj_blocks, TNT, smem, st>>>(m, make_const(p), T, S, G, key, call, stats);
-    else tile_fly_kernel<false><<<ntiles + inj_blocks, TNT, smem, st>>>(m, make_const(p), T, S, G, key, call, stats);
+    if (shape == 1) launch_fly<120, 256>(layered, ntiles + inj_blocks, smem, st, m, make_const(p), T, S, G, key, call, stats);
+    else launch_fly<60, 128>(layered, ntiles + inj_blocks, smem, st, m, make_const(p), T, S, G, key, call, stats);
     launches++;
   }
   tile_scan_kernel<<<1, 1024, 0, st>>>(S, G.ntx_next * G.ntz_next, G.cur ^ 1);
-  const long long work = (long long)S.cap;
-  long long blocks = (work + 255) / 256;
+  long long blocks = ((long long)S.cap + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   tile_scatter_kernel<<<(int)blocks, 256, 0, st>>>(m, S, G, key, call, stats);
   return launches + 2;
 }
 
-cudaError_t tile_configure(bool layered, int pcap) {
-  const size_t smem = tile_smem_bytes(layered, pcap);
-  return layered ? cudaFuncSetAttribute(tile_fly_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                 : cudaFuncSetAttribute(tile_fly_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t tile_configure(int shape, bool layered, int pcap) {
+  const int smem = (int)tile_smem_bytes(shape, layered, pcap);
+  const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  if (shape == 1)
+    return layered ? cudaFuncSetAttribute(tile_fly_kernel<120, 256, true>, at, smem) : cudaFuncSetAttribute(tile_fly_kernel<120, 256, false>, at, smem);
+  return layered ? cudaFuncSetAttribute(tile_fly_kernel<60, 128, true>, at, smem) : cudaFuncSetAttribute(tile_fly_kernel<60, 128, false>, at, smem);
 }
 
 void preload_tile() {
   cudaFuncAttributes a;
-  cudaFuncGetAttributes(&a, tile_fly_kernel<false>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<true>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, true>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, true>);
   cudaFuncGetAttributes(&a, tile_scan_kernel);
   cudaFuncGetAttributes(&a, tile_scatter_kernel);
 }

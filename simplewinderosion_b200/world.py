@@ -22,7 +22,7 @@ MASSFLOW_TRACK, MOMENTUMX_TRACK, MOMENTUMY_TRACK, MOMENTUMZ_TRACK = 5, 6, 7, 8
 NUM_PLANES = 9
 MODE_DETERMINISTIC, MODE_PARALLEL = 0, 1
 OPT_CASCADE_VARIANT, OPT_CASCADE_INTERVAL, OPT_KERNEL_TIMING, OPT_CUDA_GRAPH, OPT_PDL, OPT_CALL_BATCHES = 1, 2, 3, 4, 5, 6
-OPT_SCHEDULE, OPT_STAGGER_ROUNDS, OPT_PERSISTENT, OPT_PERIODIC, OPT_TILE_ROUNDS = 7, 8, 9, 10, 11
+OPT_SCHEDULE, OPT_STAGGER_ROUNDS, OPT_PERSISTENT, OPT_PERIODIC, OPT_TILE_ROUNDS, OPT_TILE_SHAPE = 7, 8, 9, 10, 11, 12
 SCHEDULE_COLOUR_QUEUES, SCHEDULE_LOCKSTEP, SCHEDULE_TILES = 0, 1, 2
 
 # numpy view of the reference's 36-byte AoS record, quad::cell (cellpool.h:226-240)
@@ -323,5 +323,5 @@ __all__ = [
     "HEIGHT", "MASSFLOW", "MOMENTUMX", "MOMENTUMY", "MOMENTUMZ", "MASSFLOW_TRACK",
     "MOMENTUMX_TRACK", "MOMENTUMY_TRACK", "MOMENTUMZ_TRACK", "NUM_PLANES",
     "MODE_DETERMINISTIC", "MODE_PARALLEL", "OPT_CASCADE_VARIANT", "OPT_CASCADE_INTERVAL", "OPT_KERNEL_TIMING", "OPT_CUDA_GRAPH", "OPT_PDL", "OPT_CALL_BATCHES",
-    "OPT_SCHEDULE", "OPT_STAGGER_ROUNDS", "OPT_PERSISTENT", "OPT_PERIODIC", "SCHEDULE_COLOUR_QUEUES", "SCHEDULE_LOCKSTEP", "SCHEDULE_TILES", "OPT_TILE_ROUNDS",
+    "OPT_SCHEDULE", "OPT_STAGGER_ROUNDS", "OPT_PERSISTENT", "OPT_PERIODIC", "SCHEDULE_COLOUR_QUEUES", "SCHEDULE_LOCKSTEP", "SCHEDULE_TILES", "OPT_TILE_ROUNDS", "OPT_TILE_SHAPE",
 ]

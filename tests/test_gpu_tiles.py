@@ -20,11 +20,13 @@ pytestmark = pytest.mark.gpu
 TILES = {swe.OPT_SCHEDULE: swe.SCHEDULE_TILES}
 
 
-def test_tiles_headline_density_quarter_particle_per_cell():
-    """1024^2 / 262,144 particles = 0.25 per cell: the density of bench.py's headline (4096^2 / 4,194,304)."""
+@pytest.mark.parametrize("shape", [1, 0], ids=["120x120", "60x60"])
+def test_tiles_headline_density_quarter_particle_per_cell(shape):
+    """1024^2 / 262,144 particles = 0.25 per cell: the density of bench.py's headline (4096^2 / 4,194,304), with the
+    tile geometry the headline runs (120 x 120 cells, 24 rounds per super-round) and with the small one."""
     n, cycles = 1024, 1 << 18
     hm = noise_map(n, seed=1, layers=8, workers=8)
-    r = compare(n, cycles, hm, opts=TILES)
+    r = compare(n, cycles, hm, opts={**TILES, swe.OPT_TILE_SHAPE: shape})
     assert abs(r["steps"]) < 0.03, r
     assert abs(r["export"]) < 0.05, r
     assert r["tv"] < 0.12 and r["spec"] > 0.99, r
@@ -33,10 +35,12 @@ def test_tiles_headline_density_quarter_particle_per_cell():
     assert r["drift"] < 2e-6, r
 
 
-def test_tiles_quarter_particle_per_cell_512():
+@pytest.mark.parametrize("shape", [0, 1], ids=["60x60", "120x120"])
+def test_tiles_quarter_particle_per_cell_512(shape):
+    """Both compiled tile geometries (a 512^2 map would pick 60 x 60 by itself; 4096^2 picks 120 x 120)."""
     n, cycles = 512, 1 << 16
     hm = noise_map(n, seed=1, layers=8, workers=4)
-    r = compare(n, cycles, hm, opts=TILES)
+    r = compare(n, cycles, hm, opts={**TILES, swe.OPT_TILE_SHAPE: shape})
     assert abs(r["steps"]) < 0.03 and abs(r["export"]) < 0.05, r
     assert r["tv"] < 0.12 and r["spec"] > 0.99, r
     assert r["field"] > 0.95 and r["profile"] > 0.9, r
@@ -74,8 +78,9 @@ def test_tiles_sparse_reference_frame():
     assert r["drift"] < 2e-6, r
 
 
+@pytest.mark.parametrize("shape", [0, 1], ids=["60x60", "120x120"])
 @pytest.mark.parametrize("nx,nz", [(100, 100), (61, 59), (200, 90), (90, 333), (20, 500)])
-def test_tiles_odd_map_shapes_counters_and_mass_balance(nx, nz):
+def test_tiles_odd_map_shapes_counters_and_mass_balance(nx, nz, shape):
     """Maps that are not multiples of the tile edge (60), smaller than a tile, and non-square: every particle is
     accounted for, the mass balance closes, the result is statistically the colour-queue scheduler's."""
     rs = np.random.RandomState(nx * 7 + nz)
@@ -83,7 +88,7 @@ def test_tiles_odd_map_shapes_counters_and_mass_balance(nx, nz):
     cycles = nx * nz // 2
     out = {}
     for name, sched in (("tiles", swe.SCHEDULE_TILES), ("queues", swe.SCHEDULE_COLOUR_QUEUES)):
-        w = swe.World(nx, nz); w.set_option(swe.OPT_SCHEDULE, sched)
+        w = swe.World(nx, nz); w.set_option(swe.OPT_SCHEDULE, sched); w.set_option(swe.OPT_TILE_SHAPE, shape)
         w.upload(hm); w.srand(5)
         for _ in range(2):
             w.erode(cycles, swe.MODE_PARALLEL)
@@ -157,12 +162,15 @@ def test_tiles_options_and_fallbacks():
     w = swe.World(96)
     w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_TILES)
     assert w.get_option(swe.OPT_SCHEDULE) == swe.SCHEDULE_TILES
-    assert w.get_option(swe.OPT_TILE_ROUNDS) == 16
+    assert w.get_option(swe.OPT_TILE_ROUNDS) == 0 and w.get_option(swe.OPT_TILE_SHAPE) == -1     # auto
     w.set_option(swe.OPT_TILE_ROUNDS, 8)
     assert w.get_option(swe.OPT_TILE_ROUNDS) == 8
-    for bad in (0, 65):
+    for bad in (-1, 65):
         with pytest.raises(swe.SweError):
             w.set_option(swe.OPT_TILE_ROUNDS, bad)
+    for bad in (-2, 2):
+        with pytest.raises(swe.SweError):
+            w.set_option(swe.OPT_TILE_SHAPE, bad)
     with pytest.raises(swe.SweError):
         w.set_option(swe.OPT_SCHEDULE, 3)
     w.upload(generate.flat_sand(96, seed=1)); w.srand(2)

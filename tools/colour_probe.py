@@ -22,6 +22,8 @@ w = swe.World(n)
 w.set_option(swe.OPT_SCHEDULE, sched)
 w.set_option(swe.OPT_STAGGER_ROUNDS, stagger)
 w.set_option(swe.OPT_PERSISTENT, int(os.environ.get("PERSISTENT", "1")))
+if "TILE_SHAPE" in os.environ:
+    w.set_option(swe.OPT_TILE_SHAPE, int(os.environ["TILE_SHAPE"]))
 if "TILE_ROUNDS" in os.environ:
     w.set_option(swe.OPT_TILE_ROUNDS, int(os.environ["TILE_ROUNDS"]))
 if kind == "noise":

@@ -12,6 +12,7 @@ if what == "fly4096":
     w.sync(); print(w.stats().last_fly_ms)
 elif what == "fly4096tile1":
     w = swe.World(4096); w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_TILES)
+    if "TILE_ROUNDS" in os.environ: w.set_option(swe.OPT_TILE_ROUNDS, int(os.environ["TILE_ROUNDS"]))
     w.generate_noise(1, 8); w.normalize(); w.srand(1)
     w.erode(1 << 22, swe.MODE_PARALLEL)
     w.sync(); print(w.stats().last_fly_ms)
