@@ -93,15 +93,22 @@ typedef enum swe_option {
    * +24 % at 0.25 particles per cell, within 1.3 % at 0.03), and batches trade throughput for that
    * fidelity. Track reset and EMA stay once per call. */
   SWE_OPT_CALL_BATCHES = 6,
-  /* Parallel mode, single-GPU engines: 0 (default) = colour-queue scheduler: the cells are coloured
-   * 3 x 3, a micro-round serves one colour, and every particle standing on a cell of that colour
-   * (one per cell, the others wait) flies one Wind::fly step, erodes and runs World::cascade on its
-   * 3x3 block at once -- blocks of one colour are disjoint, so each particle sees the reference's
-   * order of operations (wind.hpp:108-114) and the height plane needs no atomics. 1 = round 1's
-   * lock-step pipeline (all particles step once, then one stamped cascade at every touched cell);
-   * faster per step, but it exports +24 % more sand than the reference at 0.25 particles per cell. */
+  /* Parallel mode: how the particles of a call are scheduled. All three keep Wind::fly's arithmetic; they differ
+   * in how close the ORDER of operations stays to the reference's one-particle-after-another loop.
+   * 2 (default) = tile-resident scheduler (single-GPU engines, closed boundary): the map is cut into tiles, one
+   * CTA keeps a tile's heights in shared memory for a super-round of K rounds of nine colour micro-rounds and
+   * serves the particles standing in the tile's interior; three shifted tilings take turns (csrc/swe_tile.cu).
+   * Stripe engines and periodic maps run schedule 0 when 2 is selected.
+   * 0 = colour-queue scheduler: the cells are coloured 3 x 3, a micro-round serves one colour over the whole map
+   * (one persistent cooperative kernel, a grid barrier per micro-round), and every particle standing on a cell
+   * of that colour (one per cell, the others wait) flies one Wind::fly step, erodes and runs World::cascade on
+   * its 3x3 block at once -- blocks of one colour are disjoint, so each particle sees the reference's order of
+   * operations (wind.hpp:108-114) and the height plane needs no atomics. Schedules 0 and 2 serve a particle the
+   * same way and are parity-green at the benchmarked densities (tests/test_gpu_density.py, test_gpu_tiles.py).
+   * 1 = round 1's lock-step pipeline (all particles step once, then one stamped cascade at every touched cell);
+   * it exports +24 % more sand than the reference at 0.25 particles per cell. */
   SWE_OPT_SCHEDULE = 7,
-  /* Colour-queue scheduler: the call's particles are injected evenly over the first S rounds (one
+  /* Colour-queue and tile-resident schedulers: the call's particles are injected evenly over the first S rounds (one
    * round = nine micro-rounds) instead of all at once, so that all particle ages are in flight
    * together as in the reference. -1 (default) = auto: S = 8 * (particles per cell) * (maxAge + 2),
    * at most 4 * (maxAge + 2); calls thinner than 0.02 particles per cell are injected at once. */
@@ -120,8 +127,8 @@ typedef enum swe_option {
    * rock plane. Default 0. */
   SWE_OPT_PERIODIC = 10,
   /* Tile-resident schedule (SWE_OPT_SCHEDULE = 2): rounds (nine micro-rounds each) a CTA keeps its tile in shared
-   * memory before the particles are re-sorted into the next, shifted tiling. 0 (default) = auto: tile edge / 5
-   * (12 for 60 x 60 tiles, 24 for 120 x 120); range [0, 64]. */
+   * memory before the particles are re-sorted into the next, shifted tiling. 0 (default) = auto
+   * (16 for 60 x 60 tiles, 24 for 120 x 120); range [0, 64]. */
   SWE_OPT_TILE_ROUNDS = 11,
   /* Tile-resident schedule: tile geometry. -1 (default) = by map size (120 x 120 cells / 256 threads when that
    * still gives every SM three tiles, else 60 x 60 / 128 threads), 0 = 60 x 60, 1 = 120 x 120. */

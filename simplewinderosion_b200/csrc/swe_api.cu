@@ -86,7 +86,8 @@ struct swe_engine {
   int opt_cuda_graph = 1;             // replay the parallel erode of a single-GPU engine as one CUDA graph
   int opt_pdl = 1;                    // programmatic dependent launches between the round kernels
   int opt_call_batches = 1;           // a parallel call's particles fly as this many successive batches
-  int opt_schedule = 0;               // 0 = colour-queue scheduler (swe_queue.cu), 1 = lock-step rounds + stamped cascade
+  int opt_schedule = 2;               // 2 = tile-resident scheduler (swe_tile.cu; stripes and periodic maps run the colour queues instead),
+                                      // 0 = colour-queue scheduler (swe_queue.cu), 1 = lock-step rounds + stamped cascade
   int opt_stagger = -1;               // colour queues: rounds over which the call's particles are injected (-1 = auto)
   ColourQueues cq{};                  // queues + claim plane of the colour-queue scheduler
   int sm_count = 148;
@@ -676,7 +677,7 @@ int erode_tile(swe_engine* e, int cycles) {
   const bool layered = e->m.rock != nullptr;
   const int shape = e->opt_tile_shape >= 0 ? e->opt_tile_shape : tile_pick(e->m.nx, e->m.nz, e->sm_count);
   const int TE = tile_edge(shape);
-  const int K = e->opt_tile_rounds > 0 ? e->opt_tile_rounds : TE / 5;
+  const int K = e->opt_tile_rounds > 0 ? e->opt_tile_rounds : (TE >= 120 ? 24 : 16);   // (A/B on B200; tools/par_emul.c mode D for the parity)
   const int life = e->p.max_age + 2;
   long long S = colour_stagger_micro(e, cycles) / 9;      // rounds
   // expected particles per tile while the injection runs (Poisson): mean + 5 sigma + slack stays on chip; a tile

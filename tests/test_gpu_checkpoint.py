@@ -82,7 +82,7 @@ def test_parallel_resume_continues_the_call_counter(tmp_path):
     # ... and so does the mass balance: sum(height) + sediment carried away is still the initial mass
     s0 = float(hm.astype(np.float64).sum())
     assert abs(c.sum_plane() + sc.sediment_lost - s0) < 2e-5 * abs(s0)
-    assert c.get_option(swe.OPT_SCHEDULE) == swe.SCHEDULE_COLOUR_QUEUES
+    assert c.get_option(swe.OPT_SCHEDULE) == swe.SCHEDULE_TILES          # (the default)
     ha, hc = a.download(), c.download()
     assert np.corrcoef((ha - hm).ravel(), (hc - hm).ravel())[0, 1] > 0.9
     d = fresh()

@@ -28,8 +28,8 @@ def compare(n, cycles, hm, calls=1, opts=None):
     ora.srand(1)
     so = sum(ora.erode(cycles).steps for _ in range(calls))
     w = swe.World(n)
-    for k, v in (opts or {}).items():
-        w.set_option(k, v)
+    for k, v in {swe.OPT_SCHEDULE: swe.SCHEDULE_COLOUR_QUEUES, **(opts or {})}.items():   # (this file pins the colour queues; the
+        w.set_option(k, v)                                                                 # default schedule is tests/test_gpu_tiles.py's)
     w.upload(hm)
     w.srand(1)
     for _ in range(calls):
@@ -121,7 +121,7 @@ def test_stagger_option_and_sparse_calls():
     and needs ~9 micro-rounds per step; a forced stagger spreads the injection."""
     n = 512
     hm = noise_map(n, seed=1, layers=8, workers=4)
-    w = swe.World(n); w.upload(hm); w.srand(1)
+    w = swe.World(n); w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_COLOUR_QUEUES); w.upload(hm); w.srand(1)
     w.erode(8 * n, swe.MODE_PARALLEL)
     a = w.stats().last_micro_rounds
     w.set_option(swe.OPT_STAGGER_ROUNDS, 600)
@@ -144,7 +144,7 @@ def test_cfg2_dune_wavelength_matches_sequential_reference():
     n, cycles, calls = 256, 1 << 16, 6
     hm = generate.flat_sand(n, seed=42)
     ora = PortWorld(n); ora.set_plane(0, hm); ora.srand(1)
-    w = swe.World(n); w.upload(hm); w.srand(1)
+    w = swe.World(n); w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_COLOUR_QUEUES); w.upload(hm); w.srand(1)
     for _ in range(calls):
         ora.erode(cycles)
         w.erode(cycles, swe.MODE_PARALLEL)

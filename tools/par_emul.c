@@ -379,3 +379,98 @@ long long emul_erode_tiles(swo_world* w, int cycles, int stagger, int T, int K, 
   if (rounds_out) *rounds_out = sr * K;
   return steps;
 }
+
+/* Option E: tile-resident super-rounds with BLOCK CLAIMS instead of colour phases (csrc/swe_tile.cu, claim mode).
+ * An ATTEMPT serves particles of all colours at once: every serviceable particle (interior of its home tile, as in
+ * option D) bids for the 3x3-lattice cells its 3x3 block touches (1, 2 or 4 of them) with a priority that is unique
+ * per particle and reshuffled every attempt; a particle whose bid is the highest on ALL its lattice cells flies one
+ * step + cascade, the others wait for the next attempt. Winners have disjoint blocks, so an attempt is conflict-free
+ * and equivalent to processing its winners one after another. Particle i becomes active at attempt i * stagger / n
+ * (granularity: the super-round of A attempts that contains it). */
+static unsigned long long emul_prio(unsigned i, unsigned t) {
+  unsigned long long z = ((unsigned long long)i << 32 | t) + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+  return (z << 24) | i;   /* unique per particle */
+}
+long long emul_erode_claims(swo_world* w, int cycles, int stagger, int T, int A, int flags, double* lost_out,
+                            long long* rounds_out) {
+  const int nx = w->nx, nz = w->nz;
+  const size_t area = (size_t)nx * nz;
+  for (int k = 5; k < 9; k++) memset(w->plane[k], 0, sizeof(float) * area);
+  long long steps = 0, sr = 0;
+  double lost = 0.0;
+  const int L = (flags & 2) ? 2 : 3;                      /* claim lattice cell edge */
+  const int lnx = nx / L + 2, lnz = nz / L + 2;
+  unsigned long long* claim = (unsigned long long*)calloc((size_t)lnx * lnz, sizeof(unsigned long long));
+  const int n = cycles;
+  swo_particle* q = (swo_particle*)malloc(sizeof(swo_particle) * (size_t)(n + 1));
+  char* alive = (char*)malloc((size_t)n + 1);
+  int* home = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+  for (int i = 0; i < n; i++) { swo_spawn(w, &q[i]); alive[i] = 1; }
+  int live = n;
+  const int ntz = nz / T + 2;
+  while (live > 0) {
+    const int off = (int)(sr % 3) * (T / 3);
+    for (int i = 0; i < n; i++) {
+      home[i] = -1;
+      if (!alive[i]) continue;
+      const int ix = (int)roundf(q[i].pos[0]), iz = (int)roundf(q[i].pos[2]);
+      if (oob(w, ix, iz)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
+      if (stagger > 0 && ((long long)i * stagger) / n >= (sr + 1) * A) continue;
+      home[i] = ((ix + off) / T) * ntz + (iz + off) / T;
+    }
+    for (int a = 0; a < A; a++) {
+      const unsigned t = (unsigned)(sr * A + a);
+      int nc = 0;
+      for (int i = 0; i < n; i++) {
+        if (!alive[i] || home[i] < 0) continue;
+        const int ix = (int)roundf(q[i].pos[0]), iz = (int)roundf(q[i].pos[2]);
+        if (oob(w, ix, iz)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
+        if (((ix + off) / T) * ntz + (iz + off) / T != home[i]) continue;
+        const int lx = (ix + off) % T, lz = (iz + off) % T;
+        if ((lx == 0 && ix != 0) || (lx == T - 1 && ix != nx - 1) || (lz == 0 && iz != 0) || (lz == T - 1 && iz != nz - 1)) continue;
+        cand[nc++] = i;
+        const unsigned long long pr = ((unsigned long long)(t + 1) << 40) ^ 0 , key = emul_prio((unsigned)i, t);
+        (void)pr;
+        for (int cx = (ix - 1 < 0 ? 0 : ix - 1) / L; cx <= (ix + 1) / L; cx++)
+          for (int cz = (iz - 1 < 0 ? 0 : iz - 1) / L; cz <= (iz + 1) / L; cz++) {
+            unsigned long long* c = &claim[(size_t)cx * lnz + cz];
+            if (*c < key) *c = key;
+          }
+      }
+      for (int j = 0; j < nc; j++) {
+        const int i = cand[j];
+        const int ix = (int)roundf(q[i].pos[0]), iz = (int)roundf(q[i].pos[2]);
+        const unsigned long long key = emul_prio((unsigned)i, t);
+        int won = 1;
+        for (int cx = (ix - 1 < 0 ? 0 : ix - 1) / L; cx <= (ix + 1) / L; cx++)
+          for (int cz = (iz - 1 < 0 ? 0 : iz - 1) / L; cz <= (iz + 1) / L; cz++)
+            if (claim[(size_t)cx * lnz + cz] != key) won = 0;
+        cand[j] = won ? i : -1;
+      }
+      /* clear the bids, then the winners step (disjoint blocks: order irrelevant) */
+      memset(claim, 0, (size_t)lnx * lnz * sizeof(unsigned long long));
+      for (int j = 0; j < nc; j++) {
+        const int i = cand[j];
+        if (i < 0) continue;
+        const int ix = (int)roundf(q[i].pos[0]), iz = (int)roundf(q[i].pos[2]);
+        int cell;
+        if (!fly_nc(w, &q[i], NULL, &cell)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
+        steps++;
+        swo_cascade(w, ix, iz);
+      }
+    }
+    sr++;
+    if (getenv("EMUL_DBG") && sr % 8 == 0) fprintf(stderr, "sr %lld live %d steps %lld\n", sr, live, steps);
+  }
+  const float lr = w->p.lrate;
+  for (int kk = 1; kk < 5; kk++) {
+    float* f = w->plane[kk]; const float* t = w->plane[kk + 4];
+    for (size_t i = 0; i < area; i++) f[i] = (1.0f - lr) * f[i] + lr * t[i];
+  }
+  free(claim); free(q); free(alive); free(home); free(cand);
+  if (lost_out) *lost_out = lost;
+  if (rounds_out) *rounds_out = sr * A;
+  return steps;
+}

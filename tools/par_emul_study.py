@@ -32,6 +32,8 @@ L.emul_erode_queues.restype = C.c_longlong
 L.emul_erode_queues.argtypes = [W, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
 L.emul_erode_tiles.restype = C.c_longlong
 L.emul_erode_tiles.argtypes = [W, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+L.emul_erode_claims.restype = C.c_longlong
+L.emul_erode_claims.argtypes = [W, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
 L.emul_erode_phased.restype = C.c_longlong
 L.emul_erode_phased.argtypes = [W, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
 
@@ -81,6 +83,9 @@ def main():
         if v.startswith("q"):   # colour queues: qS,order
             B, S = (int(x) for x in v[1:].split(","))
             Cm, V, K = -2, 0, 1
+        elif v.startswith("c"):   # tile-resident super-rounds with block claims: cS,T,A,flags (S in attempts)
+            B, S, V, K = (int(x) for x in v[1:].split(","))
+            Cm = -4
         elif v.startswith("t"):   # tile-resident super-rounds: tS,T,K,flags
             B, S, V, K = (int(x) for x in v[1:].split(","))   # stagger, T, K, flags
             Cm = -3
@@ -96,6 +101,8 @@ def main():
         for _ in range(calls):
             if Cm == -2:
                 sg += L.emul_erode_queues(wv, cycles, B, S, C.byref(lost), C.byref(rr))
+            elif Cm == -4:
+                sg += L.emul_erode_claims(wv, cycles, B, S, V, K, C.byref(lost), C.byref(rr))
             elif Cm == -3:
                 sg += L.emul_erode_tiles(wv, cycles, B, S, V, K, C.byref(lost), C.byref(rr))
             elif Cm == -1:
