@@ -543,7 +543,6 @@ def run_ours(args) -> None:
     if world == 1:
         w = swe.World(n, device=local)
         w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_TILES)
-        tile_rounds = w.get_option(swe.OPT_TILE_ROUNDS)
     else:
         # weak scaling: every GPU owns one n x n stripe of an (n*world) x n map (copies of the
         # single-GPU map stacked along the wind axis) and the call flies particles*world particles.
@@ -624,7 +623,7 @@ def run_ours(args) -> None:
         w.set_option(swe.OPT_KERNEL_TIMING, 1)
     round_ms = casc_ms = fly_ms = erode_ms = 0.0
     fly_steps = 0
-    micro_rounds = 0
+    micro_rounds = super_rounds = 0
     for _ in range(args.steps):
         s_before = w.stats().steps
         w.erode(particles_call, swe.MODE_PARALLEL)
@@ -632,6 +631,7 @@ def run_ours(args) -> None:
         round_ms += s.last_round_ms; casc_ms += s.last_cascade_ms; fly_ms += s.last_fly_ms; erode_ms += s.last_erode_ms
         fly_steps += s.steps - s_before
         micro_rounds += s.last_micro_rounds
+        super_rounds += s.last_super_rounds
     if lockstep:
         w.set_option(swe.OPT_KERNEL_TIMING, 0)
     rounds_per_call = w.params.max_age + 2
@@ -711,17 +711,17 @@ def run_ours(args) -> None:
                 "result_check_mean_height": mean_h},
         "gpu_launches": int(launches),
         "roofline": ({
-            "bound": "hbm", "kernel": "tile_fly_kernel (Wind::fly + erosion + World::cascade per particle step; one CTA per 60x60 tile, "
+            "bound": "hbm", "kernel": "tile_fly_kernel (Wind::fly + erosion + World::cascade per particle step; one CTA per 120x120 tile, "
                                       "heights and particles in shared memory)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic("tile_fly"), "peak_source": peak_src,
             "algorithmic_bytes_per_step": BYTES_PER_STEP,
-            "launches_per_step": micro_rounds / args.steps / (9.0 * tile_rounds),
-            "kernel_ms_per_launch": fly_ms / max(1.0, micro_rounds / (9.0 * tile_rounds)),
-            "algorithmic_bytes_per_launch": BYTES_PER_STEP * fly_steps / max(1.0, micro_rounds / (9.0 * tile_rounds)),
+            "launches_per_step": super_rounds / args.steps,
+            "kernel_ms_per_launch": fly_ms / max(1, super_rounds),
+            "algorithmic_bytes_per_launch": BYTES_PER_STEP * fly_steps / max(1, super_rounds),
             "share_of_step": {"tile_fly_kernel + scan + scatter (one super-round each)": fly_ms / erode_ms,
                               "track reset + EMA": 1.0 - fly_ms / erode_ms},
-            "super_rounds_per_step": micro_rounds / args.steps / (9.0 * tile_rounds),
+            "micro_rounds_per_step": micro_rounds / args.steps,
             "note": "104 B/step is SURVEY 8(d)'s figure for flight + cascade, which this one kernel does. `traffic` is the DRAM "
                     "traffic of ONE mid-call launch under ncu (the launches of a call differ in size: the injection ramps "
                     "up and down); per particle step it is ~4x BELOW the algorithmic bytes because a tile's heights are "
@@ -747,7 +747,8 @@ def run_ours(args) -> None:
     }
     line["config"]["schedule"] = (
         "lock-step rounds (stripe engines; round 1's schedule: NOT parity-green at this density, DESIGN.md 6)" if lockstep else
-        f"tile-resident: 60x60-cell tiles, one CTA per tile for {tile_rounds} rounds of nine colour micro-rounds per launch, three "
+        f"tile-resident: 120x120-cell tiles, one CTA per tile for {micro_rounds // max(1, 9 * super_rounds)} rounds of nine colour "
+        f"micro-rounds per launch, three "
         f"shifted tilings, interior-only service, in-register cascade, automatic stagger "
         f"({int(8 * particles / (n * n) * rounds_per_call + 0.5)} rounds); parity-green at this density "
         f"(tests/test_gpu_tiles.py)" if world == 1 else

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SWE_ABI_VERSION 2
+#define SWE_ABI_VERSION 3
 
 typedef enum swe_status {
   SWE_OK = 0,
@@ -177,8 +177,9 @@ typedef struct swe_stats {
   double last_round_ms;    /* with SWE_OPT_KERNEL_TIMING: sum over the particle-round kernels */
   double last_cascade_ms;  /* with SWE_OPT_KERNEL_TIMING: sum over the per-round cascade kernels */
   uint64_t stripe_overflow;/* stripe engines: particles dropped for lack of buffer space (must be 0) */
-  uint64_t last_micro_rounds;/* colour-queue scheduler: micro-rounds (kernel launches) the last swe_erode needed */
-  uint64_t queue_dropped;  /* colour-queue scheduler: particles lost to a full queue (must be 0) */
+  uint64_t last_micro_rounds;/* colour-queue / tile scheduler: micro-rounds the last swe_erode needed */
+  uint64_t queue_dropped;  /* colour-queue / tile scheduler: particle records lost to a full queue (must be 0) */
+  uint64_t last_super_rounds;/* tile-resident scheduler: super-rounds (tile_fly_kernel launches) of the last swe_erode; 0 otherwise */
 } swe_stats;
 
 /* Threading contract. An engine is not re-entrant: calls on ONE engine must come from one host thread at a time

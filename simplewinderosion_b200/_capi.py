@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWE_B200_LIB") or os.path.join(_HERE, "libswe_b200.so")   # override: kernel-variant experiments
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class SweError(RuntimeError):
@@ -67,6 +67,7 @@ class Stats(C.Structure):
         ("stripe_overflow", C.c_uint64),
         ("last_micro_rounds", C.c_uint64),
         ("queue_dropped", C.c_uint64),
+        ("last_super_rounds", C.c_uint64),
     ]
 
 

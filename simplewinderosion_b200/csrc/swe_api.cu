@@ -92,6 +92,7 @@ struct swe_engine {
   ColourQueues cq{};                  // queues + claim plane of the colour-queue scheduler
   int sm_count = 148;
   int last_micro_rounds = 0;          // micro-rounds the last colour-queue call needed
+  int last_super_rounds = 0;          // tile scheduler: super-rounds of the last call
   int opt_persistent = 1;             // colour queues: one cooperative launch per call (0 = one launch per micro-round)
   int coop_ok = 0;                    // device supports cooperative launches
   uint64_t claim_tags_used = 0;       // upper bound of the claim tags handed out since the last clearing
@@ -587,6 +588,7 @@ int colour_launch_persistent(swe_engine* e, int cycles) {
   if (err != cudaSuccess) return fail(SWE_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(err));
   e->launches++;
   e->last_micro_rounds = -1;   // read back lazily (swe_get_stats)
+  e->last_super_rounds = 0;
   return SWE_OK;
 }
 
@@ -723,6 +725,7 @@ int erode_tile(swe_engine* e, int cycles) {
     }
   }
   e->last_micro_rounds = s * 9 * K;
+  e->last_super_rounds = s;
   return erode_epilogue(e);
 }
 
@@ -1542,6 +1545,7 @@ int swe_get_stats(swe_engine* e, swe_stats* out) {
     if (pc[3] == 2u) return fail(SWE_ERR_STATE, "colour-queue kernel: micro-round cap reached with particles alive");
   }
   out->last_micro_rounds = (uint64_t)(e->last_micro_rounds < 0 ? 0 : e->last_micro_rounds);
+  out->last_super_rounds = (uint64_t)e->last_super_rounds;
   if (e->cq.count) {
     unsigned dropped = 0;
     SWE_CUDA(cudaMemcpy(&dropped, e->cq.count + 19 * 32, sizeof dropped, cudaMemcpyDeviceToHost));

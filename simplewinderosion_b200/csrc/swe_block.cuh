@@ -76,6 +76,52 @@ SWB_HD void kswap(unsigned long long& a, unsigned long long& b) {
   a = hi; b = lo;
 }
 
+// Sorted order of the eight neighbours (single-layer form): key[i] = the i-th neighbour in the reference's order
+// (height descending, slot ascending among equal heights), packed by sort_key. `filler` stands in for neighbours
+// outside the map: they never move (slot > 7 in the key: infinite gap below), so where they land in the order has
+// no effect on the result and any value will do -- which makes the sort independent of the centre and lets a
+// caller run it before (or interleaved with) the Wind::fly arithmetic that produces the centre's new height.
+SWB_HD void sort_neighbours(const float (&h)[8], unsigned valid, float filler, unsigned long long (&key)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const bool ok = (valid >> k) & 1u;
+    key[k] = sort_key(ok ? h[k] : filler, ok ? k : 8 + k);
+  }
+#define SWB_KS(i, j) kswap(key[i], key[j])
+  SWB_KS(0, 2); SWB_KS(1, 3); SWB_KS(4, 6); SWB_KS(5, 7);
+  SWB_KS(0, 4); SWB_KS(1, 5); SWB_KS(2, 6); SWB_KS(3, 7);
+  SWB_KS(0, 1); SWB_KS(2, 3); SWB_KS(4, 5); SWB_KS(6, 7);
+  SWB_KS(2, 4); SWB_KS(3, 5);
+  SWB_KS(1, 4); SWB_KS(3, 6);
+  SWB_KS(1, 2); SWB_KS(3, 4); SWB_KS(5, 6);
+#undef SWB_KS
+}
+
+// The transfer chain of world.hpp:122-151 on neighbours already in sorted order (v[i] / s[i] / r[i] = height, slot,
+// bedrock of the i-th). Returns the moved mask; c is updated.
+template <bool LAYERED>
+SWB_HD unsigned transfer_chain(float& c, float (&v)[8], const int (&s)[8], const float (&r)[8], const Thr T, float rock_c) {
+  unsigned moved = 0u;
+  float cc = c;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float t = s[i] > 7 ? SWB_INF : (((0xA5u >> s[i]) & 1u) ? T.diag : T.ortho);   // slots {0,2,5,7} are diagonal
+    const float diff = SWB_SUB(cc, v[i]);                          // world.hpp:127
+    const float excess = SWB_SUB(fabsf(diff), t);                  // :133
+    bool go = (diff != 0.0f) && (excess > 0.0f);                   // :128, :135
+    float transfer = SWB_MUL(SWB_MUL(T.settling, excess), 0.5f);   // :139 (x/2 == x*0.5 exactly)
+    if (LAYERED) {                                                 // extension: only sand moves
+      const float sand = (diff > 0.0f) ? SWB_SUB(cc, rock_c) : SWB_SUB(v[i], r[i]);
+      transfer = fminf(transfer, fmaxf(sand, 0.0f));
+      go = go && (transfer > 0.0f);
+    }
+    const float sgn = (diff > 0.0f) ? transfer : -transfer;        // :142-149
+    if (go) { cc = SWB_SUB(cc, sgn); v[i] = SWB_ADD(v[i], sgn); moved |= 1u << i; }
+  }
+  c = cc;
+  return moved;
+}
+
 // In:  c = centre height, h[k] = height of neighbour slot k, valid bit k = neighbour inside the map
 //      (closed boundary, cellpool.h:432-438); layered: rock_c / rk[k] = bedrock heights (extension).
 // Out: c updated; v[i] / s[i] = height and slot of the i-th neighbour in sorted order, moved bit i =
@@ -104,42 +150,11 @@ SWB_HD unsigned cascade_sorted(float& c, const float (&h)[8], unsigned valid, co
 #undef SWB_CS
   } else {
     unsigned long long key[8];
+    sort_neighbours(h, valid, c, key);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const bool ok = (valid >> k) & 1u;
-      key[k] = sort_key(ok ? h[k] : c, ok ? k : 8 + k);
-      r[k] = 0.0f;
-    }
-#define SWB_KS(i, j) kswap(key[i], key[j])
-    SWB_KS(0, 2); SWB_KS(1, 3); SWB_KS(4, 6); SWB_KS(5, 7);
-    SWB_KS(0, 4); SWB_KS(1, 5); SWB_KS(2, 6); SWB_KS(3, 7);
-    SWB_KS(0, 1); SWB_KS(2, 3); SWB_KS(4, 5); SWB_KS(6, 7);
-    SWB_KS(2, 4); SWB_KS(3, 5);
-    SWB_KS(1, 4); SWB_KS(3, 6);
-    SWB_KS(1, 2); SWB_KS(3, 4); SWB_KS(5, 6);
-#undef SWB_KS
-#pragma unroll
-    for (int k = 0; k < 8; k++) { v[k] = key_height(key[k]); s[k] = 15 - (int)(key[k] & 15ull); }
+    for (int k = 0; k < 8; k++) { v[k] = key_height(key[k]); s[k] = 15 - (int)(key[k] & 15ull); r[k] = 0.0f; }
   }
-  unsigned moved = 0u;
-  float cc = c;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const float t = s[i] > 7 ? SWB_INF : (((0xA5u >> s[i]) & 1u) ? T.diag : T.ortho);   // slots {0,2,5,7} are diagonal
-    const float diff = SWB_SUB(cc, v[i]);                          // world.hpp:127
-    const float excess = SWB_SUB(fabsf(diff), t);                  // :133
-    bool go = (diff != 0.0f) && (excess > 0.0f);                   // :128, :135
-    float transfer = SWB_MUL(SWB_MUL(T.settling, excess), 0.5f);   // :139 (x/2 == x*0.5 exactly)
-    if (LAYERED) {                                                 // extension: only sand moves
-      const float sand = (diff > 0.0f) ? SWB_SUB(cc, rock_c) : SWB_SUB(v[i], r[i]);
-      transfer = fminf(transfer, fmaxf(sand, 0.0f));
-      go = go && (transfer > 0.0f);
-    }
-    const float sgn = (diff > 0.0f) ? transfer : -transfer;        // :142-149
-    if (go) { cc = SWB_SUB(cc, sgn); v[i] = SWB_ADD(v[i], sgn); moved |= 1u << i; }
-  }
-  c = cc;
-  return moved;
+  return transfer_chain<LAYERED>(c, v, s, r, T, rock_c);
 }
 
 }  // namespace block

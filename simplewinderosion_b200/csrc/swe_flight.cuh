@@ -79,6 +79,7 @@ __device__ __forceinline__ int cell_colour(int x, int z) { return (x % 3) * 3 + 
 
 // Wind::fly (wind.hpp:28-112) for a particle that owns its cell: heights come in registers, the
 // erosion amount goes out. Returns dh: the centre cell loses dh (wind.hpp:110-111).
+template <bool ALWAYS_RNG = false>   // true: draw the turbulence numbers unconditionally (no branch in the middle of the step)
 __device__ __forceinline__ float fly_owned(const ParConst& C, PState& q, float hc, float hxm, float hxp, float hzm,
                                            float hzp, bool xm, bool xp, bool zm, bool zp, uint4 rng_ctr, uint2 key,
                                            float& collision_out, float& tx, float& ty, float& tz, float& tsed) {
@@ -124,7 +125,7 @@ __device__ __forceinline__ float fly_owned(const ParConst& C, PState& q, float h
   }
   {
     const float amp = 0.1f * hfac * collision;                                    // :83
-    if (amp > 0.0f) {
+    if (ALWAYS_RNG || amp > 0.0f) {
       const uint4 r = philox4x32_10(rng_ctr, key);
       const float s = amp * (1.0f / 500.0f);
       sx += s * ((float)__umulhi(r.x, 1001u) - 500.0f);

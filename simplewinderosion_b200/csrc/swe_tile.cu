@@ -35,6 +35,12 @@
 
 namespace swe {
 
+#ifndef SWE_TILE_ALWAYS_RNG
+#define SWE_TILE_ALWAYS_RNG 1      // draw the turbulence numbers of a step unconditionally: with ~24 lanes per warp some lane needs them
+#endif                             // anyway, and without the branch the step is one basic block for the instruction scheduler
+#ifndef SWE_TILE_STORE_ALL
+#define SWE_TILE_STORE_ALL 1
+#endif
 constexpr unsigned DEAD = 0x0eu;     // pcol value of a particle that died in this super-round
 constexpr unsigned PARKED = 0x0fu;   // pcol value of a particle that is not served (parked, not loaded)
 
@@ -223,12 +229,16 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
           for (int k = 0; k < 8; k++)
             if ((valid >> k) & 1u) rk[k] = rs[li + block::slot_dx(k) * TT + block::slot_dz(k)];
         }
+        // the order of the neighbours does not depend on the centre (swe_block.cuh: sort_neighbours), so the sorting
+        // network is issued here, where it interleaves with the flight arithmetic instead of waiting for its result
+        unsigned long long key8[8];
+        if (!LAYERED) block::sort_neighbours(h, valid, hc, key8);
         PState q;
         q.px = a.x; q.py = a.y; q.pz = a.z; q.sed = a.w;
         q.sx = b.x; q.sy = b.y; q.sz = b.z; q.age = __float_as_int(b.w);
         const size_t ci = (size_t)ix * (size_t)nz + (size_t)iz;
         float collision, tx, ty, tz, tsed;
-        float dh = fly_owned(C, q, hc, h[1], h[6], h[3], h[4], xm, xp, zm, zp,
+        float dh = fly_owned<SWE_TILE_ALWAYS_RNG != 0>(C, q, hc, h[1], h[6], h[3], h[4], xm, xp, zm, zp,
                              make_uint4((uint32_t)ci, call, G.micro0 + tag - 1u, 0xAu), key, collision, tx, ty, tz, tsed);
         red_add_v4(m.track + ci, tsed, tx, ty, tz);                                              // wind.hpp:93-96
         if (LAYERED && dh > 0.0f) {
@@ -243,13 +253,21 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         q.sed += dh;
         float v[8];
         int s[8];
-        const unsigned moved = LAYERED ? block::cascade_sorted<true>(c1, h, valid, T, v, s, rock_c, rk)   // :114
-                                       : block::cascade_sorted<false>(c1, h, valid, T, v, s, rock_c, rk);
+        unsigned moved;                                                                          // :114
+        if (LAYERED) moved = block::cascade_sorted<true>(c1, h, valid, T, v, s, rock_c, rk);
+        else {
+          float r8[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) { v[k] = block::key_height(key8[k]); s[k] = 15 - (int)(key8[k] & 15ull); r8[k] = 0.0f; }
+          moved = block::transfer_chain<false>(c1, v, s, r8, T, rock_c);
+        }
         if (moved != 0u || dh != 0.0f) { hs[li] = c1; dirty = 1; }
-        // slot -> (dx + 1, dz + 1) packed four bits per slot (world.hpp:83-92): two shifts instead of the branches of slot_dx / slot_dz
+        // slot -> (dx + 1, dz + 1) packed four bits per slot (world.hpp:83-92): two shifts instead of the branches of
+        // slot_dx / slot_dz. An inner tile stores all eight neighbours (an unmoved one gets its own value back: the block
+        // is owned) -- eight plain stores instead of eight branches.
 #pragma unroll
         for (int i8 = 0; i8 < 8; i8++)
-          if ((moved >> i8) & 1u) {
+          if ((SWE_TILE_STORE_ALL && inner) || ((moved >> i8) & 1u)) {
             const unsigned code = (0xa9864210u >> (4 * s[i8])) & 15u;
             hs[li + (int)(code >> 2) * TT + (int)(code & 3u) - (TT + 1)] = v[i8];
           }

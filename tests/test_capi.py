@@ -36,7 +36,7 @@ def test_only_swe_symbols_are_exported():
 
 
 def test_abi_version_and_defaults():
-    assert swe.lib.swe_abi_version() == 2
+    assert swe.lib.swe_abi_version() == 3
     p = swe.default_params()
     # wind.hpp:23-26, world.hpp:30-32, cellpool.h:184, wind.hpp:13
     assert p.max_age == 512 and p.boundarylayer == 2.0 and p.mapscale == 80

@@ -222,6 +222,7 @@ def test_call_batches_trade_throughput_for_sequential_fidelity():
     res = {}
     for b in (1, 8):
         w = swe.World(n)
+        w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_LOCKSTEP)      # (batches are an option of the lock-step schedule)
         w.set_option(swe.OPT_CALL_BATCHES, b)
         w.upload(hm)
         w.srand(1)
