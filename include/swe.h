@@ -229,6 +229,14 @@ int swe_download_plane(swe_engine* e, int plane, float* dst, ptrdiff_t stride_by
  * height, the wind map reads the momentum fields): five packed planes height, massflow, momentumx,
  * momentumy, momentumz (5*nx*nz floats) with one pass over the field plane and one synchronisation. */
 int swe_download_frame(swe_engine* e, float* dst5);
+/* The same read-back, pipelined with the next swe_erode: _begin enqueues the copies and returns; the height plane
+ * (dst5[0 .. cells)) travels on the engine's stream, the four flow-field planes are snapshotted on the device and
+ * travel on a side stream while later work on the engine's stream proceeds. _wait(e, 0) blocks until the height
+ * plane has arrived, _wait(e, 1) until all five planes have (and must be called before the next _begin reuses the
+ * snapshot; _begin does so itself if the caller did not). dst5 must stay valid until _wait(e, 1); use pinned host
+ * memory (swe_host_alloc) for a truly asynchronous copy. */
+int swe_download_frame_begin(swe_engine* e, float* dst5);
+int swe_download_frame_wait(swe_engine* e, int all);
 /* Whole reference pool in one go: `cells` points at nx*nz 36-byte quad::cell records. */
 int swe_upload_cells(swe_engine* e, const void* cells);
 int swe_download_cells(swe_engine* e, void* cells);

@@ -114,6 +114,8 @@ PROTOTYPES = {
     "swe_upload_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_download_plane": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_ssize_t]),
     "swe_download_frame": (C.c_int, [_E, C.c_void_p]),
+    "swe_download_frame_begin": (C.c_int, [_E, C.c_void_p]),
+    "swe_download_frame_wait": (C.c_int, [_E, C.c_int]),
     "swe_get_option": (C.c_int, [_E, C.c_int, C.POINTER(C.c_int)]),
     "swe_import_stats": (C.c_int, [_E, C.POINTER(Stats)]),
     "swe_upload_cells": (C.c_int, [_E, C.c_void_p]),

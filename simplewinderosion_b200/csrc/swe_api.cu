@@ -97,6 +97,12 @@ struct swe_engine {
   int coop_ok = 0;                    // device supports cooperative launches
   uint64_t claim_tags_used = 0;       // upper bound of the claim tags handed out since the last clearing
   int persist_blocks_per_sm = 0;
+  // pipelined frame read-back (swe_download_frame_begin / _wait): private snapshot of the four flow fields, side stream
+  float* d_frame = nullptr;
+  size_t frame_bytes = 0;
+  cudaStream_t frame_stream = nullptr;
+  cudaEvent_t ev_frame_src = nullptr, ev_frame_h = nullptr, ev_frame_f = nullptr;
+  bool frame_pending = false;
   TileSched ts{};                     // tile-resident scheduler (swe_tile.cu): records sorted by tile
   int opt_tile_rounds = 0;            // rounds (nine micro-rounds each) a CTA keeps its tile per super-round (0 = auto: edge / 5)
   int opt_tile_shape = -1;            // -1 = by map size (tile_pick), else the index of a compiled tile geometry
@@ -936,6 +942,11 @@ void swe_destroy(swe_engine* e) {
   cudaFree(e->cq.a); cudaFree(e->cq.b); cudaFree(e->cq.count); cudaFree(e->cq.claim);
   cudaFree(e->cq.claim32); cudaFree(e->cq.persist);
   cudaFree(e->ts.count); cudaFree(e->ts.pa[0]);
+  if (e->frame_stream) { cudaStreamSynchronize(e->frame_stream); cudaStreamDestroy(e->frame_stream); }
+  cudaFree(e->d_frame);
+  if (e->ev_frame_src) cudaEventDestroy(e->ev_frame_src);
+  if (e->ev_frame_h) cudaEventDestroy(e->ev_frame_h);
+  if (e->ev_frame_f) cudaEventDestroy(e->ev_frame_f);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : e->st.ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1090,6 +1101,53 @@ int swe_download_frame(swe_engine* e, float* dst5) {
   SWE_CUDA(cudaMemcpyAsync(dst5 + n, e->d_scratch, 4 * bytes, cudaMemcpyDeviceToHost, e->stream));
   SWE_CUDA(cudaStreamSynchronize(e->stream));
   finish_timers(e);
+  return SWE_OK;
+}
+
+// The same read-back, pipelined: the height plane is copied on the engine's stream (the caller needs it before it
+// can hand the map back), the four flow-field planes are snapshotted on the device (one unpack pass) and travel to
+// the host on a side stream WHILE THE NEXT swe_erode RUNS -- the snapshot is private, so nothing the next call does
+// can change what arrives. swe_download_frame_wait(e, 0) returns when the height plane is in dst5[0], (e, 1) when
+// all five planes are. dst5 must stay valid (pinned memory for a truly asynchronous copy) until wait(e, 1).
+int swe_download_frame_begin(swe_engine* e, float* dst5) {
+  if (int rc = bind(e)) return rc;
+  if (!dst5) return fail(SWE_ERR_INVALID, "dst is NULL");
+  const size_t n = e->host_cells(), bytes = n * sizeof(float);
+  const MapView ov = e->owned();
+  if (!e->frame_stream) {
+    SWE_CUDA(cudaStreamCreateWithFlags(&e->frame_stream, cudaStreamNonBlocking));
+    SWE_CUDA(cudaEventCreateWithFlags(&e->ev_frame_src, cudaEventDisableTiming));
+    SWE_CUDA(cudaEventCreateWithFlags(&e->ev_frame_h, cudaEventDisableTiming));
+    SWE_CUDA(cudaEventCreateWithFlags(&e->ev_frame_f, cudaEventDisableTiming));
+  }
+  if (e->frame_pending) SWE_CUDA(cudaEventSynchronize(e->ev_frame_f));   // the previous frame still owns the snapshot
+  if (e->frame_bytes < 4 * bytes) {
+    cudaFree(e->d_frame); e->d_frame = nullptr; e->frame_bytes = 0;
+    SWE_CUDA(cudaMalloc(&e->d_frame, 4 * bytes));
+    e->frame_bytes = 4 * bytes;
+  }
+  launch_unpack_field(ov, false, e->d_frame, e->stream);
+  if (int rc = check_launch(e, "unpack_field")) return rc;
+  SWE_CUDA(cudaEventRecord(e->ev_frame_src, e->stream));
+  SWE_CUDA(cudaMemcpyAsync(dst5, ov.height, bytes, cudaMemcpyDeviceToHost, e->stream));
+  SWE_CUDA(cudaEventRecord(e->ev_frame_h, e->stream));
+  // the flow fields queue up BEHIND the height plane: both copies share the device-to-host engine, and started together
+  // they would interleave and the plane the caller is waiting for would take as long as all five (measured: 6.0 vs 1.3 ms)
+  SWE_CUDA(cudaStreamWaitEvent(e->frame_stream, e->ev_frame_h, 0));
+  SWE_CUDA(cudaMemcpyAsync(dst5 + n, e->d_frame, 4 * bytes, cudaMemcpyDeviceToHost, e->frame_stream));
+  SWE_CUDA(cudaEventRecord(e->ev_frame_f, e->frame_stream));
+  e->frame_pending = true;
+  return SWE_OK;
+}
+
+int swe_download_frame_wait(swe_engine* e, int all) {
+  if (int rc = bind(e)) return rc;
+  if (!e->frame_pending) return fail(SWE_ERR_STATE, "no frame read-back in flight (swe_download_frame_begin)");
+  SWE_CUDA(cudaEventSynchronize(e->ev_frame_h));
+  if (all) {
+    SWE_CUDA(cudaEventSynchronize(e->ev_frame_f));
+    e->frame_pending = false;
+  }
   return SWE_OK;
 }
 

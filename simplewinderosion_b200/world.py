@@ -174,6 +174,17 @@ class World:
         check(lib.swe_download_frame(self._h, out.ctypes.data))
         return out
 
+    def download_frame_begin(self, out: np.ndarray) -> None:
+        """Pipelined form of download_frame: returns at once; the height plane arrives on the engine's stream, the four
+        flow-field planes on a side stream while the next erode runs. `out` (5, nx, nz) should be pinned memory and
+        must stay alive until download_frame_wait(True)."""
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == 5 * self.nx * self.nz
+        check(lib.swe_download_frame_begin(self._h, out.ctypes.data))
+
+    def download_frame_wait(self, all_planes: bool = True) -> None:
+        """Block until the height plane (all_planes=False) or all five planes of the frame in flight have arrived."""
+        check(lib.swe_download_frame_wait(self._h, 1 if all_planes else 0))
+
     # layered-terrain extension (bedrock under the sand; not in the reference snapshot)
     def upload_rock(self, rock: np.ndarray) -> None:
         a = np.ascontiguousarray(rock, dtype=np.float32)

@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import simplewinderosion_b200 as swe
+from simplewinderosion_b200 import generate
 from tests.oracle_lib import PortWorld
 
 pytestmark = pytest.mark.gpu
@@ -303,6 +304,31 @@ def test_strided_aos_roundtrip():
     for opt, val in ((swe.OPT_SCHEDULE, 1), (swe.OPT_STAGGER_ROUNDS, 33), (swe.OPT_PERSISTENT, 0), (swe.OPT_CALL_BATCHES, 5)):
         w2.set_option(opt, val)
         assert w2.get_option(opt) == val
+
+
+def test_pipelined_frame_readback_is_a_snapshot():
+    """swe_download_frame_begin / _wait: the height plane arrives on the engine's stream, the four flow fields are
+    snapshotted on the device and arrive on a side stream -- an erode enqueued in between must not change them."""
+    n = 256
+    w = swe.World(n)
+    w.upload(generate.gaussian_hill(n)); w.srand(3)
+    w.erode(20000, swe.MODE_PARALLEL)
+    ref = w.download_frame()
+    out = np.full((5, n, n), np.nan, dtype=np.float32)
+    w.download_frame_begin(out)
+    w.download_frame_wait(False)
+    assert np.array_equal(out[0], ref[0])
+    w.erode(20000, swe.MODE_PARALLEL)                 # changes height and (at its end) the flow fields
+    w.download_frame_wait(True)
+    assert np.array_equal(out, ref)
+    assert not np.array_equal(w.download_frame()[1], ref[1])
+    with pytest.raises(swe.SweError):
+        w.download_frame_wait(True)                   # nothing in flight
+    out2 = np.empty_like(out)
+    w.download_frame_begin(out); w.download_frame_begin(out2)      # a second begin waits for the first frame itself
+    w.download_frame_wait(True)
+    assert np.array_equal(out, out2)
+    w.close()
 
 
 def test_error_paths():

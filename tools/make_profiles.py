@@ -14,7 +14,8 @@ def launches(path, out):
     tot = sum(sum(v) for v in d.values())
     with open(out, "w") as f:
         f.write(f"# ncu launch list summary ({os.path.basename(path)}): `ncu --metrics gpu__time_duration.sum --clock-control none` "
-                f"over `python bench.py --steps 1 --warmup 3 --skip-cpu --skip-cascade --skip-layered --skip-cfg4` (first {sum(len(v) for v in d.values())} launches; "
+                f"over `python bench.py --steps 1 --warmup 3 --skip-cpu --skip-cascade --skip-layered --skip-cfg4` ({sum(len(v) for v in d.values())} launches"
+                f"{' of the timed call, after --launch-skip 900' if tag == 'r2t' else ' from the start'}; "
                 f"cold-cache, serialised: compare SHARES)\n\n| kernel | launches | total ms | share | mean us |\n|---|---|---|---|---|\n")
         for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"| {k} | {len(v)} | {sum(v)/1e6:.3f} | {100*sum(v)/tot:.1f} % | {sum(v)/len(v)/1e3:.1f} |\n")
@@ -25,10 +26,14 @@ def ncu_summary(rep, out, title):
         f.write(f"# {title}\n# source: ncu --set full --clock-control none --import-source on, one launch\n" + txt)
     return txt
 
+src = os.path.join(G, f"stat_parity_tiles_{tag}.txt")
+if os.path.exists(src):
+    open(os.path.join(P, "r2_stat_parity_tiles.txt"), "w").write(open(src).read())
 if os.path.exists(os.path.join(G, f"launches_{tag}.csv")):
     launches(os.path.join(G, f"launches_{tag}.csv"), os.path.join(P, f"{tag}_launches_summary.md"))
 traffic = {}
-for name, title in (("colour_persistent", "colour_persistent_kernel (Wind::fly + erosion + World::cascade per particle step, all micro-rounds of one World::erode), 4096^2 FBm map, 4,194,304 particles"),
+for name, title in (("tile_fly", "tile_fly_kernel<120,256> (Wind::fly + erosion + World::cascade per particle step; one super-round = 24 rounds x 9 micro-rounds of every 120x120 tile), 4096^2 FBm map, 4,194,304 particles per call, launch 41 of ~97 (mid-call, tiles fully populated)"),
+                    ("colour_persistent", "colour_persistent_kernel (Wind::fly + erosion + World::cascade per particle step, all micro-rounds of one World::erode), 4096^2 FBm map, 4,194,304 particles"),
                     ("par_round", "par_round_kernel, 4096^2 FBm map, 4,194,304 particles, one round (step ~150 of a call)"),
                     ("cascade_stamped", "cascade_tile_kernel<stamped,TMA>, same run: World::cascade at the cells touched in the round"),
                     ("cascade_sweep8192", "cascade_tile_kernel<plain,TMA>, 8192^2 U(0,1) map, one whole-map sweep (sweep 3: dense path, everything moves)"),
