@@ -511,7 +511,12 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    out_stream = sys.stdout
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 when the first communicator is
+        # created, so everything else that lands on fd 1 during the run is sent to stderr
+        out_stream = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
@@ -797,7 +802,7 @@ def run_ours(args) -> None:
             "value": s / t, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": f"one World::erode({args.cpu_cycles}) = {s} particle-steps on the same {n}^2 map, "
                       f"1 thread (the reference is single-threaded), {t:.1f} s"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -37,7 +37,8 @@ PLANE_NAMES = ["height", "massflow", "momentumx", "momentumy", "momentumz",
                "massflow_track", "momentumx_track", "momentumy_track", "momentumz_track"]
 # engine options that change what a parallel run computes (swe_option values)
 _OPTIONS = {"cascade_interval": _world.OPT_CASCADE_INTERVAL, "call_batches": _world.OPT_CALL_BATCHES,
-            "schedule": _world.OPT_SCHEDULE, "stagger_rounds": _world.OPT_STAGGER_ROUNDS}
+            "schedule": _world.OPT_SCHEDULE, "stagger_rounds": _world.OPT_STAGGER_ROUNDS,
+            "tile_rounds": _world.OPT_TILE_ROUNDS, "tile_shape": _world.OPT_TILE_SHAPE}
 _PARAM_FIELDS = ["max_age", "boundarylayer", "suspension", "gravity", "lrate", "maxdiff", "settling",
                  "mapscale", "abrasion"]
 

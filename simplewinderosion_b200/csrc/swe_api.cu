@@ -683,7 +683,8 @@ int need_tiles(swe_engine* e, int cycles) {
 int erode_tile(swe_engine* e, int cycles) {
   if (int rc = need_tiles(e, cycles)) return rc;
   const bool layered = e->m.rock != nullptr;
-  const int shape = e->opt_tile_shape >= 0 ? e->opt_tile_shape : tile_pick(e->m.nx, e->m.nz, e->sm_count);
+  // (a layered engine keeps two planes per tile in shared memory: only ONE 120 x 120 tile would fit an SM)
+  const int shape = e->opt_tile_shape >= 0 ? e->opt_tile_shape : (layered ? 0 : tile_pick(e->m.nx, e->m.nz, e->sm_count));
   const int TE = tile_edge(shape);
   const int K = e->opt_tile_rounds > 0 ? e->opt_tile_rounds : (TE >= 120 ? 24 : 16);   // (A/B on B200; tools/par_emul.c mode D for the parity)
   const int life = e->p.max_age + 2;

@@ -85,8 +85,11 @@ struct TileGeom {
   int pcap;                          // particles of a tile that take part (the rest of its segment stays parked); multiple of 64
 };
 
+// Register budget: three resident 256-thread CTAs per SM (shared memory allows three 120 x 120 tiles) = at most 85
+// registers. Measured on B200: left to itself with a 255-register budget ptxas takes 87, only two CTAs fit, and the
+// headline call goes from 166 to 201 ms.
 template <int TT, int TNT, bool LAYERED>
-__global__ void __launch_bounds__(TNT)
+__global__ void __launch_bounds__(TNT, TNT >= 256 ? 3 : 6)
 tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, uint2 key, uint32_t call, DevStats* stats) {
   constexpr int TLAT = TT / 3;
   static_assert(TT % 3 == 0 && TNT % 32 == 0, "tile edge: multiple of 3");
