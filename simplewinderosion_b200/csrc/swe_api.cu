@@ -132,6 +132,12 @@ struct swe_engine {
     unsigned seq = 0;
     std::vector<void*> ipc_opened;       // peer mappings to close at destroy
     bool ring = false;                   // swe_stripe_connect_ring: colour-queue scheduler available
+    bool tiles = false;                  // ... and the tile-resident scheduler (queue buffers big enough for its tables)
+    TileStripeHost th{};                 // tile scheduler on stripes: neighbours' planes / records / tables (peer pointers)
+    TileSched ts{};                      // this rank's records and tables, carved out of the (exported) queue buffers
+    unsigned long long tile_seq = 0;     // cross-GPU barriers passed so far (same on every rank)
+    int below_rows = 0, above_rows = 0;  // stored rows of the neighbours (their track plane follows their height plane)
+    bool merged_planes = false;          // height and track share one allocation (so that one IPC handle maps both)
     int rank = 0, nranks = 1, colocated = 1;
     void* mailboxes[SWE_MAX_STRIPE_RANKS] = {};
     int persist_blocks_per_sm = 0;
@@ -328,8 +334,11 @@ StripeRound stripe_round_ctx(swe_engine* e) {
   return sr;
 }
 
+bool stripe_uses_tiles(const swe_engine* e) {   // (a layered stripe keeps the colour queues: the bedrock of a neighbour's rows is not mapped)
+  return e->st.enabled && e->st.ring && e->st.tiles && e->opt_schedule == 2 && !e->m.rock;
+}
 bool stripe_uses_colour_queues(const swe_engine* e) {
-  return e->st.enabled && e->st.ring && e->opt_schedule != 1 && e->coop_ok && e->st.persist_blocks_per_sm > 0;
+  return e->st.enabled && e->st.ring && e->opt_schedule != 1 && e->coop_ok && e->st.persist_blocks_per_sm > 0 && !stripe_uses_tiles(e);
 }
 
 int stripe_erode_begin(swe_engine* e, int cycles) {
@@ -680,15 +689,27 @@ int need_tiles(swe_engine* e, int cycles) {
 // Whole particle phase on the tile-resident schedule: particle i becomes active at round i * S / n (S = the
 // stagger of the colour-queue scheduler), at the granularity of a super-round; super-rounds are enqueued until
 // the device reports that no record is left (checked every few super-rounds once the injection is over).
-int erode_tile(swe_engine* e, int cycles) {
-  if (int rc = need_tiles(e, cycles)) return rc;
+struct TilePlan {
+  int shape, K, pcap, inj_srs, first_check, max_srs;
+  long long S, n;
+  int started_before(long long round) const {             // particles with start round floor(i S / n) < round
+    if (S <= 0) return round > 0 ? (int)n : 0;
+    const long long v = (round * n + S - 1) / S;
+    return (int)(v > n ? n : v);
+  }
+};
+
+// Geometry, rounds per super-round, on-chip list capacity and the number of super-rounds to enqueue before the first
+// completion check. Depends only on the (global) map, the parameters and the options: every rank of a stripe group
+// computes the same plan.
+int tile_plan(swe_engine* e, int cycles, TilePlan* P) {
   const bool layered = e->m.rock != nullptr;
   // (a layered engine keeps two planes per tile in shared memory: only ONE 120 x 120 tile would fit an SM)
   const int shape = e->opt_tile_shape >= 0 ? e->opt_tile_shape : (layered ? 0 : tile_pick(e->m.nx, e->m.nz, e->sm_count));
   const int TE = tile_edge(shape);
   const int K = e->opt_tile_rounds > 0 ? e->opt_tile_rounds : (TE >= 120 ? 24 : 16);   // (A/B on B200; tools/par_emul.c mode D for the parity)
   const int life = e->p.max_age + 2;
-  long long S = colour_stagger_micro(e, cycles) / 9;      // rounds
+  const long long S = colour_stagger_micro(e, cycles) / 9;      // rounds
   // expected particles per tile while the injection runs (Poisson): mean + 5 sigma + slack stays on chip; a tile
   // with more than that parks the excess for a super-round (never lost)
   const double density = (double)cycles / ((double)e->m.nx * (double)e->m.nz);
@@ -704,36 +725,122 @@ int erode_tile(swe_engine* e, int cycles) {
     if (err != cudaSuccess) return fail(SWE_ERR_CUDA, "tile kernel configuration failed: %s", cudaGetErrorString(err));
     e->tile_pcap[shape][layered] = pcap;
   }
+  P->shape = shape; P->K = K; P->pcap = pcap; P->S = S; P->n = cycles;
+  P->inj_srs = S > 0 ? (int)((S + K - 1) / K) : 1;         // super-rounds that receive new particles
+  P->first_check = P->inj_srs + (life * 6 / 10 + K - 1) / K;
+  P->max_srs = P->inj_srs + 64 * ((life + K - 1) / K) + 64;
+  return SWE_OK;
+}
+
+int erode_tile(swe_engine* e, int cycles) {
+  if (int rc = need_tiles(e, cycles)) return rc;
+  TilePlan P;
+  if (int rc = tile_plan(e, cycles, &P)) return rc;
+  const int K = P.K;
   if (int rc = erode_prologue(e)) return rc;
-  const long long n = cycles;
-  auto started_before = [&](long long round) -> int {     // particles with start round floor(i S / n) < round
-    if (S <= 0) return round > 0 ? (int)n : 0;
-    const long long v = (round * n + S - 1) / S;
-    return (int)(v > n ? n : v);
-  };
-  const int inj_srs = S > 0 ? (int)((S + K - 1) / K) : 1;  // super-rounds that receive new particles
-  int nl = launch_tile_super_round(e->m, e->p, e->ts, shape, -1, K, pcap, 0, started_before(K), e->seed, e->call_index,
+  int nl = launch_tile_super_round(e->m, e->p, e->ts, P.shape, -1, K, P.pcap, 0, P.started_before(K), e->seed, e->call_index,
                                    e->d_stats, e->stream);
-  int first_check = inj_srs + (life * 6 / 10 + K - 1) / K;
-  const int max_srs = inj_srs + 64 * ((life + K - 1) / K) + 64;
   int s = 0;
   for (;; s++) {
-    if (s >= max_srs) return fail(SWE_ERR_STATE, "tile scheduler: particles still alive after %d super-rounds", s);
-    const int lo = started_before((long long)(s + 1) * K), hi = started_before((long long)(s + 2) * K);
-    nl += launch_tile_super_round(e->m, e->p, e->ts, shape, s, K, pcap, lo, hi, e->seed, e->call_index, e->d_stats, e->stream);
-    if (s + 1 >= first_check && (s + 1 - first_check) % 4 == 0) {
+    if (s >= P.max_srs) return fail(SWE_ERR_STATE, "tile scheduler: particles still alive after %d super-rounds", s);
+    const int lo = P.started_before((long long)(s + 1) * K), hi = P.started_before((long long)(s + 2) * K);
+    nl += launch_tile_super_round(e->m, e->p, e->ts, P.shape, s, K, P.pcap, lo, hi, e->seed, e->call_index, e->d_stats, e->stream);
+    if (s + 1 >= P.first_check && (s + 1 - P.first_check) % 4 == 0) {
       if (int rc = check_launch(e, "tile super-round", nl)) return rc;
       nl = 0;
       unsigned info[2];
       SWE_CUDA(cudaMemcpyAsync(info, e->ts.info, sizeof info, cudaMemcpyDeviceToHost, e->stream));
       SWE_CUDA(cudaStreamSynchronize(e->stream));
       if (info[1] != 0u) return fail(SWE_ERR_STATE, "tile scheduler dropped %u particle records", info[1]);
-      if (info[0] == 0u && s + 1 >= inj_srs) { s++; break; }
+      if (info[0] == 0u && s + 1 >= P.inj_srs) { s++; break; }
     }
   }
   e->last_micro_rounds = s * 9 * K;
   e->last_super_rounds = s;
   return erode_epilogue(e);
+}
+
+// The same schedule on the stripes of ONE map (n engines driven by this host thread: 1 with one process per GPU,
+// several for logical stripes). Every rank launches the tiles it owns (csrc/swe_tile.cu: TileStripe); a cross-GPU
+// barrier kernel follows each phase of a super-round; the completion check reads the GLOBAL number of records,
+// which the barrier after the scan sums over all ranks, so every rank takes the same decision.
+int erode_tile_stripes(swe_engine** engines, int n, int cycles) {
+  TilePlan P{};
+  for (int i = 0; i < n; i++) {
+    swe_engine* e = engines[i];
+    if (int rc = bind(e)) return rc;
+    TilePlan Q;
+    if (int rc = tile_plan(e, cycles, &Q)) return rc;
+    if (i == 0) P = Q;
+    else if (Q.shape != P.shape || Q.K != P.K || Q.S != P.S) return fail(SWE_ERR_STATE, "stripes disagree on the tile plan");
+    if (e->cq.cap < 1 || e->st.ts.cap < 1) return fail(SWE_ERR_STATE, "stripe engine has no tile tables");
+    if (e->st.own_hi - e->st.own_lo < 2 * tile_edge(Q.shape) || e->m.nx / e->st.nranks - 8 < 2 * tile_edge(Q.shape))
+      return fail(SWE_ERR_STATE, "tile schedule on stripes: every stripe must be at least two tiles (%d rows) tall; "
+                                 "use SWE_OPT_TILE_SHAPE = 0 or SWE_OPT_SCHEDULE = 0", 2 * tile_edge(Q.shape));
+    if (int rc = erode_prologue(e)) return rc;
+    const size_t words = (size_t)e->st.ts.max_tiles + 1;
+    SWE_CUDA(cudaMemsetAsync(e->st.ts.count, 0, (4 * words + 16) * sizeof(unsigned), e->stream));
+  }
+  const int K = P.K;
+  int nl = 0;
+  auto round = [&](int s, int lo, int hi, bool want_sum) -> int {
+    for (int phase = 0; phase < 3; phase++)
+      for (int i = 0; i < n; i++) {
+        swe_engine* e = engines[i];
+        if (int rc = bind(e)) return rc;
+        nl += launch_tile_phase(phase, e->m, e->p, e->st.ts, P.shape, s, K, P.pcap, lo, hi, e->seed, e->call_index, e->d_stats,
+                                e->stream, &e->st.th);
+        void* boxes[SWE_MAX_STRIPE_RANKS] = {};
+        for (int r = 0; r < e->st.nranks; r++) boxes[r] = static_cast<char*>(e->st.mailboxes[r]) + SWE_TILE_MAILBOX_OFFSET;
+        launch_tile_xbar(boxes, e->st.rank, e->st.nranks, ++e->st.tile_seq, e->st.ts.info, want_sum && phase == 1, e->stream);
+        nl++;
+      }
+    return SWE_OK;
+  };
+  if (int rc = round(-1, 0, P.started_before(K), false)) return rc;
+  int s = 0;
+  for (;; s++) {
+    if (s >= P.max_srs) return fail(SWE_ERR_STATE, "tile scheduler: particles still alive after %d super-rounds", s);
+    const int lo = P.started_before((long long)(s + 1) * K), hi = P.started_before((long long)(s + 2) * K);
+    const bool check = s + 1 >= P.first_check && (s + 1 - P.first_check) % 4 == 0;
+    if (int rc = round(s, lo, hi, check)) return rc;
+    if (check) {
+      unsigned info[SWE_MAX_STRIPE_RANKS * 4][4];
+      for (int i = 0; i < n; i++) {
+        if (int rc = bind(engines[i])) return rc;
+        if (int rc = check_launch(engines[i], "tile super-round (stripes)", i == 0 ? nl : 0)) return rc;
+        SWE_CUDA(cudaMemcpyAsync(info[i], engines[i]->st.ts.info, sizeof info[i], cudaMemcpyDeviceToHost, engines[i]->stream));
+      }
+      nl = 0;
+      for (int i = 0; i < n; i++) {
+        if (int rc = bind(engines[i])) return rc;
+        SWE_CUDA(cudaStreamSynchronize(engines[i]->stream));
+      }
+      for (int i = 0; i < n; i++) {
+        if (info[i][3] != 0u) return fail(SWE_ERR_STATE, "tile scheduler: cross-GPU barrier watchdog fired on stripe %d", engines[i]->st.rank);
+        if (info[i][1] != 0u) return fail(SWE_ERR_STATE, "tile scheduler dropped %u particle records on stripe %d", info[i][1], engines[i]->st.rank);
+      }
+      if (info[0][2] == 0u && s + 1 >= P.inj_srs) { s++; break; }
+    }
+  }
+  for (int i = 0; i < n; i++) {
+    engines[i]->last_micro_rounds = s * 9 * K;
+    engines[i]->last_super_rounds = s;
+  }
+  // the tiles worked on the owners' memory; bring every rank's ghost rows up to date for what follows
+  if (n > 1) {
+    if (int rc = swe_stripe_group_sync_halos(engines, n)) return rc;
+  } else {
+    int nh = 0;
+    const unsigned q = stripe_exchange_begin(engines[0], false, &nh);
+    stripe_exchange_end(engines[0], q, &nh);
+    if (int rc = check_launch(engines[0], "stripe halo refresh", nh)) return rc;
+  }
+  for (int i = 0; i < n; i++) {
+    if (int rc = bind(engines[i])) return rc;
+    if (int rc = erode_epilogue(engines[i])) return rc;
+  }
+  return SWE_OK;
 }
 
 int erode_prologue(swe_engine* e) {   // (the timers of an earlier call are read at the next synchronising entry point)
@@ -843,9 +950,18 @@ static int create_engine(swe_engine** out, int nx, int nz, int own_lo, int own_h
   TRY(cudaEventCreate(&e->ev_a)); TRY(cudaEventCreate(&e->ev_b));
   TRY(cudaEventCreate(&e->ev_c)); TRY(cudaEventCreate(&e->ev_d));
   TRY(cudaEventCreate(&e->ev_f0)); TRY(cudaEventCreate(&e->ev_f1));
-  TRY(cudaMalloc(&e->m.height, n * sizeof(float)));
+  if (stripe) {
+    // one allocation for height + track: the neighbours map it through ONE IPC handle and reach the track vectors of
+    // the rows next to the stripe boundary (tile scheduler: a tile that straddles the boundary adds them in place)
+    const size_t hbytes = (n * sizeof(float) + 255) / 256 * 256;
+    TRY(cudaMalloc(&e->m.height, hbytes + n * sizeof(float4)));
+    e->m.track = reinterpret_cast<float4*>(reinterpret_cast<char*>(e->m.height) + hbytes);
+    e->st.merged_planes = true;
+  } else {
+    TRY(cudaMalloc(&e->m.height, n * sizeof(float)));
+    TRY(cudaMalloc(&e->m.track, n * sizeof(float4)));
+  }
   TRY(cudaMalloc(&e->m.field, n * sizeof(float4)));
-  TRY(cudaMalloc(&e->m.track, n * sizeof(float4)));
   TRY(cudaMalloc(&e->d_stats, sizeof(DevStats)));
   TRY(cudaMalloc(&e->d_rng, sizeof(DetRand)));
   TRY(cudaMalloc(&e->d_small, 64 * sizeof(float)));
@@ -935,7 +1051,8 @@ void swe_destroy(swe_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->m.height); cudaFree(e->m.field); cudaFree(e->m.track);
+  cudaFree(e->m.height); cudaFree(e->m.field);
+  if (!e->st.merged_planes) cudaFree(e->m.track);
   cudaFree(e->d_stats); cudaFree(e->d_rng); cudaFree(e->d_small); cudaFree(e->d_scratch);
   cudaFree(e->pbuf.a); cudaFree(e->pbuf.b); cudaFree(e->pbuf.live); cudaFree(e->d_stamp);
   cudaFree(e->st.arena); cudaFree(e->st.d_pid); cudaFree(e->st.d_vars);
@@ -1254,6 +1371,10 @@ int swe_erode(swe_engine* e, int cycles, int mode) {
     return fail(SWE_ERR_STATE, "deterministic mode reproduces the reference, which has no rock layer");
   if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_schedule == 2 && !e->m.periodic)
     return erode_tile(e, cycles);
+  if (e->st.enabled && cycles > 0 && stripe_uses_tiles(e)) {   // one process per GPU: this rank's share of the stripe group
+    swe_engine* one[1] = {e};
+    return erode_tile_stripes(one, 1, cycles);
+  }
   if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_schedule != 1)
     return erode_colour(e, cycles);   // (also the tile schedule on a torus: tiles do not wrap)
   if (!e->st.enabled && mode == SWE_MODE_PARALLEL && cycles > 0 && e->opt_cuda_graph && !e->opt_kernel_timing)
@@ -1300,6 +1421,10 @@ int swe_stripe_group_erode(swe_engine** engines, int n, int cycles) {
     if (int rc = stripe_erode_check(engines[i], cycles, SWE_MODE_PARALLEL)) return rc;
     if (engines[i]->p.max_age != engines[0]->p.max_age) return fail(SWE_ERR_INVALID, "stripes disagree on max_age");
   }
+  const bool tiles = stripe_uses_tiles(engines[0]);
+  for (int i = 0; i < n; i++)
+    if (stripe_uses_tiles(engines[i]) != tiles) return fail(SWE_ERR_STATE, "stripes disagree on the schedule");
+  if (tiles && cycles > 0) return erode_tile_stripes(engines, n, cycles);
   const bool colour = stripe_uses_colour_queues(engines[0]);
   for (int i = 0; i < n; i++)
     if (stripe_uses_colour_queues(engines[i]) != colour) return fail(SWE_ERR_STATE, "stripes disagree on the schedule");
@@ -1670,6 +1795,7 @@ int swe_stripe_export(swe_engine* e, swe_stripe_link* out) {
   out->x0 = e->m.x0; out->inbox_capacity = e->st.inbox_capacity;
   out->queue_a = e->cq.a; out->queue_b = e->cq.b; out->queue_count = e->cq.count; out->persist = e->cq.persist;
   out->queue_cap = e->cq.cap;
+  out->reserved = e->m.rows;          // stored rows: the track plane follows the height plane in the same allocation
   return SWE_OK;
 }
 
@@ -1687,9 +1813,9 @@ int swe_stripe_export_ipc(swe_engine* e, void* buf, size_t buf_bytes) {
   SWE_CUDA(cudaIpcGetMemHandle(&h[4], e->cq.b));
   SWE_CUDA(cudaIpcGetMemHandle(&h[5], e->cq.count));
   SWE_CUDA(cudaIpcGetMemHandle(&h[6], e->cq.persist));
-  static_assert(7 * sizeof(cudaIpcMemHandle_t) + 3 * sizeof(int) <= SWE_STRIPE_IPC_BYTES, "ipc blob size");
+  static_assert(7 * sizeof(cudaIpcMemHandle_t) + 4 * sizeof(int) <= SWE_STRIPE_IPC_BYTES, "ipc blob size");
   std::memcpy(b, h, sizeof h);
-  const int meta[3] = {e->m.x0, e->st.inbox_capacity, e->cq.cap};
+  const int meta[4] = {e->m.x0, e->st.inbox_capacity, e->cq.cap, e->m.rows};
   std::memcpy(b + sizeof h, meta, sizeof meta);
   return SWE_OK;
 }
@@ -1700,7 +1826,7 @@ int swe_stripe_open_ipc(swe_engine* e, const void* buf, size_t buf_bytes, swe_st
   const unsigned char* b = static_cast<const unsigned char*>(buf);
   cudaIpcMemHandle_t h[7];
   std::memcpy(h, b, sizeof h);
-  int meta[3];
+  int meta[4];
   std::memcpy(meta, b + sizeof h, sizeof meta);
   void* ptr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < 7; i++) {
@@ -1710,7 +1836,7 @@ int swe_stripe_open_ipc(swe_engine* e, const void* buf, size_t buf_bytes, swe_st
   std::memset(out, 0, sizeof *out);
   out->height = ptr[0]; out->stamp = ptr[1]; out->arena = ptr[2];
   out->queue_a = ptr[3]; out->queue_b = ptr[4]; out->queue_count = ptr[5]; out->persist = ptr[6];
-  out->x0 = meta[0]; out->inbox_capacity = meta[1]; out->queue_cap = meta[2];
+  out->x0 = meta[0]; out->inbox_capacity = meta[1]; out->queue_cap = meta[2]; out->reserved = meta[3];
   return SWE_OK;
 }
 
@@ -1752,6 +1878,53 @@ int swe_stripe_connect_ring(swe_engine* e, int rank, int n, const swe_stripe_lin
   S.persist_blocks_per_sm = colour_persistent_blocks_per_sm_stripe();
   (void)cudaGetLastError();
   S.ring = true;
+  // tile-resident scheduler on stripes: records and per-tile tables live inside the queue buffers (they are what
+  // the neighbours have mapped); available when every rank's buffers are big enough and its stripe is at least two
+  // tiles tall -- decided from numbers every rank knows, so that all ranks decide alike
+  {
+    const int shape = tile_pick(e->m.nx, e->m.nz, e->sm_count);
+    const int words = tile_max_tiles(e->m.nx, e->m.nz) + 1;
+    auto layout = [&](void* qa, void* qb, int qcap, TileSched* out) -> bool {
+      if (!qa || !qb || qcap < 1024) return false;
+      if ((4ull * words + 16ull) * sizeof(unsigned) > 16ull * (unsigned long long)qcap * sizeof(float4)) return false;
+      float4* a = static_cast<float4*>(qa);
+      float4* b = static_cast<float4*>(qb);
+      out->pa[0] = a; out->pa[1] = a + qcap; out->pb[0] = b; out->pb[1] = b + qcap;
+      unsigned* tab = reinterpret_cast<unsigned*>(a + 2 * (size_t)qcap);
+      out->count = tab; out->base[0] = tab + words; out->base[1] = tab + 2 * (size_t)words;
+      out->cursor = tab + 3 * (size_t)words; out->info = tab + 4 * (size_t)words;
+      out->cap = qcap; out->max_tiles = words - 1;
+      return true;
+    };
+    bool ok = (e->m.nx / n - 8) >= 2 * tile_edge(shape) && (S.own_hi - S.own_lo) >= 2 * tile_edge(shape) && S.merged_planes;
+    ok = ok && layout(e->cq.a, e->cq.b, e->cq.cap, &S.ts);
+    TileStripeHost H{};
+    H.enabled = 1; H.own_lo = S.own_lo; H.own_hi = S.own_hi;
+    H.has_below = rank > 0; H.has_above = rank + 1 < n;
+    if (ok && H.has_below) {
+      const swe_stripe_link& l = links[rank - 1];
+      ok = l.reserved > 0 && layout(l.queue_a, l.queue_b, l.queue_cap, &H.below);
+      H.below_h = static_cast<float*>(l.height); H.below_x0 = l.x0;
+      H.below_lo = l.x0 == 0 ? 0 : l.x0 + GHOST_LO;
+      const size_t hbytes = ((size_t)l.reserved * (size_t)e->m.nz * sizeof(float) + 255) / 256 * 256;
+      H.below_t = reinterpret_cast<float4*>(static_cast<char*>(l.height) + hbytes);
+    }
+    if (ok && H.has_above) {
+      const swe_stripe_link& l = links[rank + 1];
+      ok = l.reserved > 0 && layout(l.queue_a, l.queue_b, l.queue_cap, &H.above);
+      H.above_h = static_cast<float*>(l.height); H.above_x0 = l.x0;
+      const size_t hbytes = ((size_t)l.reserved * (size_t)e->m.nz * sizeof(float) + 255) / 256 * 256;
+      H.above_t = reinterpret_cast<float4*>(static_cast<char*>(l.height) + hbytes);
+    }
+    S.tiles = ok;
+    S.th = H;
+    S.tile_seq = 0;
+    if (ok) {
+      SWE_CUDA(cudaMemsetAsync(S.ts.count, 0, (4 * (size_t)words + 16) * sizeof(unsigned), e->stream));
+      SWE_CUDA(cudaMemsetAsync(static_cast<char*>(e->cq.persist) + SWE_TILE_MAILBOX_OFFSET, 0, 1024, e->stream));
+      SWE_CUDA(cudaStreamSynchronize(e->stream));
+    }
+  }
   return SWE_OK;
 }
 

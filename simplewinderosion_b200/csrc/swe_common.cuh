@@ -219,6 +219,7 @@ struct StripeQueues {
 constexpr int SWE_MAX_STRIPE_RANKS = 8;
 constexpr size_t SWE_PERSIST_BYTES = 4096;        // PersistCtl at 0, barrier mailbox at 1024
 constexpr size_t SWE_MAILBOX_OFFSET = 1024;
+constexpr size_t SWE_TILE_MAILBOX_OFFSET = 3072;  // tile scheduler on stripes: its own barrier mailbox ring (16 slots x 8 ranks x 8 bytes)
 constexpr size_t SWE_GROUP_OFFSET = 2048;         // copies 1..15 of the grid barrier's release word, 128 B apart
 int colour_persistent_blocks_per_sm(bool layered);
 int colour_persistent_blocks_per_sm_stripe();
@@ -241,6 +242,20 @@ struct TileSched {
   int cap;                  // records per array
   int max_tiles;
 };
+// Stripe context of the tile scheduler (host side): this rank's rows and the neighbours' planes, record arrays and
+// tile tables as device pointers valid on this GPU (peer mappings).
+struct TileStripeHost {
+  int enabled;
+  int own_lo, own_hi, below_lo;        // below_lo = first row the rank below owns
+  int has_below, has_above;
+  float* below_h; float4* below_t; int below_x0;
+  float* above_h; float4* above_t; int above_x0;
+  TileSched below, above;
+};
+int launch_tile_phase(int phase, const MapView& m, const swe_params& p, const TileSched& S, int shape, int s, int K, int pcap,
+                      int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st,
+                      const TileStripeHost* H);
+void launch_tile_xbar(void* const* mailboxes, int rank, int nranks, unsigned long long seq, unsigned* info, bool want_sum, cudaStream_t st);
 int tile_shapes();                   // tile geometries compiled in (0 = 60 x 60 cells / 128 threads, 1 = 120 x 120 / 256)
 int tile_edge(int shape);
 int tile_threads(int shape);

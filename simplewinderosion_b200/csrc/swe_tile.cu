@@ -85,12 +85,68 @@ struct TileGeom {
   int pcap;                          // particles of a tile that take part (the rest of its segment stays parked); multiple of 64
 };
 
+// ---- multi-GPU row stripes --------------------------------------------------------------------------------
+// The tiling is GLOBAL (the same tiles as on one GPU); a tile belongs to the rank that owns the row of its centre, so
+// tiles partition the map exactly as before and a super-round still needs no communication. A tile that straddles a
+// stripe boundary reads and writes the neighbour's rows (heights, track vectors) directly in the neighbour's memory
+// (peer mappings over NVLink: once per super-round for the heights); survivors whose next tile belongs to a neighbour
+// are counted and scattered into the NEIGHBOUR's segment tables and record arrays (system-scope atomics, peer
+// stores). Ranks meet three times per super-round (after fly + count, after the scan, after the scatter:
+// tile_xbar_kernel) instead of once per micro-round.
+struct TileStripe {
+  int enabled;
+  int own_lo, own_hi;                 // global rows this rank owns
+  int a_lo_cur;                       // first tile row of the CURRENT tiling this rank owns
+  int a_lo_next, a_hi_next;           // tile rows of the NEXT tiling this rank owns: [a_lo_next, a_hi_next)
+  int a_lo_next_below;                // first tile row of the next tiling owned by the rank below (its last is a_lo_next - 1)
+  int has_below, has_above;
+  float* below_h; float4* below_t; int below_x0;      // neighbour's height / track plane and the global row of its first stored row
+  float* above_h; float4* above_t; int above_x0;
+  unsigned* below_count; unsigned* above_count;       // neighbour's per-tile counts (next tiling)
+  const unsigned* below_base; const unsigned* above_base;   // neighbour's segment bases of the next tiling
+  unsigned* below_cursor; unsigned* above_cursor;
+  float4* below_pa; float4* below_pb; float4* above_pa; float4* above_pb;   // neighbour's record arrays of the next tiling
+  unsigned* below_info; unsigned* above_info;
+  int below_cap, above_cap;
+};
+
+__device__ __forceinline__ float ld_sys_f32(const float* a) {
+  float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void st_sys_f32(float* a, float v) {
+  asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_sys_u32(const unsigned* a) {
+  unsigned v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void red_add_v4_sys(float4* addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// owner of tile row a of the next tiling: -1 = the rank below, 0 = this rank, +1 = the rank above
+__device__ __forceinline__ int next_owner(const TileStripe& X, int a) {
+  return a < X.a_lo_next ? -1 : (a >= X.a_hi_next ? 1 : 0);
+}
+// one atomic per warp and (owner, tile): the count lives on the owner
+__device__ __forceinline__ void count_dest_stripe(const TileSched& S, const TileStripe& X, int a, int b, int ntz, bool active) {
+  const int own = active ? next_owner(X, a) : 0;
+  const int idx = active ? (a - (own < 0 ? X.a_lo_next_below : (own > 0 ? X.a_hi_next : X.a_lo_next))) * ntz + b : 0;
+  const unsigned has = __ballot_sync(0xffffffffu, active);
+  if (active) {
+    const unsigned grp = __match_any_sync(has, (own + 1) * 0x10000000 + idx);
+    if ((int)(threadIdx.x & 31u) == __ffs(grp) - 1) {
+      if (own == 0) atomicAdd(S.count + idx, (unsigned)__popc(grp));
+      else atomicAdd_system((own < 0 ? X.below_count : X.above_count) + idx, (unsigned)__popc(grp));
+    }
+  }
+}
+
 // Register budget: three resident 256-thread CTAs per SM (shared memory allows three 120 x 120 tiles) = at most 85
 // registers. Measured on B200: left to itself with a 255-register budget ptxas takes 87, only two CTAs fit, and the
 // headline call goes from 166 to 201 ms.
-template <int TT, int TNT, bool LAYERED>
+template <int TT, int TNT, bool LAYERED, bool STRIPE>
 __global__ void __launch_bounds__(TNT, TNT >= 256 ? 3 : 6)
-tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, uint2 key, uint32_t call, DevStats* stats) {
+tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, uint2 key, uint32_t call, DevStats* stats,
+                const TileStripe X) {
   constexpr int TLAT = TT / 3;
   static_assert(TT % 3 == 0 && TNT % 32 == 0, "tile edge: multiple of 3");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -113,7 +169,13 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         spawn_position_iid(id, nx, nz, key, call, px, pz);
         const int ix = __float2int_rd(px + 0.5f), iz = __float2int_rd(pz + 0.5f);
         active = !m.oob(ix, iz);                                     // (dies in its first fly() call: never stored)
-        if (active) dest = tile_of(ix, iz, G.off_next, G.ntz_next, TT);
+        if (active) {
+          if (STRIPE) {                                              // every rank walks the whole list and keeps its own tiles' particles
+            const int a = (ix + G.off_next) / TT;
+            active = a >= X.a_lo_next && a < X.a_hi_next;
+            dest = (a - X.a_lo_next) * G.ntz_next + (iz + G.off_next) / TT;
+          } else dest = tile_of(ix, iz, G.off_next, G.ntz_next, TT);
+        }
       }
       count_dest(S.count, dest, active);
     }
@@ -127,7 +189,7 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
   const int np = min(n, G.pcap);
   float4* ga = (G.cur ? S.pa[1] : S.pa[0]) + seg;      // this tile's records: nobody else touches them in this launch
   float4* gb = (G.cur ? S.pb[1] : S.pb[0]) + seg;
-  const int x0 = ((int)blockIdx.x / G.ntz_cur) * TT - G.off_cur, z0 = ((int)blockIdx.x % G.ntz_cur) * TT - G.off_cur;
+  const int x0 = ((STRIPE ? X.a_lo_cur : 0) + (int)blockIdx.x / G.ntz_cur) * TT - G.off_cur, z0 = ((int)blockIdx.x % G.ntz_cur) * TT - G.off_cur;
   // a tile that does not touch the map's edge: every neighbour of a served cell exists
   const bool inner = x0 > 0 && z0 > 0 && x0 + TT < nx && z0 + TT < nz;
 
@@ -148,8 +210,13 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
   for (int i = tid; i < TT * TT; i += TNT) {
     const int gx = x0 + i / TT, gz = z0 + i % TT;
     const bool in = gx >= 0 && gx < nx && gz >= 0 && gz < nz;
-    hs[i] = in ? __ldcg(m.height + (size_t)gx * (size_t)nz + gz) : 0.0f;
-    if (LAYERED) rs[i] = in ? __ldcg(m.rock + (size_t)gx * (size_t)nz + gz) : 0.0f;
+    if (STRIPE && in && (gx < X.own_lo || gx >= X.own_hi)) {        // a neighbour's row: read it where it lives
+      hs[i] = gx < X.own_lo ? ld_sys_f32(X.below_h + (size_t)(gx - X.below_x0) * (size_t)nz + gz)
+                            : ld_sys_f32(X.above_h + (size_t)(gx - X.above_x0) * (size_t)nz + gz);
+      continue;
+    }
+    hs[i] = in ? __ldcg(m.height + (size_t)(gx - m.x0) * (size_t)nz + gz) : 0.0f;
+    if (LAYERED) rs[i] = in ? __ldcg(m.rock + (size_t)(gx - m.x0) * (size_t)nz + gz) : 0.0f;
   }
   for (int i = tid; i < TLAT * TLAT; i += TNT) claim[i] = 0u;
   const int npad = (np + 15) & ~15;
@@ -239,11 +306,14 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         PState q;
         q.px = a.x; q.py = a.y; q.pz = a.z; q.sed = a.w;
         q.sx = b.x; q.sy = b.y; q.sz = b.z; q.age = __float_as_int(b.w);
-        const size_t ci = (size_t)ix * (size_t)nz + (size_t)iz;
+        const size_t ci = (size_t)ix * (size_t)nz + (size_t)iz;      // global cell number (RNG counter)
         float collision, tx, ty, tz, tsed;
         float dh = fly_owned<SWE_TILE_ALWAYS_RNG != 0>(C, q, hc, h[1], h[6], h[3], h[4], xm, xp, zm, zp,
                              make_uint4((uint32_t)ci, call, G.micro0 + tag - 1u, 0xAu), key, collision, tx, ty, tz, tsed);
-        red_add_v4(m.track + ci, tsed, tx, ty, tz);                                              // wind.hpp:93-96
+        if (STRIPE && (ix < X.own_lo || ix >= X.own_hi))                                         // wind.hpp:93-96
+          red_add_v4_sys((ix < X.own_lo ? X.below_t + (size_t)(ix - X.below_x0) * (size_t)nz : X.above_t + (size_t)(ix - X.above_x0) * (size_t)nz) + iz,
+                         tsed, tx, ty, tz);
+        else red_add_v4(m.track + (size_t)(ix - m.x0) * (size_t)nz + (size_t)iz, tsed, tx, ty, tz);
         if (LAYERED && dh > 0.0f) {
           // layered extension: only the sand above the bedrock is picked up; the unmet demand grinds the rock
           // at `abrasion` efficiency (rock -> suspended sediment). The cell is owned: plain updates.
@@ -293,27 +363,32 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
   if (__syncthreads_or(dirty)) {
     for (int i = tid; i < TT * TT; i += TNT) {
       const int gx = x0 + i / TT, gz = z0 + i % TT;
-      if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) m.height[(size_t)gx * (size_t)nz + gz] = hs[i];
+      if (!(gx >= 0 && gx < nx && gz >= 0 && gz < nz)) continue;
+      if (STRIPE && (gx < X.own_lo || gx >= X.own_hi))
+        st_sys_f32((gx < X.own_lo ? X.below_h + (size_t)(gx - X.below_x0) * (size_t)nz : X.above_h + (size_t)(gx - X.above_x0) * (size_t)nz) + gz, hs[i]);
+      else m.height[(size_t)(gx - m.x0) * (size_t)nz + gz] = hs[i];
     }
   }
   if (LAYERED && __syncthreads_or(dirty_rock)) {
     for (int i = tid; i < TT * TT; i += TNT) {
       const int gx = x0 + i / TT, gz = z0 + i % TT;
-      if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) m.rock[(size_t)gx * (size_t)nz + gz] = rs[i];
+      if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) m.rock[(size_t)(gx - m.x0) * (size_t)nz + gz] = rs[i];
     }
   }
   for (int p0 = 0; p0 < n; p0 += TNT) {
     const int p = p0 + tid;
     bool alive = false;
-    int dest = 0;
+    int dest = 0, da = 0, db = 0;
     if (p < n) {
       alive = p >= np || pcol[p] != DEAD;              // (beyond pcap: parked for this super-round)
       if (alive) {
         const float4 a = __ldcg(ga + p);
-        dest = tile_of(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), G.off_next, G.ntz_next, TT);
+        da = (__float2int_rd(a.x + 0.5f) + G.off_next) / TT; db = (__float2int_rd(a.z + 0.5f) + G.off_next) / TT;
+        dest = da * G.ntz_next + db;
       }
     }
-    count_dest(S.count, dest, alive);
+    if (STRIPE) count_dest_stripe(S, X, da, db, G.ntz_next, alive);
+    else count_dest(S.count, dest, alive);
   }
 
   for (int o = 16; o > 0; o >>= 1) {
@@ -368,7 +443,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(TileSched S, int nt, in
 // Moves every surviving record of the current segments, and the particles injected for the next super-round,
 // into the segment of the tile (next tiling) its cell belongs to.
 __global__ void __launch_bounds__(256) tile_scatter_kernel(MapView m, TileSched S, TileGeom G, uint2 key, uint32_t call,
-                                                           DevStats* stats) {
+                                                           DevStats* stats, const TileStripe X) {
   const unsigned total = (G.cur ? S.base[1] : S.base[0])[G.ntx_cur * G.ntz_cur];
   const unsigned ninj = (unsigned)(G.inj_hi - G.inj_lo);
   const unsigned all = total + ninj;
@@ -393,19 +468,41 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(MapView m, TileSched 
       b = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
       n_new++;
       active = !m.oob(__float2int_rd(px + 0.5f), __float2int_rd(pz + 0.5f));
-      if (!active) n_oob++;                                          // dies in its first fly() call
+      if (!active) {                                                 // dies in its first fly() call (stripes: counted by the rank whose rows are nearest)
+        const int sx = __float2int_rd(px + 0.5f);
+        if (!X.enabled || (sx < X.own_hi && (sx >= X.own_lo || !X.has_below)) || (sx >= X.own_hi && !X.has_above)) n_oob++;
+        else n_new--;
+      }
     }
-    int dest = 0;
-    if (active) dest = tile_of(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), G.off_next, G.ntz_next, G.edge);
+    int dest = 0, own = 0;
+    if (active) {
+      const int ta = (__float2int_rd(a.x + 0.5f) + G.off_next) / G.edge, tb = (__float2int_rd(a.z + 0.5f) + G.off_next) / G.edge;
+      if (X.enabled) {
+        own = next_owner(X, ta);
+        if (j >= total) {                              // a new particle: every rank walks the whole list and keeps its own
+          if (own != 0) { active = false; n_new--; }
+        }
+        dest = (ta - (own < 0 ? X.a_lo_next_below : (own > 0 ? X.a_hi_next : X.a_lo_next))) * G.ntz_next + tb;
+        if (active && ((own < 0 && !X.has_below) || (own > 0 && !X.has_above) || dest < 0)) {   // cannot happen: stripes are taller than a tile
+          active = false; atomicAdd(S.info + 1, 1u);
+        }
+      } else dest = ta * G.ntz_next + tb;
+    }
     const unsigned has = __ballot_sync(0xffffffffu, active);
     if (active) {
-      const unsigned grp = __match_any_sync(has, dest);
+      const unsigned grp = __match_any_sync(has, (own + 1) * 0x10000000 + dest);
       const int leader = __ffs(grp) - 1;
       unsigned wb = 0u;
-      if ((int)lane == leader) wb = atomicAdd(S.cursor + dest, (unsigned)__popc(grp));
+      if ((int)lane == leader)
+        wb = own == 0 ? atomicAdd(S.cursor + dest, (unsigned)__popc(grp))
+                      : atomicAdd_system((own < 0 ? X.below_cursor : X.above_cursor) + dest, (unsigned)__popc(grp));
       wb = __shfl_sync(grp, wb, leader);
-      const unsigned slot = base[dest] + wb + (unsigned)__popc(grp & ((1u << lane) - 1u));
-      if (slot < (unsigned)S.cap) { da[slot] = a; db[slot] = b; }
+      const unsigned b0 = own == 0 ? base[dest] : ld_sys_u32((own < 0 ? X.below_base : X.above_base) + dest);
+      const unsigned slot = b0 + wb + (unsigned)__popc(grp & ((1u << lane) - 1u));
+      float4* oa = own == 0 ? da : (own < 0 ? X.below_pa : X.above_pa);
+      float4* ob = own == 0 ? db : (own < 0 ? X.below_pb : X.above_pb);
+      const unsigned ocap = own == 0 ? (unsigned)S.cap : (unsigned)(own < 0 ? X.below_cap : X.above_cap);
+      if (slot < ocap) { oa[slot] = a; ob[slot] = b; }
       else atomicAdd(S.info + 1, 1u);                                // cannot happen: cap >= particles per call
     }
   }
@@ -417,6 +514,46 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(MapView m, TileSched 
     if (n_new) atomicAdd(&stats->particles, (unsigned long long)n_new);
     if (n_oob) atomicAdd(&stats->exits_oob, (unsigned long long)n_oob);
   }
+}
+
+// Cross-GPU barrier between the phases of a super-round (one warp, thread 0 works). Every rank publishes
+// (sequence number, records it holds for the next super-round) into EVERY rank's mailbox ring (16 slots x 8 ranks of
+// 8-byte words, one 64-byte line per slot) and waits for its two NEIGHBOURS only -- the ranks whose memory it reads
+// and writes. want_sum: also wait for all ranks' words of this sequence number (every rank runs the same sequence,
+// so they all arrive) and leave the global number of records in info[2] for the host's completion check.
+struct TileMail { unsigned long long* box[8]; int rank, nranks; };
+__global__ void tile_xbar_kernel(TileMail M, unsigned long long seq, unsigned* info, int want_sum) {
+  if (threadIdx.x != 0) return;
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  const unsigned long long word = (seq << 32) | (unsigned long long)info[0];
+  const int slot = (int)(seq & 15ull);
+  for (int i = 0; i < M.nranks; i++)
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(M.box[i] + slot * 8 + M.rank), "l"(word) : "memory");
+  const unsigned long long* mine = M.box[M.rank];
+  const long long t0 = clock64();
+  unsigned long long total = 0ull;
+  for (int i = 0; i < M.nranks; i++) {
+    const bool neighbour = i == M.rank - 1 || i == M.rank + 1;
+    if (!neighbour && !want_sum) continue;
+    unsigned long long w;
+    unsigned spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(mine + slot * 8 + i) : "memory");
+      if ((w >> 32) == (seq & 0xffffffffull)) break;
+      __nanosleep(100);
+      if ((++spins & 1023u) == 0u && clock64() - t0 > 16000000000LL) { info[3] = 1u; return; }   // ~8 s: never hang the device
+    }
+    total += w & 0xffffffffull;
+  }
+  if (want_sum) info[2] = (unsigned)(total > 0xffffffffull ? 0xffffffffull : total);
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+
+void launch_tile_xbar(void* const* mailboxes, int rank, int nranks, unsigned long long seq, unsigned* info, bool want_sum, cudaStream_t st) {
+  TileMail M{};
+  for (int i = 0; i < nranks && i < 8; i++) M.box[i] = static_cast<unsigned long long*>(mailboxes[i]);
+  M.rank = rank; M.nranks = nranks;
+  tile_xbar_kernel<<<1, 32, 0, st>>>(M, seq, info, want_sum ? 1 : 0);
 }
 
 static size_t tile_smem_bytes(int shape, bool layered, int pcap) {
@@ -462,23 +599,30 @@ int tile_pick(int nx, int nz, int sm_count) {
   return tiles >= 3LL * sm_count ? 1 : 0;
 }
 
-template <int TT, int TNT>
-static void launch_fly(bool layered, int grid, size_t smem, cudaStream_t st, const MapView& m, const ParConst& C, const block::Thr& T,
-                       const TileSched& S, const TileGeom& G, uint2 key, uint32_t call, DevStats* stats) {
-  if (layered) tile_fly_kernel<TT, TNT, true><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats);
-  else tile_fly_kernel<TT, TNT, false><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats);
+// stripes: first tile row (tiling offset off) whose centre row lies at or beyond global row x
+static int first_tile_row(int x, int tt, int off, int nx) {
+  const int ntx = (nx + off + tt - 1) / tt;
+  if (x <= 0) return 0;
+  if (x >= nx) return ntx;
+  const int num = x + off - tt / 2;
+  int a = num <= 0 ? 0 : (num + tt - 1) / tt;
+  return a > ntx ? ntx : a;
 }
 
-// Super-round s of a call (s = -1: only the injection of super-round 0's particles). Returns the launches made.
-int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSched& S, int shape, int s, int K, int pcap,
-                            int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st) {
-  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  block::Thr T;
-  T.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;   // host IEEE fp32: the values exact::cascade_thresholds computes
-  T.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
-  T.settling = p.settling;
-  const int tt = kShapes[shape].edge, nt = kShapes[shape].threads;
-  TileGeom G;
+template <int TT, int TNT>
+static void launch_fly(bool layered, bool stripe, int grid, size_t smem, cudaStream_t st, const MapView& m, const ParConst& C,
+                       const block::Thr& T, const TileSched& S, const TileGeom& G, uint2 key, uint32_t call, DevStats* stats,
+                       const TileStripe& X) {
+  if (stripe) tile_fly_kernel<TT, TNT, false, true><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
+  else if (layered) tile_fly_kernel<TT, TNT, true, false><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
+  else tile_fly_kernel<TT, TNT, false, false><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
+}
+
+// Geometry of super-round s (s = -1: only the injection of super-round 0's particles) for a single-GPU engine or one
+// rank of a stripe group.
+static void tile_round_setup(const MapView& m, int shape, int s, int K, int pcap, int inj_lo, int inj_hi,
+                             const TileSched& S, const TileStripeHost* H, TileGeom& G, TileStripe& X) {
+  const int tt = kShapes[shape].edge;
   if (s >= 0) G = tile_geom(m, tt, s);
   else {                                      // no tiles yet: cur = 1 holds an empty segment table (base[1][0] = 0)
     G = tile_geom(m, tt, 2);                  // (s + 1) % 3 == 0  -> next tiling is tiling 0
@@ -487,37 +631,94 @@ int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSch
   G.inj_lo = inj_lo; G.inj_hi = inj_hi;
   G.micro0 = s >= 0 ? (unsigned)s * 9u * (unsigned)K : 0u;
   G.K = K; G.pcap = pcap;
-  const int ntiles = G.ntx_cur * G.ntz_cur;
-  const int inj_blocks = (inj_hi - inj_lo + nt * 8 - 1) / (nt * 8);
-  const bool layered = m.rock != nullptr;
-  const size_t smem = tile_smem_bytes(shape, layered, pcap);
-  int launches = 0;
-  if (ntiles + inj_blocks > 0) {
-    if (shape == 1) launch_fly<120, 256>(layered, ntiles + inj_blocks, smem, st, m, make_const(p), T, S, G, key, call, stats);
-    else launch_fly<60, 128>(layered, ntiles + inj_blocks, smem, st, m, make_const(p), T, S, G, key, call, stats);
-    launches++;
+  X = TileStripe{};
+  if (!H || !H->enabled) return;
+  const int nxt = G.cur ^ 1;
+  X.enabled = 1; X.own_lo = H->own_lo; X.own_hi = H->own_hi;
+  X.has_below = H->has_below; X.has_above = H->has_above;
+  const int a_lo_cur = first_tile_row(H->own_lo, tt, G.off_cur, m.nx), a_hi_cur = first_tile_row(H->own_hi, tt, G.off_cur, m.nx);
+  X.a_lo_cur = a_lo_cur;
+  if (s >= 0) G.ntx_cur = a_hi_cur - a_lo_cur;                       // tile rows this rank launches
+  X.a_lo_next = first_tile_row(H->own_lo, tt, G.off_next, m.nx);
+  X.a_hi_next = first_tile_row(H->own_hi, tt, G.off_next, m.nx);
+  X.a_lo_next_below = H->has_below ? first_tile_row(H->below_lo, tt, G.off_next, m.nx) : 0;
+  G.ntx_next = X.a_hi_next - X.a_lo_next;                            // tile rows of the next tiling this rank owns (scan length)
+  X.below_h = H->below_h; X.below_t = H->below_t; X.below_x0 = H->below_x0;
+  X.above_h = H->above_h; X.above_t = H->above_t; X.above_x0 = H->above_x0;
+  X.below_count = H->below.count; X.above_count = H->above.count;
+  X.below_base = H->below.base[nxt]; X.above_base = H->above.base[nxt];
+  X.below_cursor = H->below.cursor; X.above_cursor = H->above.cursor;
+  X.below_pa = H->below.pa[nxt]; X.below_pb = H->below.pb[nxt];
+  X.above_pa = H->above.pa[nxt]; X.above_pb = H->above.pb[nxt];
+  X.below_info = H->below.info; X.above_info = H->above.info;
+  X.below_cap = H->below.cap; X.above_cap = H->above.cap;
+}
+
+// The three phases of a super-round. phase 0: fly + count (skipped when there is nothing to launch), 1: scan, 2: scatter.
+// Stripe groups put a cross-GPU barrier (launch_tile_xbar) after each of them. Returns the launches made.
+int launch_tile_phase(int phase, const MapView& m, const swe_params& p, const TileSched& S, int shape, int s, int K, int pcap,
+                      int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st,
+                      const TileStripeHost* H) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  TileGeom G;
+  TileStripe X;
+  tile_round_setup(m, shape, s, K, pcap, inj_lo, inj_hi, S, H, G, X);
+  const int nt = kShapes[shape].threads;
+  if (phase == 0) {
+    block::Thr T;
+    T.ortho = sqrtf(1.0f) * p.maxdiff * 1.0f;   // host IEEE fp32: the values exact::cascade_thresholds computes
+    T.diag = sqrtf(2.0f) * p.maxdiff * 1.0f;
+    T.settling = p.settling;
+    const int ntiles = G.ntx_cur * G.ntz_cur;
+    const int inj_blocks = (inj_hi - inj_lo + nt * 8 - 1) / (nt * 8);
+    const bool layered = m.rock != nullptr;
+    const size_t smem = tile_smem_bytes(shape, layered, pcap);
+    if (ntiles + inj_blocks <= 0) return 0;
+    if (shape == 1) launch_fly<120, 256>(layered, X.enabled != 0, ntiles + inj_blocks, smem, st, m, make_const(p), T, S, G, key, call, stats, X);
+    else launch_fly<60, 128>(layered, X.enabled != 0, ntiles + inj_blocks, smem, st, m, make_const(p), T, S, G, key, call, stats, X);
+    return 1;
   }
-  tile_scan_kernel<<<1, 1024, 0, st>>>(S, G.ntx_next * G.ntz_next, G.cur ^ 1);
+  if (phase == 1) {
+    tile_scan_kernel<<<1, 1024, 0, st>>>(S, G.ntx_next * G.ntz_next, G.cur ^ 1);
+    return 1;
+  }
   long long blocks = ((long long)S.cap + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  tile_scatter_kernel<<<(int)blocks, 256, 0, st>>>(m, S, G, key, call, stats);
-  return launches + 2;
+  tile_scatter_kernel<<<(int)blocks, 256, 0, st>>>(m, S, G, key, call, stats, X);
+  return 1;
+}
+
+int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSched& S, int shape, int s, int K, int pcap,
+                            int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st) {
+  int n = 0;
+  for (int phase = 0; phase < 3; phase++)
+    n += launch_tile_phase(phase, m, p, S, shape, s, K, pcap, inj_lo, inj_hi, seed, call, stats, st, nullptr);
+  return n;
 }
 
 cudaError_t tile_configure(int shape, bool layered, int pcap) {
   const int smem = (int)tile_smem_bytes(shape, layered, pcap);
   const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
-  if (shape == 1)
-    return layered ? cudaFuncSetAttribute(tile_fly_kernel<120, 256, true>, at, smem) : cudaFuncSetAttribute(tile_fly_kernel<120, 256, false>, at, smem);
-  return layered ? cudaFuncSetAttribute(tile_fly_kernel<60, 128, true>, at, smem) : cudaFuncSetAttribute(tile_fly_kernel<60, 128, false>, at, smem);
+  cudaError_t err;
+  if (shape == 1) {
+    err = layered ? cudaFuncSetAttribute(tile_fly_kernel<120, 256, true, false>, at, smem) : cudaFuncSetAttribute(tile_fly_kernel<120, 256, false, false>, at, smem);
+    if (err == cudaSuccess && !layered) err = cudaFuncSetAttribute(tile_fly_kernel<120, 256, false, true>, at, smem);
+  } else {
+    err = layered ? cudaFuncSetAttribute(tile_fly_kernel<60, 128, true, false>, at, smem) : cudaFuncSetAttribute(tile_fly_kernel<60, 128, false, false>, at, smem);
+    if (err == cudaSuccess && !layered) err = cudaFuncSetAttribute(tile_fly_kernel<60, 128, false, true>, at, smem);
+  }
+  return err;
 }
 
 void preload_tile() {
   cudaFuncAttributes a;
-  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, false>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, true>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, false>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, true>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, false, false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, true, false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, false, true>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, false, false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, true, false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, false, true>);
+  cudaFuncGetAttributes(&a, tile_xbar_kernel);
   cudaFuncGetAttributes(&a, tile_scan_kernel);
   cudaFuncGetAttributes(&a, tile_scatter_kernel);
 }

@@ -55,14 +55,29 @@ def main():
     w.srand(5)
     w.erode(cycles, swe.MODE_PARALLEL)
     st = w.stats()
-    t = torch.tensor([st.particles, st.exits_oob + st.exits_age, st.steps, st.stripe_overflow], dtype=torch.float64, device="cuda")
+    # stripes of 512 / world rows are at least two 60-row tiles tall: the call ran the tile-resident schedule (global
+    # tiling, boundary tiles working in the neighbour's memory, three cross-GPU barriers per super-round)
+    assert st.last_super_rounds > 0, "the tile-resident schedule did not run on the stripes"
+    single = swe.World(n, device=local)
+    single.upload(hm2); single.srand(5)
+    single.erode(cycles, swe.MODE_PARALLEL)
+    mine, ref = w.download() - hm2[lo:hi], single.download()[lo:hi] - hm2[lo:hi]
+    corr = float(np.corrcoef(mine.ravel(), ref.ravel())[0, 1])
+    assert corr > 0.9, f"rank {rank}: erosion field of the stripe vs a single engine: {corr}"
+    fx, fr = w.download(swe.MOMENTUMX), single.download(swe.MOMENTUMX)[lo:hi]
+    assert abs(float(fx.mean()) / float(fr.mean()) - 1.0) < 0.1, "flow field of the stripe vs a single engine"
+    steps_single = single.stats().steps
+    single.close()
+    t = torch.tensor([st.particles, st.exits_oob + st.exits_age, st.steps, st.stripe_overflow + st.queue_dropped], dtype=torch.float64, device="cuda")
     m = torch.tensor([w.sum_plane(), st.sediment_lost], dtype=torch.float64, device="cuda")
     dist.all_reduce(t); dist.all_reduce(m)
     s0 = float(hm2.astype(np.float64).sum())
     if rank == 0:
         assert int(t[0]) == cycles and int(t[1]) == cycles and int(t[3]) == 0, t.tolist()
         assert abs(float(m[0] + m[1]) - s0) < 2e-6 * s0 + 1e-4, (m.tolist(), s0)
-        print(f"MGPU_OK world={world} steps={int(t[2])} mass_drift={float(m[0] + m[1]) - s0:.3e}")
+        assert abs(int(t[2]) / steps_single - 1.0) < 0.02, (int(t[2]), steps_single)
+        print(f"MGPU_OK world={world} steps={int(t[2])} (single engine {steps_single}) super_rounds={st.last_super_rounds} "
+              f"mass_drift={float(m[0] + m[1]) - s0:.3e} field_corr_rank0={corr:.4f}")
     dist.barrier()
     w.close()
     dist.destroy_process_group()

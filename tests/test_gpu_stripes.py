@@ -101,6 +101,62 @@ def test_striped_erode_accounts_for_every_particle(n, world, cycles, ring):
     assert abs(float(f.mean()) / float(single.download(swe.MOMENTUMX).mean()) - 1.0) < 0.05
 
 
+@pytest.mark.parametrize("nx,nz,world,shape", [(512, 512, 2, -1), (768, 320, 3, -1), (1024, 256, 4, 0), (1024, 384, 4, 1), (512, 200, 2, 1)])
+def test_striped_erode_tile_schedule(nx, nz, world, shape):
+    """The tile-resident schedule on stripes (stripes at least two tiles tall): global tiling, a tile belongs to the rank
+    that owns its centre row and reads / writes a neighbour's rows in the neighbour's memory, survivors are scattered
+    into the owner's segment tables, three cross-stripe barriers per super-round. Against a single engine on the same
+    schedule: every particle accounted for, mass balance, same statistics."""
+    from tests.oracle_lib import noise_map
+    cycles = nx * nz // 4
+    hm = (noise_map(max(nx, nz), seed=1, layers=8, workers=4)[:nx, :nz]).astype(np.float32).copy()
+    g = make_stripes(nx, nz, world, cycles, hm)
+    ws = g.worlds
+    single, other = swe.World(nx, nz), swe.World(nx, nz)
+    for w, seed in [(w, 7) for w in ws] + [(single, 7), (other, 8)]:
+        w.set_option(swe.OPT_SCHEDULE, swe.SCHEDULE_TILES)
+        w.set_option(swe.OPT_TILE_SHAPE, shape)
+        w.srand(seed)
+    single.upload(hm); other.upload(hm)
+    if shape == 1 and nx // world < 248:
+        with pytest.raises(swe.SweError):        # stripes of 256 rows are fine for 120-row tiles, shorter ones are refused loudly
+            g.erode(cycles)
+        return
+    s0 = float(hm.astype(np.float64).sum())
+    for _ in range(2):
+        g.erode(cycles)
+        single.erode(cycles, swe.MODE_PARALLEL)
+        other.erode(cycles, swe.MODE_PARALLEL)
+    sts = [w.stats() for w in ws]
+    ss = single.stats()
+    assert all(s.last_super_rounds == sts[0].last_super_rounds > 0 for s in sts)          # the tile path ran, in lock step
+    assert sum(s.particles for s in sts) == 2 * cycles == sum(s.exits_oob + s.exits_age for s in sts)
+    assert sum(s.stripe_overflow + s.queue_dropped for s in sts) == 0
+    assert abs(sum(s.steps for s in sts) / ss.steps - 1.0) < 0.01
+    lost = sum(s.sediment_lost for s in sts)
+    total = sum(w.sum_plane() for w in ws)
+    assert abs(total + lost - s0) < 2e-6 * abs(s0)
+    assert abs(lost / ss.sediment_lost - 1.0) < 0.03
+    got, ref = g.gather(), single.download()
+    assert np.isfinite(got).all()
+    baseline = np.corrcoef((other.download() - hm).ravel(), (ref - hm).ravel())[0, 1]
+    assert np.corrcoef((got - hm).ravel(), (ref - hm).ravel())[0, 1] > baseline - 0.02, baseline
+    # the rows either side of every stripe boundary look like the single engine's (no seam in the erosion field)
+    for w in ws[:-1]:
+        hi = w.bounds[w.rank][1]
+        seam = slice(hi - 3, hi + 3)
+        assert np.corrcoef((got[seam] - hm[seam]).ravel(), (ref[seam] - hm[seam]).ravel())[0, 1] > baseline - 0.1
+    # flow fields: the track vectors of a neighbour's rows were added in the neighbour's memory
+    f, fs = g.gather(swe.MOMENTUMX), single.download(swe.MOMENTUMX)
+    assert abs(float(f.mean()) / float(fs.mean()) - 1.0) < 0.03
+    for w in ws[:-1]:
+        hi = w.bounds[w.rank][1]
+        assert abs(float(f[hi - 2:hi + 2].mean()) / float(fs[hi - 2:hi + 2].mean()) - 1.0) < 0.15
+    # whole-map sweeps still work on the refreshed ghost rows
+    g.cascade_sweep(1)
+    assert np.isfinite(g.gather()).all()
+
+
 def test_stripe_engine_guards():
     ws = make_stripes(64, 64, 2, 256, generate.flat_sand(64)).worlds
     w = ws[0]
