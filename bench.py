@@ -414,8 +414,7 @@ def cfg4_strong(swe, rank: int, world: int, device: int, barrier, max_over_ranks
             else:
                 one_cq = r
     out = {"workload": f"cfg4: {n}x{n} FBm dune field, {particles} particles per World::erode (0.0625 per cell), "
-                       f"{'tile-resident schedule' if world == 1 else 'colour-queue schedule on row stripes'}, {steps} timed calls "
-                       f"after 1 warm-up",
+                       f"tile-resident schedule{'' if world == 1 else ' on row stripes'}, {steps} timed calls after 1 warm-up",
            "unit": UNIT, "n_gpus": world}
     if world == 1:
         out.update(one)
@@ -441,12 +440,12 @@ def cfg4_strong(swe, rank: int, world: int, device: int, barrier, max_over_ranks
     total = sum_over_ranks(float(st.steps - s0))
     dropped = sum_over_ranks(float(st.queue_dropped + st.stripe_overflow))
     w.close()
-    out.update({"value": total / (ms * 1e-3), "ms_per_step": ms / steps, "dropped_particles": int(dropped)})
+    out.update({"value": total / (ms * 1e-3), "ms_per_step": ms / steps, "dropped_particles": int(dropped),
+                "schedule": "tile-resident" if st.last_super_rounds > 0 else "colour queues"})
     if rank == 0:
-        out["one_gpu_same_run"] = one                         # best single-GPU path (tile-resident schedule)
-        out["one_gpu_same_schedule"] = one_cq                 # the stripes' own schedule on one GPU
+        out["one_gpu_same_run"] = one                         # the same call on one GPU (tile-resident schedule)
+        out["one_gpu_colour_queues"] = one_cq                 # ... and on the colour-queue schedule, for reference
         out["speedup_vs_1gpu"] = out["value"] / one["value"]
-        out["speedup_vs_1gpu_same_schedule"] = out["value"] / one_cq["value"]
     return out
 
 
@@ -708,15 +707,26 @@ def run_ours(args) -> None:
             "parallelism": "single GPU" if world == 1 else
             f"{world} row stripes of a {n if args.strong else n * world}x{n} map ({rows_local} rows and "
             f"~{particles_call // world} particles per GPU), "
-            f"one persistent colour-queue kernel per GPU; grid barrier across the GPUs every micro-round (mailbox words in peer "
-            f"memory over NVLink); 3x3 blocks on a stripe boundary are read and written in the neighbour's memory; particles "
-            f"crossing a boundary are appended to the neighbour's queue (system-scope atomics)",
+            + ("tile-resident schedule on a GLOBAL tiling: every GPU launches the tiles whose centre row it owns; a tile that "
+               "straddles a stripe boundary loads / stores the neighbour's rows in the neighbour's memory over NVLink once per "
+               "super-round and adds their track vectors there (system-scope reductions); surviving particles whose next tile "
+               "belongs to a neighbour are counted and scattered into the neighbour's segment tables (peer atomics and stores); "
+               "three barrier kernels per super-round (mailbox words in peer memory), no NCCL on the data path"
+               if super_rounds > 0 else
+               "one persistent colour-queue kernel per GPU; grid barrier across the GPUs every micro-round (mailbox words in peer "
+               "memory over NVLink); 3x3 blocks on a stripe boundary are read and written in the neighbour's memory; particles "
+               "crossing a boundary are appended to the neighbour's queue (system-scope atomics)"),
             "stripe_overflow": int(overflow_total),
-            **({} if world == 1 else {"exchange": {
+            **({} if world == 1 else {"exchange": ({
+                "barriers_per_step": 3 * (super_rounds / max(1, args.steps) + 1),
+                "what": "per super-round and stripe boundary: the rows of the straddling tiles beyond the boundary (<= 2/3 of a "
+                        "tile edge x nz floats, read once and written back once), 32 B per particle whose next tile belongs to "
+                        "the neighbour, three 8-byte barrier words to every rank; one halo refresh (12 rows) per call",
+                "super_rounds_per_step": super_rounds / max(1, args.steps)} if super_rounds > 0 else {
                 "per_micro_round_per_rank_bytes": int(8 * world),
                 "what": "one 8-byte barrier word to every rank per micro-round; 32 B per particle handed to a neighbour's queue; "
                         "4 B loads/stores of the neighbour's boundary rows by the particles standing next to them; "
-                        "one halo refresh (12 rows) per call", "micro_rounds_per_step": micro_rounds / max(1, args.steps)}}),
+                        "one halo refresh (12 rows) per call", "micro_rounds_per_step": micro_rounds / max(1, args.steps)})}),
             "l2": "working set > 600 MiB per GPU (height 64 + track 256 + field 256 MiB + live particle records + claim lattice) "
                   "> 126 MB L2; no flush needed",
             "steps_per_particle": total_steps / max(1.0, total_particles),
@@ -745,7 +755,7 @@ def run_ours(args) -> None:
                     "up and down); per particle step it is ~4x BELOW the algorithmic bytes because a tile's heights are "
                     "read and written once per super-round, not per step. The kernel is bound by instruction issue and "
                     "the dependent chain of a step, not by HBM (DESIGN.md 4)"}
-            if world == 1 else {
+            if super_rounds > 0 else {
             "bound": "hbm", "kernel": "colour_persistent_kernel (Wind::fly + erosion + World::cascade per particle step)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic("colour_persistent"), "peak_source": peak_src,
@@ -769,7 +779,8 @@ def run_ours(args) -> None:
         f"micro-rounds per launch, three "
         f"shifted tilings, interior-only service, in-register cascade, automatic stagger "
         f"({int(8 * particles / (n * n) * rounds_per_call + 0.5)} rounds); parity-green at this density "
-        f"(tests/test_gpu_tiles.py)" if world == 1 else
+        f"(tests/test_gpu_tiles.py)" + ("" if world == 1 else "; on stripes: global tiling, a tile belongs to the rank that owns its "
+        "centre row, three cross-GPU barriers per super-round (tests/test_gpu_stripes.py)") if super_rounds > 0 else
         f"colour queues: 9-colour micro-rounds, one particle per cell, in-register cascade, automatic stagger "
         f"({int(8 * particles / (n * n) * rounds_per_call + 0.5)} rounds); parity-green at this density "
         f"(tests/test_gpu_density.py)")
