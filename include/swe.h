@@ -98,7 +98,9 @@ typedef enum swe_option {
    * 2 (default) = tile-resident scheduler (single-GPU engines, closed boundary): the map is cut into tiles, one
    * CTA keeps a tile's heights in shared memory for a super-round of K rounds of nine colour micro-rounds and
    * serves the particles standing in the tile's interior; three shifted tilings take turns (csrc/swe_tile.cu).
-   * Stripe engines and periodic maps run schedule 0 when 2 is selected.
+   * On stripe engines wired with swe_stripe_connect_ring the tiling is global: a tile belongs to the rank that
+   * owns its centre row and works on a neighbour's rows in the neighbour's memory; stripes must be at least two
+   * tiles tall, otherwise (and for layered stripes and periodic maps) schedule 0 runs when 2 is selected.
    * 0 = colour-queue scheduler: the cells are coloured 3 x 3, a micro-round serves one colour over the whole map
    * (one persistent cooperative kernel, a grid barrier per micro-round), and every particle standing on a cell
    * of that colour (one per cell, the others wait) flies one Wind::fly step, erodes and runs World::cascade on
