@@ -21,11 +21,12 @@ the reference snapshot). One JSON line is printed by rank 0.
             heights read + written, four tracks read + written) / its device time, against
             MEASURED_PEAKS.json hbm_gbs; cascade_roofline is the same for the whole-map cascade
             sweep (8 B/cell/sweep) on the 8192^2 random-slope workload
-  schedule  the single-GPU headline runs the tile-resident scheduler (SWE_OPT_SCHEDULE = 2,
-            parity-green against the sequential oracle at this density, tests/test_gpu_tiles.py);
-            the colour-queue scheduler (the stripes' schedule, equally parity-green) and round 1's
-            lock-step schedule, which exports +24 % more sand than the reference, are timed
-            beside it as `colour_queue_schedule` and `lockstep_all_at_once`
+  schedule  the headline runs the tile-resident scheduler (SWE_OPT_SCHEDULE = 2, parity-green
+            against the sequential oracle at this density, tests/test_gpu_tiles.py), on one GPU and
+            on the stripes of a multi-GPU run (tests/test_gpu_stripes.py); the colour-queue scheduler
+            (equally parity-green) and round 1's lock-step schedule, which exports +24 % more sand
+            than the reference, are timed beside it as `colour_queue_schedule` and
+            `lockstep_all_at_once`
   cpu_baseline  the unmodified reference (oracle/_ref) timed on one host core on a bounded
             sample of the same workload (the reference is single-threaded, world.hpp:100)
 """

@@ -380,9 +380,14 @@ int swe_stripe_connect(swe_engine* e, const swe_stripe_link* below, const swe_st
  * row order (the entry of this rank, links[rank], is ignored; n <= 8). Neighbours rank-1 / rank+1 serve the halo
  * and hand-off paths as in swe_stripe_connect; in addition every rank's barrier mailbox is mapped, because the
  * persistent flight kernels of all ranks run the same micro-round sequence and meet at a barrier that spans the
- * GPUs (peer stores over NVLink, system-scope release/acquire). With it a stripe engine runs the colour-queue
- * schedule (SWE_OPT_SCHEDULE = 0, parity-green at high particle density); a particle in a boundary row reads and
- * writes the neighbour's rows of its 3x3 block directly in the neighbour's memory. `colocated` = stripe engines
+ * GPUs (peer stores over NVLink, system-scope release/acquire). With it a stripe engine runs the tile-resident
+ * schedule (SWE_OPT_SCHEDULE = 2, the default: global tiling, a tile belongs to the rank that owns its centre row and
+ * works on a neighbour's rows in the neighbour's memory, three cross-GPU barriers per super-round; stripes at least
+ * two tiles tall, single layer) or the colour-queue schedule (SWE_OPT_SCHEDULE = 0, and whenever the tile schedule
+ * does not apply): a particle in a boundary row reads and writes the neighbour's rows of its 3x3 block directly in
+ * the neighbour's memory. Both are parity-green at high particle density. NOTE: with the tile schedule swe_erode on
+ * a stripe engine is COLLECTIVE AND BLOCKING: every rank must call it with the same arguments, seed and options (the
+ * ranks meet on the device), and it returns when the call's last particle has died. `colocated` = stripe engines
  * sharing this GPU (1 with one process per GPU; logical stripes in one process: their number), which caps the
  * co-resident grid of each kernel. Without it (swe_stripe_connect only) a stripe engine runs the lock-step
  * schedule. */

@@ -113,7 +113,8 @@ def test_checkpoint_is_written_atomically_and_keeps_options(tmp_path):
     w.set_option(swe.OPT_STAGGER_ROUNDS, 77)
     path = str(tmp_path / "o.swe")
     h = checkpoint.save(w, path)
-    assert h["options"] == {"cascade_interval": 1, "call_batches": 3, "schedule": 1, "stagger_rounds": 77}
+    assert h["options"] == {"cascade_interval": 1, "call_batches": 3, "schedule": 1, "stagger_rounds": 77, "tile_rounds": 0,
+                            "tile_shape": -1}
     assert os.listdir(str(tmp_path)) == ["o.swe"]               # no temporary file left behind
     w2 = checkpoint.load(path)
     assert (w2.get_option(swe.OPT_SCHEDULE), w2.get_option(swe.OPT_CALL_BATCHES), w2.get_option(swe.OPT_STAGGER_ROUNDS)) == (1, 3, 77)
