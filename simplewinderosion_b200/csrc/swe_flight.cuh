@@ -16,9 +16,10 @@ struct ParConst {
   int max_age;
 };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+template <int ROUNDS = 10>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
-  for (int r = 0; r < 10; r++) {
+  for (int r = 0; r < ROUNDS; r++) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -26,6 +27,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox4x32<10>(c, k); }
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -79,7 +81,7 @@ __device__ __forceinline__ int cell_colour(int x, int z) { return (x % 3) * 3 + 
 
 // Wind::fly (wind.hpp:28-112) for a particle that owns its cell: heights come in registers, the
 // erosion amount goes out. Returns dh: the centre cell loses dh (wind.hpp:110-111).
-template <bool ALWAYS_RNG = false>   // true: draw the turbulence numbers unconditionally (no branch in the middle of the step)
+template <bool ALWAYS_RNG = false, int RNG_ROUNDS = 10>   // ALWAYS_RNG: draw the turbulence numbers unconditionally (no branch in the middle of the step)
 __device__ __forceinline__ float fly_owned(const ParConst& C, PState& q, float hc, float hxm, float hxp, float hzm,
                                            float hzp, bool xm, bool xp, bool zm, bool zp, uint4 rng_ctr, uint2 key,
                                            float& collision_out, float& tx, float& ty, float& tz, float& tsed) {
@@ -126,7 +128,7 @@ __device__ __forceinline__ float fly_owned(const ParConst& C, PState& q, float h
   {
     const float amp = 0.1f * hfac * collision;                                    // :83
     if (ALWAYS_RNG || amp > 0.0f) {
-      const uint4 r = philox4x32_10(rng_ctr, key);
+      const uint4 r = philox4x32<RNG_ROUNDS>(rng_ctr, key);
       const float s = amp * (1.0f / 500.0f);
       sx += s * ((float)__umulhi(r.x, 1001u) - 500.0f);
       sy += s * ((float)__umulhi(r.y, 1001u) - 500.0f);

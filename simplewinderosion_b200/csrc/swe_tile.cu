@@ -1,4 +1,5 @@
-// swe_tile.cu -- parallel World::erode of a single-GPU engine: the TILE-RESIDENT scheduler.
+// swe_tile.cu -- parallel World::erode: the TILE-RESIDENT scheduler (single-GPU engines, and the stripes of a
+// multi-GPU map: TileStripe below).
 //
 // Same per-particle semantics as the colour-queue scheduler (swe_queue.cu): a particle claims its cell for a
 // micro-round of its cell's colour, flies ONE Wind::fly step (wind.hpp:28-112) against the current heights,
@@ -38,8 +39,11 @@ namespace swe {
 #ifndef SWE_TILE_ALWAYS_RNG
 #define SWE_TILE_ALWAYS_RNG 1      // draw the turbulence numbers of a step unconditionally: with ~24 lanes per warp some lane needs them
 #endif                             // anyway, and without the branch the step is one basic block for the instruction scheduler
+#ifndef SWE_TILE_PHILOX_ROUNDS
+#define SWE_TILE_PHILOX_ROUNDS 10  // rounds of the counter-based generator behind the turbulence numbers (7 was measured on B200:
+#endif                             // 168 against 170 ms per headline call -- not worth leaving the standard variant)
 #ifndef SWE_TILE_STORE_ALL
-#define SWE_TILE_STORE_ALL 1
+#define SWE_TILE_STORE_ALL 1       // inner tiles store all eight neighbours of a block back (plain stores instead of eight branches)
 #endif
 constexpr unsigned DEAD = 0x0eu;     // pcol value of a particle that died in this super-round
 constexpr unsigned PARKED = 0x0fu;   // pcol value of a particle that is not served (parked, not loaded)
@@ -308,7 +312,7 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         q.sx = b.x; q.sy = b.y; q.sz = b.z; q.age = __float_as_int(b.w);
         const size_t ci = (size_t)ix * (size_t)nz + (size_t)iz;      // global cell number (RNG counter)
         float collision, tx, ty, tz, tsed;
-        float dh = fly_owned<SWE_TILE_ALWAYS_RNG != 0>(C, q, hc, h[1], h[6], h[3], h[4], xm, xp, zm, zp,
+        float dh = fly_owned<SWE_TILE_ALWAYS_RNG != 0, SWE_TILE_PHILOX_ROUNDS>(C, q, hc, h[1], h[6], h[3], h[4], xm, xp, zm, zp,
                              make_uint4((uint32_t)ci, call, G.micro0 + tag - 1u, 0xAu), key, collision, tx, ty, tz, tsed);
         if (STRIPE && (ix < X.own_lo || ix >= X.own_hi))                                         // wind.hpp:93-96
           red_add_v4_sys((ix < X.own_lo ? X.below_t + (size_t)(ix - X.below_x0) * (size_t)nz : X.above_t + (size_t)(ix - X.above_x0) * (size_t)nz) + iz,
