@@ -1,7 +1,12 @@
 """TOOL (CPU, test infrastructure): how the statistical parity of parallel-mode scheduling variants with
 the sequential reference depends on the schedule, using tools/par_emul.c (oracle physics).
     python tools/par_emul_study.py n density map variants...
-a variant is B,S,V,C,K = batches, stagger rounds, visibility, cascade mode, steps per round."""
+a variant is B,S,V,C,K = batches, stagger rounds, visibility, cascade mode, steps per round (lock-step family), or
+    qS,order         colour queues (csrc/swe_queue.cu): stagger S in MICRO-rounds, colour order 0 / 1
+    pB,skip,T,S      colour-phased rounds, optionally tile-local with stale halos (T > 0)
+    tS,T,K,flags     tile-resident super-rounds (csrc/swe_tile.cu): stagger S in rounds, tile edge T, K rounds per
+                     super-round, flags & 1 = per-round instead of per-super-round injection
+    cS,T,A,flags     the same with block claims instead of colour phases (not built): S and A in attempts"""
 import ctypes as C
 import os
 import subprocess
