@@ -132,8 +132,10 @@ typedef enum swe_option {
    * memory before the particles are re-sorted into the next, shifted tiling. 0 (default) = auto
    * (16 for 60 x 60 tiles, 24 for 120 x 120); range [0, 64]. */
   SWE_OPT_TILE_ROUNDS = 11,
-  /* Tile-resident schedule: tile geometry. -1 (default) = by map size (120 x 120 cells / 256 threads when that
-   * still gives every SM three tiles, else 60 x 60 / 128 threads), 0 = 60 x 60, 1 = 120 x 120. */
+  /* Tile-resident schedule: tile geometry (rows x columns). -1 (default) = by map size and wind: 14,400-cell tiles /
+   * 256 threads when that still gives every SM three tiles -- 240 x 60 or 60 x 240, elongated along the prevailing
+   * wind, when pspeed points mostly along x or z, else 120 x 120 -- otherwise 60 x 60 / 128 threads.
+   * 0 = 60 x 60, 1 = 120 x 120, 2 = 240 x 60, 3 = 60 x 240. */
   SWE_OPT_TILE_SHAPE = 12
 } swe_option;
 

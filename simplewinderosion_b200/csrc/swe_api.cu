@@ -106,7 +106,7 @@ struct swe_engine {
   TileSched ts{};                     // tile-resident scheduler (swe_tile.cu): records sorted by tile
   int opt_tile_rounds = 0;            // rounds (nine micro-rounds each) a CTA keeps its tile per super-round (0 = auto: edge / 5)
   int opt_tile_shape = -1;            // -1 = by map size (tile_pick), else the index of a compiled tile geometry
-  int tile_pcap[2][2] = {{0, 0}, {0, 0}};   // particle capacity the fly kernel is configured for [shape][layered]
+  int tile_pcap[8][2] = {};           // particle capacity the fly kernel is configured for [shape][layered]
   int smem_optin = 0;
   CallCtl* d_ctl = nullptr;           // seed / call index of the current call (read by graph-replayed kernels)
   struct CachedGraph { uint64_t key; cudaGraphExec_t exec; };
@@ -705,15 +705,22 @@ struct TilePlan {
 int tile_plan(swe_engine* e, int cycles, TilePlan* P) {
   const bool layered = e->m.rock != nullptr;
   // (a layered engine keeps two planes per tile in shared memory: only ONE 120 x 120 tile would fit an SM)
-  const int shape = e->opt_tile_shape >= 0 ? e->opt_tile_shape : (layered ? 0 : tile_pick(e->m.nx, e->m.nz, e->sm_count));
-  const int TE = tile_edge(shape);
-  const int K = e->opt_tile_rounds > 0 ? e->opt_tile_rounds : (TE >= 120 ? 24 : 16);   // (A/B on B200; tools/par_emul.c mode D for the parity)
+  int shape = e->opt_tile_shape >= 0 ? e->opt_tile_shape
+                                     : (layered ? 0 : tile_pick(e->m.nx, e->m.nz, e->sm_count, e->p.pspeed[0], e->p.pspeed[2]));
+  if (e->st.enabled && e->opt_tile_shape < 0) {
+    // stripes must be two tiles tall: step down to a shorter tile when they are not (decided from the nominal stripe
+    // height nx / ranks, which every rank knows, so that all ranks pick the same geometry)
+    const int nominal = e->m.nx / (e->st.nranks > 0 ? e->st.nranks : 1) - 8;
+    if (nominal < 2 * tile_edge_x(shape)) shape = nominal >= 2 * tile_edge_x(1) && shape != 0 ? 1 : 0;
+  }
+  const int tile_cells = tile_edge_x(shape) * tile_edge_z(shape);
+  const int K = e->opt_tile_rounds > 0 ? e->opt_tile_rounds : (tile_cells > 3600 ? 24 : 16);   // (A/B on B200; tools/par_emul.c mode D for the parity)
   const int life = e->p.max_age + 2;
   const long long S = colour_stagger_micro(e, cycles) / 9;      // rounds
   // expected particles per tile while the injection runs (Poisson): mean + 5 sigma + slack stays on chip; a tile
   // with more than that parks the excess for a super-round (never lost)
   const double density = (double)cycles / ((double)e->m.nx * (double)e->m.nz);
-  const double lam = density * TE * TE * (S > 0 ? (double)life / (double)(S + life) : 1.0);
+  const double lam = density * tile_cells * (S > 0 ? (double)life / (double)(S + life) : 1.0);
   int pcap = ((int)(lam + 5.0 * std::sqrt(lam) + 64.0) + 63) / 64 * 64;
   if (const char* dbg = std::getenv("SWE_DEBUG_TILE_PCAP")) { const int v = std::atoi(dbg); if (v >= 64) pcap = v / 64 * 64; }
   const int pmax = tile_max_pcap(shape, layered, e->smem_optin > 0 ? e->smem_optin : 49152);
@@ -774,9 +781,9 @@ int erode_tile_stripes(swe_engine** engines, int n, int cycles) {
     if (i == 0) P = Q;
     else if (Q.shape != P.shape || Q.K != P.K || Q.S != P.S) return fail(SWE_ERR_STATE, "stripes disagree on the tile plan");
     if (e->cq.cap < 1 || e->st.ts.cap < 1) return fail(SWE_ERR_STATE, "stripe engine has no tile tables");
-    if (e->st.own_hi - e->st.own_lo < 2 * tile_edge(Q.shape) || e->m.nx / e->st.nranks - 8 < 2 * tile_edge(Q.shape))
+    if (e->st.own_hi - e->st.own_lo < 2 * tile_edge_x(Q.shape) || e->m.nx / e->st.nranks - 8 < 2 * tile_edge_x(Q.shape))
       return fail(SWE_ERR_STATE, "tile schedule on stripes: every stripe must be at least two tiles (%d rows) tall; "
-                                 "use SWE_OPT_TILE_SHAPE = 0 or SWE_OPT_SCHEDULE = 0", 2 * tile_edge(Q.shape));
+                                 "use SWE_OPT_TILE_SHAPE = 0 or SWE_OPT_SCHEDULE = 0", 2 * tile_edge_x(Q.shape));
     if (int rc = erode_prologue(e)) return rc;
     const size_t words = (size_t)e->st.ts.max_tiles + 1;
     SWE_CUDA(cudaMemsetAsync(e->st.ts.count, 0, (4 * words + 16) * sizeof(unsigned), e->stream));
@@ -1882,7 +1889,6 @@ int swe_stripe_connect_ring(swe_engine* e, int rank, int n, const swe_stripe_lin
   // the neighbours have mapped); available when every rank's buffers are big enough and its stripe is at least two
   // tiles tall -- decided from numbers every rank knows, so that all ranks decide alike
   {
-    const int shape = tile_pick(e->m.nx, e->m.nz, e->sm_count);
     const int words = tile_max_tiles(e->m.nx, e->m.nz) + 1;
     auto layout = [&](void* qa, void* qb, int qcap, TileSched* out) -> bool {
       if (!qa || !qb || qcap < 1024) return false;
@@ -1896,7 +1902,7 @@ int swe_stripe_connect_ring(swe_engine* e, int rank, int n, const swe_stripe_lin
       out->cap = qcap; out->max_tiles = words - 1;
       return true;
     };
-    bool ok = (e->m.nx / n - 8) >= 2 * tile_edge(shape) && (S.own_hi - S.own_lo) >= 2 * tile_edge(shape) && S.merged_planes;
+    bool ok = (e->m.nx / n - 8) >= 2 * tile_edge_x(0) && (S.own_hi - S.own_lo) >= 2 * tile_edge_x(0) && S.merged_planes;   // (the smallest tile)
     ok = ok && layout(e->cq.a, e->cq.b, e->cq.cap, &S.ts);
     TileStripeHost H{};
     H.enabled = 1; H.own_lo = S.own_lo; H.own_hi = S.own_hi;

@@ -48,16 +48,19 @@ namespace swe {
 constexpr unsigned DEAD = 0x0eu;     // pcol value of a particle that died in this super-round
 constexpr unsigned PARKED = 0x0fu;   // pcol value of a particle that is not served (parked, not loaded)
 
-// Two tile geometries (host picks per call: tile_pick): 120 x 120 cells / 256 threads for big maps (more particles per
-// micro-round and CTA: fuller warps; measured on the 4096^2 headline: 170 ms against 200 ms with 60 x 60), 60 x 60 /
-// 128 threads for maps that would not fill the GPU with 120 x 120 tiles.
-struct TileShape { int edge, threads; };
-static const TileShape kShapes[2] = {{60, 128}, {120, 256}};
-int tile_shapes() { return 2; }
-int tile_edge(int shape) { return kShapes[shape].edge; }
+// Tile geometries (host picks per call: tile_pick). 60 x 60 cells / 128 threads for maps that would not fill the GPU
+// with bigger tiles; 14,400-cell tiles / 256 threads for big maps (more particles per micro-round and CTA: fuller
+// warps; measured on the 4096^2 headline: 170 ms against 200 ms with 60 x 60) in three aspect ratios: 120 x 120, and
+// 240 x 60 / 60 x 240 ELONGATED ALONG THE PREVAILING WIND -- a particle travels up to ~2 cells per round downwind, so a
+// tile that is long in that direction parks fewer particles on its border ring (tools/par_emul.c: exported-sand bias
+// against the sequential reference +2.2 % instead of +3.4 %, erosion-field correlation 0.968 instead of 0.963).
+struct TileShape { int ex, ez, threads; };     // rows (x), columns (z), threads per CTA
+static const TileShape kShapes[4] = {{60, 60, 128}, {120, 120, 256}, {240, 60, 256}, {60, 240, 256}};
+int tile_shapes() { return 4; }
+int tile_edge_x(int shape) { return kShapes[shape].ex; }
+int tile_edge_z(int shape) { return kShapes[shape].ez; }
 int tile_threads(int shape) { return kShapes[shape].threads; }
 
-__device__ __forceinline__ int tile_of(int ix, int iz, int off, int ntz, int tt) { return ((ix + off) / tt) * ntz + (iz + off) / tt; }
 
 // one atomic per warp and destination tile
 __device__ __forceinline__ void count_dest(unsigned* count, int dest, bool active) {
@@ -69,19 +72,19 @@ __device__ __forceinline__ void count_dest(unsigned* count, int dest, bool activ
 }
 
 // colour under which the particle standing on (ix, iz) is served by the tile with origin (x0, z0), or PARKED
-template <int TT>
+template <int TX, int TZ>
 __device__ __forceinline__ unsigned service_colour(int ix, int iz, int x0, int z0, int nx, int nz) {
   const int lx = ix - x0, lz = iz - z0;
-  if ((unsigned)lx >= (unsigned)TT || (unsigned)lz >= (unsigned)TT) return PARKED;          // left the tile
-  if ((lx == 0 && ix != 0) || (lx == TT - 1 && ix != nx - 1) || (lz == 0 && iz != 0) || (lz == TT - 1 && iz != nz - 1))
+  if ((unsigned)lx >= (unsigned)TX || (unsigned)lz >= (unsigned)TZ) return PARKED;          // left the tile
+  if ((lx == 0 && ix != 0) || (lx == TX - 1 && ix != nx - 1) || (lz == 0 && iz != 0) || (lz == TZ - 1 && iz != nz - 1))
     return PARKED;                                                                         // border ring
   return (unsigned)((lx % 3) * 3 + lz % 3);
 }
 
 struct TileGeom {
-  int edge;                          // tile edge T (multiple of 3)
-  int off_cur, ntx_cur, ntz_cur;     // tiling served now: tile (a, b) covers [a T - off, (a + 1) T - off) x [b T - off, ...)
-  int off_next, ntx_next, ntz_next;  // tiling of the next super-round
+  int ex, ez;                        // tile edges in x (rows) and z (columns), multiples of 3
+  int offx_cur, offz_cur, ntx_cur, ntz_cur;      // tiling served now: tile (a, b) covers [a ex - offx, (a + 1) ex - offx) x [b ez - offz, ...)
+  int offx_next, offz_next, ntx_next, ntz_next;  // tiling of the next super-round
   int cur;                           // index of the record arrays / base array that hold the current segments
   int inj_lo, inj_hi;                // particle ids injected for the NEXT super-round
   unsigned micro0;                   // number of the super-round's first micro-round within the call (RNG counter)
@@ -147,12 +150,12 @@ __device__ __forceinline__ void count_dest_stripe(const TileSched& S, const Tile
 // Register budget: three resident 256-thread CTAs per SM (shared memory allows three 120 x 120 tiles) = at most 85
 // registers. Measured on B200: left to itself with a 255-register budget ptxas takes 87, only two CTAs fit, and the
 // headline call goes from 166 to 201 ms.
-template <int TT, int TNT, bool LAYERED, bool STRIPE>
+template <int TX, int TZ, int TNT, bool LAYERED, bool STRIPE>
 __global__ void __launch_bounds__(TNT, TNT >= 256 ? 3 : 6)
 tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, uint2 key, uint32_t call, DevStats* stats,
                 const TileStripe X) {
-  constexpr int TLAT = TT / 3;
-  static_assert(TT % 3 == 0 && TNT % 32 == 0, "tile edge: multiple of 3");
+  constexpr int TLATZ = TZ / 3, TCELLS = TX * TZ, TLAT2 = (TX / 3) * (TZ / 3);
+  static_assert(TX % 3 == 0 && TZ % 3 == 0 && TNT % 32 == 0, "tile edges: multiples of 3");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = (int)threadIdx.x;
   const unsigned lane = (unsigned)tid & 31u;
@@ -175,10 +178,10 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         active = !m.oob(ix, iz);                                     // (dies in its first fly() call: never stored)
         if (active) {
           if (STRIPE) {                                              // every rank walks the whole list and keeps its own tiles' particles
-            const int a = (ix + G.off_next) / TT;
+            const int a = (ix + G.offx_next) / TX;
             active = a >= X.a_lo_next && a < X.a_hi_next;
-            dest = (a - X.a_lo_next) * G.ntz_next + (iz + G.off_next) / TT;
-          } else dest = tile_of(ix, iz, G.off_next, G.ntz_next, TT);
+            dest = (a - X.a_lo_next) * G.ntz_next + (iz + G.offz_next) / TZ;
+          } else dest = ((ix + G.offx_next) / TX) * G.ntz_next + (iz + G.offz_next) / TZ;
         }
       }
       count_dest(S.count, dest, active);
@@ -193,15 +196,15 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
   const int np = min(n, G.pcap);
   float4* ga = (G.cur ? S.pa[1] : S.pa[0]) + seg;      // this tile's records: nobody else touches them in this launch
   float4* gb = (G.cur ? S.pb[1] : S.pb[0]) + seg;
-  const int x0 = ((STRIPE ? X.a_lo_cur : 0) + (int)blockIdx.x / G.ntz_cur) * TT - G.off_cur, z0 = ((int)blockIdx.x % G.ntz_cur) * TT - G.off_cur;
+  const int x0 = ((STRIPE ? X.a_lo_cur : 0) + (int)blockIdx.x / G.ntz_cur) * TX - G.offx_cur, z0 = ((int)blockIdx.x % G.ntz_cur) * TZ - G.offz_cur;
   // a tile that does not touch the map's edge: every neighbour of a served cell exists
-  const bool inner = x0 > 0 && z0 > 0 && x0 + TT < nx && z0 + TT < nz;
+  const bool inner = x0 > 0 && z0 > 0 && x0 + TX < nx && z0 + TZ < nz;
 
   // ---- shared memory: heights [rock] | claim lattice | list | pcol ----
   float* hs = reinterpret_cast<float*>(smem_raw);
-  float* rs = hs + (LAYERED ? TT * TT : 0);
-  unsigned* claim = reinterpret_cast<unsigned*>(rs + TT * TT);
-  unsigned short* list = reinterpret_cast<unsigned short*>(claim + TLAT * TLAT);
+  float* rs = hs + (LAYERED ? TCELLS : 0);
+  unsigned* claim = reinterpret_cast<unsigned*>(rs + TCELLS);
+  unsigned short* list = reinterpret_cast<unsigned short*>(claim + TLAT2);
   uint4* pcol128 = reinterpret_cast<uint4*>(list + G.pcap);               // pcap is a multiple of 64
   unsigned char* pcol = reinterpret_cast<unsigned char*>(pcol128);
   __shared__ unsigned s_n[2];
@@ -211,8 +214,8 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
   if (tid < 2) s_n[tid] = 0u;
   if (tid == 2) s_lost = 0.0f;
   if (tid < 3) s_stat[tid] = 0u;
-  for (int i = tid; i < TT * TT; i += TNT) {
-    const int gx = x0 + i / TT, gz = z0 + i % TT;
+  for (int i = tid; i < TCELLS; i += TNT) {
+    const int gx = x0 + i / TZ, gz = z0 + i % TZ;
     const bool in = gx >= 0 && gx < nx && gz >= 0 && gz < nz;
     if (STRIPE && in && (gx < X.own_lo || gx >= X.own_hi)) {        // a neighbour's row: read it where it lives
       hs[i] = gx < X.own_lo ? ld_sys_f32(X.below_h + (size_t)(gx - X.below_x0) * (size_t)nz + gz)
@@ -222,13 +225,13 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
     hs[i] = in ? __ldcg(m.height + (size_t)(gx - m.x0) * (size_t)nz + gz) : 0.0f;
     if (LAYERED) rs[i] = in ? __ldcg(m.rock + (size_t)(gx - m.x0) * (size_t)nz + gz) : 0.0f;
   }
-  for (int i = tid; i < TLAT * TLAT; i += TNT) claim[i] = 0u;
+  for (int i = tid; i < TLAT2; i += TNT) claim[i] = 0u;
   const int npad = (np + 15) & ~15;
   for (int p = tid; p < npad; p += TNT) {
     unsigned col = PARKED;
     if (p < np) {
       const float4 a = __ldcg(ga + p);
-      col = service_colour<TT>(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), x0, z0, nx, nz);
+      col = service_colour<TX, TZ>(__float2int_rd(a.x + 0.5f), __float2int_rd(a.z + 0.5f), x0, z0, nx, nz);
     }
     pcol[p] = (unsigned char)col;
   }
@@ -285,8 +288,8 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         const int ix = __float2int_rd(a.x + 0.5f), iz = __float2int_rd(a.z + 0.5f);               // wind.hpp:30
         const int lx = ix - x0, lz = iz - z0;
         // one particle per cell per micro-round; the others wait for the colour's next turn
-        if (atomicMax(&claim[(lx / 3) * TLAT + lz / 3], tag) >= tag) continue;
-        const int li = lx * TT + lz;
+        if (atomicMax(&claim[(lx / 3) * TLATZ + lz / 3], tag) >= tag) continue;
+        const int li = lx * TZ + lz;
         const bool xm = inner || ix > 0, xp = inner || ix + 1 < nx, zm = inner || iz > 0, zp = inner || iz + 1 < nz;
         const unsigned valid = inner ? 0xffu :
                                ((xm && zm ? 1u : 0u) | (xm ? 2u : 0u) | (xm && zp ? 4u : 0u) | (zm ? 8u : 0u) |
@@ -295,13 +298,13 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         float h[8];
 #pragma unroll
         for (int k = 0; k < 8; k++)
-          h[k] = ((valid >> k) & 1u) ? hs[li + block::slot_dx(k) * TT + block::slot_dz(k)] : hc;
+          h[k] = ((valid >> k) & 1u) ? hs[li + block::slot_dx(k) * TZ + block::slot_dz(k)] : hc;
         float rock_c = 0.0f, rk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (LAYERED) {
           rock_c = rs[li];
 #pragma unroll
           for (int k = 0; k < 8; k++)
-            if ((valid >> k) & 1u) rk[k] = rs[li + block::slot_dx(k) * TT + block::slot_dz(k)];
+            if ((valid >> k) & 1u) rk[k] = rs[li + block::slot_dx(k) * TZ + block::slot_dz(k)];
         }
         // the order of the neighbours does not depend on the centre (swe_block.cuh: sort_neighbours), so the sorting
         // network is issued here, where it interleaves with the flight arithmetic instead of waiting for its result
@@ -346,14 +349,14 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
         for (int i8 = 0; i8 < 8; i8++)
           if ((SWE_TILE_STORE_ALL && inner) || ((moved >> i8) & 1u)) {
             const unsigned code = (0xa9864210u >> (4 * s[i8])) & 15u;
-            hs[li + (int)(code >> 2) * TT + (int)(code & 3u) - (TT + 1)] = v[i8];
+            hs[li + (int)(code >> 2) * TZ + (int)(code & 3u) - (TZ + 1)] = v[i8];
           }
         n_steps++;
         const int jx = __float2int_rd(q.px + 0.5f), jz = __float2int_rd(q.pz + 0.5f);
         unsigned col;
         if (m.oob(jx, jz)) { n_oob++; lost += q.sed; q.age = -1; col = DEAD; }                   // :32-38 (the next fly() call)
         else if (q.age > C.max_age) { n_age++; lost += q.sed; q.age = -1; col = DEAD; }          // :45-46
-        else col = service_colour<TT>(jx, jz, x0, z0, nx, nz);
+        else col = service_colour<TX, TZ>(jx, jz, x0, z0, nx, nz);
         __stcg(ga + p, make_float4(q.px, q.py, q.pz, q.sed));
         __stcg(gb + p, make_float4(q.sx, q.sy, q.sz, __int_as_float(q.age)));
         pcol[p] = (unsigned char)col;
@@ -365,8 +368,8 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
 
   // ---- store: heights if anything moved; destination counts of the survivors (dead records carry age < 0) ----
   if (__syncthreads_or(dirty)) {
-    for (int i = tid; i < TT * TT; i += TNT) {
-      const int gx = x0 + i / TT, gz = z0 + i % TT;
+    for (int i = tid; i < TCELLS; i += TNT) {
+      const int gx = x0 + i / TZ, gz = z0 + i % TZ;
       if (!(gx >= 0 && gx < nx && gz >= 0 && gz < nz)) continue;
       if (STRIPE && (gx < X.own_lo || gx >= X.own_hi))
         st_sys_f32((gx < X.own_lo ? X.below_h + (size_t)(gx - X.below_x0) * (size_t)nz : X.above_h + (size_t)(gx - X.above_x0) * (size_t)nz) + gz, hs[i]);
@@ -374,8 +377,8 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
     }
   }
   if (LAYERED && __syncthreads_or(dirty_rock)) {
-    for (int i = tid; i < TT * TT; i += TNT) {
-      const int gx = x0 + i / TT, gz = z0 + i % TT;
+    for (int i = tid; i < TCELLS; i += TNT) {
+      const int gx = x0 + i / TZ, gz = z0 + i % TZ;
       if (gx >= 0 && gx < nx && gz >= 0 && gz < nz) m.rock[(size_t)(gx - m.x0) * (size_t)nz + gz] = rs[i];
     }
   }
@@ -387,7 +390,7 @@ tile_fly_kernel(MapView m, ParConst C, block::Thr T, TileSched S, TileGeom G, ui
       alive = p >= np || pcol[p] != DEAD;              // (beyond pcap: parked for this super-round)
       if (alive) {
         const float4 a = __ldcg(ga + p);
-        da = (__float2int_rd(a.x + 0.5f) + G.off_next) / TT; db = (__float2int_rd(a.z + 0.5f) + G.off_next) / TT;
+        da = (__float2int_rd(a.x + 0.5f) + G.offx_next) / TX; db = (__float2int_rd(a.z + 0.5f) + G.offz_next) / TZ;
         dest = da * G.ntz_next + db;
       }
     }
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(MapView m, TileSched 
     }
     int dest = 0, own = 0;
     if (active) {
-      const int ta = (__float2int_rd(a.x + 0.5f) + G.off_next) / G.edge, tb = (__float2int_rd(a.z + 0.5f) + G.off_next) / G.edge;
+      const int ta = (__float2int_rd(a.x + 0.5f) + G.offx_next) / G.ex, tb = (__float2int_rd(a.z + 0.5f) + G.offz_next) / G.ez;
       if (X.enabled) {
         own = next_owner(X, ta);
         if (j >= total) {                              // a new particle: every rank walks the whole list and keeps its own
@@ -561,9 +564,9 @@ void launch_tile_xbar(void* const* mailboxes, int rank, int nranks, unsigned lon
 }
 
 static size_t tile_smem_bytes(int shape, bool layered, int pcap) {
-  const int tt = kShapes[shape].edge;
-  return (size_t)(layered ? 2 : 1) * tt * tt * sizeof(float) + (size_t)pcap * (sizeof(unsigned short) + 1) +
-         (size_t)(tt / 3) * (tt / 3) * sizeof(unsigned) + 16;
+  const int ex = kShapes[shape].ex, ez = kShapes[shape].ez;
+  return (size_t)(layered ? 2 : 1) * ex * ez * sizeof(float) + (size_t)pcap * (sizeof(unsigned short) + 1) +
+         (size_t)(ex / 3) * (ez / 3) * sizeof(unsigned) + 16;
 }
 
 // largest pcap (multiple of 64) the device can give one CTA; the list holds 16-bit particle indices
@@ -574,13 +577,13 @@ int tile_max_pcap(int shape, bool layered, int smem_optin) {
   return p < 64 ? 0 : (int)(p > 32768 ? 32768 : p);
 }
 
-static TileGeom tile_geom(const MapView& m, int tt, int s) {
+static TileGeom tile_geom(const MapView& m, int ex, int ez, int s) {
   TileGeom G{};
-  G.edge = tt;
-  G.off_cur = (s % 3) * (tt / 3);
-  G.ntx_cur = (m.nx + G.off_cur + tt - 1) / tt; G.ntz_cur = (m.nz + G.off_cur + tt - 1) / tt;
-  G.off_next = ((s + 1) % 3) * (tt / 3);
-  G.ntx_next = (m.nx + G.off_next + tt - 1) / tt; G.ntz_next = (m.nz + G.off_next + tt - 1) / tt;
+  G.ex = ex; G.ez = ez;
+  G.offx_cur = (s % 3) * (ex / 3); G.offz_cur = (s % 3) * (ez / 3);
+  G.ntx_cur = (m.nx + G.offx_cur + ex - 1) / ex; G.ntz_cur = (m.nz + G.offz_cur + ez - 1) / ez;
+  G.offx_next = ((s + 1) % 3) * (ex / 3); G.offz_next = ((s + 1) % 3) * (ez / 3);
+  G.ntx_next = (m.nx + G.offx_next + ex - 1) / ex; G.ntz_next = (m.nz + G.offz_next + ez - 1) / ez;
   G.cur = s & 1;
   return G;
 }
@@ -589,18 +592,21 @@ static TileGeom tile_geom(const MapView& m, int tt, int s) {
 int tile_max_tiles(int nx, int nz) {
   int best = 0;
   for (const TileShape& sh : kShapes) {
-    const int off = 2 * (sh.edge / 3);
-    const int t = ((nx + off + sh.edge - 1) / sh.edge) * ((nz + off + sh.edge - 1) / sh.edge);
+    const int t = ((nx + 2 * (sh.ex / 3) + sh.ex - 1) / sh.ex) * ((nz + 2 * (sh.ez / 3) + sh.ez - 1) / sh.ez);
     if (t > best) best = t;
   }
   return best;
 }
 
-// Shape for a map: the big tiles when they still give every SM a few CTAs
-int tile_pick(int nx, int nz, int sm_count) {
-  const int big = kShapes[1].edge;
-  const long long tiles = (long long)((nx + big - 1) / big) * ((nz + big - 1) / big);
-  return tiles >= 3LL * sm_count ? 1 : 0;
+// Shape for a map and a prevailing wind (px, pz): the big tiles when they still give every SM a few CTAs, elongated
+// along the wind when it blows mostly along one axis
+int tile_pick(int nx, int nz, int sm_count, float px, float pz) {
+  const long long tiles = (long long)((nx + 119) / 120) * ((nz + 119) / 120);
+  if (tiles < 3LL * sm_count) return 0;
+  const float ax = fabsf(px), az = fabsf(pz);
+  if (ax >= 2.0f * az && nx >= 2 * kShapes[2].ex) return 2;
+  if (az >= 2.0f * ax && nz >= 2 * kShapes[3].ez) return 3;
+  return 1;
 }
 
 // stripes: first tile row (tiling offset off) whose centre row lies at or beyond global row x
@@ -613,23 +619,23 @@ static int first_tile_row(int x, int tt, int off, int nx) {
   return a > ntx ? ntx : a;
 }
 
-template <int TT, int TNT>
+template <int TX, int TZ, int TNT>
 static void launch_fly(bool layered, bool stripe, int grid, size_t smem, cudaStream_t st, const MapView& m, const ParConst& C,
                        const block::Thr& T, const TileSched& S, const TileGeom& G, uint2 key, uint32_t call, DevStats* stats,
                        const TileStripe& X) {
-  if (stripe) tile_fly_kernel<TT, TNT, false, true><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
-  else if (layered) tile_fly_kernel<TT, TNT, true, false><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
-  else tile_fly_kernel<TT, TNT, false, false><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
+  if (stripe) tile_fly_kernel<TX, TZ, TNT, false, true><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
+  else if (layered) tile_fly_kernel<TX, TZ, TNT, true, false><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
+  else tile_fly_kernel<TX, TZ, TNT, false, false><<<grid, TNT, smem, st>>>(m, C, T, S, G, key, call, stats, X);
 }
 
 // Geometry of super-round s (s = -1: only the injection of super-round 0's particles) for a single-GPU engine or one
 // rank of a stripe group.
 static void tile_round_setup(const MapView& m, int shape, int s, int K, int pcap, int inj_lo, int inj_hi,
                              const TileSched& S, const TileStripeHost* H, TileGeom& G, TileStripe& X) {
-  const int tt = kShapes[shape].edge;
-  if (s >= 0) G = tile_geom(m, tt, s);
+  const int tt = kShapes[shape].ex;           // (stripes cut the map along x: tile rows)
+  if (s >= 0) G = tile_geom(m, kShapes[shape].ex, kShapes[shape].ez, s);
   else {                                      // no tiles yet: cur = 1 holds an empty segment table (base[1][0] = 0)
-    G = tile_geom(m, tt, 2);                  // (s + 1) % 3 == 0  -> next tiling is tiling 0
+    G = tile_geom(m, kShapes[shape].ex, kShapes[shape].ez, 2);   // (s + 1) % 3 == 0  -> next tiling is tiling 0
     G.ntx_cur = 0; G.ntz_cur = 0; G.cur = 1;
   }
   G.inj_lo = inj_lo; G.inj_hi = inj_hi;
@@ -640,12 +646,12 @@ static void tile_round_setup(const MapView& m, int shape, int s, int K, int pcap
   const int nxt = G.cur ^ 1;
   X.enabled = 1; X.own_lo = H->own_lo; X.own_hi = H->own_hi;
   X.has_below = H->has_below; X.has_above = H->has_above;
-  const int a_lo_cur = first_tile_row(H->own_lo, tt, G.off_cur, m.nx), a_hi_cur = first_tile_row(H->own_hi, tt, G.off_cur, m.nx);
+  const int a_lo_cur = first_tile_row(H->own_lo, tt, G.offx_cur, m.nx), a_hi_cur = first_tile_row(H->own_hi, tt, G.offx_cur, m.nx);
   X.a_lo_cur = a_lo_cur;
   if (s >= 0) G.ntx_cur = a_hi_cur - a_lo_cur;                       // tile rows this rank launches
-  X.a_lo_next = first_tile_row(H->own_lo, tt, G.off_next, m.nx);
-  X.a_hi_next = first_tile_row(H->own_hi, tt, G.off_next, m.nx);
-  X.a_lo_next_below = H->has_below ? first_tile_row(H->below_lo, tt, G.off_next, m.nx) : 0;
+  X.a_lo_next = first_tile_row(H->own_lo, tt, G.offx_next, m.nx);
+  X.a_hi_next = first_tile_row(H->own_hi, tt, G.offx_next, m.nx);
+  X.a_lo_next_below = H->has_below ? first_tile_row(H->below_lo, tt, G.offx_next, m.nx) : 0;
   G.ntx_next = X.a_hi_next - X.a_lo_next;                            // tile rows of the next tiling this rank owns (scan length)
   X.below_h = H->below_h; X.below_t = H->below_t; X.below_x0 = H->below_x0;
   X.above_h = H->above_h; X.above_t = H->above_t; X.above_x0 = H->above_x0;
@@ -678,8 +684,14 @@ int launch_tile_phase(int phase, const MapView& m, const swe_params& p, const Ti
     const bool layered = m.rock != nullptr;
     const size_t smem = tile_smem_bytes(shape, layered, pcap);
     if (ntiles + inj_blocks <= 0) return 0;
-    if (shape == 1) launch_fly<120, 256>(layered, X.enabled != 0, ntiles + inj_blocks, smem, st, m, make_const(p), T, S, G, key, call, stats, X);
-    else launch_fly<60, 128>(layered, X.enabled != 0, ntiles + inj_blocks, smem, st, m, make_const(p), T, S, G, key, call, stats, X);
+    const int grid = ntiles + inj_blocks;
+    const bool stripe = X.enabled != 0;
+    switch (shape) {
+      case 1: launch_fly<120, 120, 256>(layered, stripe, grid, smem, st, m, make_const(p), T, S, G, key, call, stats, X); break;
+      case 2: launch_fly<240, 60, 256>(layered, stripe, grid, smem, st, m, make_const(p), T, S, G, key, call, stats, X); break;
+      case 3: launch_fly<60, 240, 256>(layered, stripe, grid, smem, st, m, make_const(p), T, S, G, key, call, stats, X); break;
+      default: launch_fly<60, 60, 128>(layered, stripe, grid, smem, st, m, make_const(p), T, S, G, key, call, stats, X); break;
+    }
     return 1;
   }
   if (phase == 1) {
@@ -700,31 +712,39 @@ int launch_tile_super_round(const MapView& m, const swe_params& p, const TileSch
   return n;
 }
 
-cudaError_t tile_configure(int shape, bool layered, int pcap) {
-  const int smem = (int)tile_smem_bytes(shape, layered, pcap);
+template <int TX, int TZ, int TNT>
+static cudaError_t configure_fly(bool layered, int smem) {
   const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
-  cudaError_t err;
-  if (shape == 1) {
-    err = layered ? cudaFuncSetAttribute(tile_fly_kernel<120, 256, true, false>, at, smem) : cudaFuncSetAttribute(tile_fly_kernel<120, 256, false, false>, at, smem);
-    if (err == cudaSuccess && !layered) err = cudaFuncSetAttribute(tile_fly_kernel<120, 256, false, true>, at, smem);
-  } else {
-    err = layered ? cudaFuncSetAttribute(tile_fly_kernel<60, 128, true, false>, at, smem) : cudaFuncSetAttribute(tile_fly_kernel<60, 128, false, false>, at, smem);
-    if (err == cudaSuccess && !layered) err = cudaFuncSetAttribute(tile_fly_kernel<60, 128, false, true>, at, smem);
-  }
+  if (layered) return cudaFuncSetAttribute(tile_fly_kernel<TX, TZ, TNT, true, false>, at, smem);
+  cudaError_t err = cudaFuncSetAttribute(tile_fly_kernel<TX, TZ, TNT, false, false>, at, smem);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(tile_fly_kernel<TX, TZ, TNT, false, true>, at, smem);
   return err;
 }
 
-void preload_tile() {
+cudaError_t tile_configure(int shape, bool layered, int pcap) {
+  const int smem = (int)tile_smem_bytes(shape, layered, pcap);
+  switch (shape) {
+    case 1: return configure_fly<120, 120, 256>(layered, smem);
+    case 2: return configure_fly<240, 60, 256>(layered, smem);
+    case 3: return configure_fly<60, 240, 256>(layered, smem);
+    default: return configure_fly<60, 60, 128>(layered, smem);
+  }
+}
+
+template <int TX, int TZ, int TNT>
+static void preload_fly() {
   cudaFuncAttributes a;
-  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, false, false>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, true, false>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<60, 128, false, true>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, false, false>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, true, false>);
-  cudaFuncGetAttributes(&a, tile_fly_kernel<120, 256, false, true>);
-  cudaFuncGetAttributes(&a, tile_xbar_kernel);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<TX, TZ, TNT, false, false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<TX, TZ, TNT, true, false>);
+  cudaFuncGetAttributes(&a, tile_fly_kernel<TX, TZ, TNT, false, true>);
+}
+
+void preload_tile() {
+  preload_fly<60, 60, 128>(); preload_fly<120, 120, 256>(); preload_fly<240, 60, 256>(); preload_fly<60, 240, 256>();
+  cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, tile_scan_kernel);
   cudaFuncGetAttributes(&a, tile_scatter_kernel);
+  cudaFuncGetAttributes(&a, tile_xbar_kernel);
 }
 
 }  // namespace swe

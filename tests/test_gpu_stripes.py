@@ -101,7 +101,8 @@ def test_striped_erode_accounts_for_every_particle(n, world, cycles, ring):
     assert abs(float(f.mean()) / float(single.download(swe.MOMENTUMX).mean()) - 1.0) < 0.05
 
 
-@pytest.mark.parametrize("nx,nz,world,shape", [(512, 512, 2, -1), (768, 320, 3, -1), (1024, 256, 4, 0), (1024, 384, 4, 1), (512, 200, 2, 1)])
+@pytest.mark.parametrize("nx,nz,world,shape", [(512, 512, 2, -1), (768, 320, 3, -1), (1024, 256, 4, 0), (1024, 384, 4, 1), (512, 200, 2, 1),
+                                               (1024, 256, 2, 2), (768, 512, 3, 3)])
 def test_striped_erode_tile_schedule(nx, nz, world, shape):
     """The tile-resident schedule on stripes (stripes at least two tiles tall): global tiling, a tile belongs to the rank
     that owns its centre row and reads / writes a neighbour's rows in the neighbour's memory, survivors are scattered
@@ -118,7 +119,7 @@ def test_striped_erode_tile_schedule(nx, nz, world, shape):
         w.set_option(swe.OPT_TILE_SHAPE, shape)
         w.srand(seed)
     single.upload(hm); other.upload(hm)
-    if shape == 1 and nx // world < 248:
+    if shape in (1, 2) and nx // world < (248 if shape == 1 else 488):
         with pytest.raises(swe.SweError):        # stripes of 256 rows are fine for 120-row tiles, shorter ones are refused loudly
             g.erode(cycles)
         return

@@ -20,10 +20,11 @@ pytestmark = pytest.mark.gpu
 TILES = {swe.OPT_SCHEDULE: swe.SCHEDULE_TILES}
 
 
-@pytest.mark.parametrize("shape", [1, 0], ids=["120x120", "60x60"])
+@pytest.mark.parametrize("shape", [2, 1, 0], ids=["240x60", "120x120", "60x60"])
 def test_tiles_headline_density_quarter_particle_per_cell(shape):
     """1024^2 / 262,144 particles = 0.25 per cell: the density of bench.py's headline (4096^2 / 4,194,304), with the
-    tile geometry the headline runs (120 x 120 cells, 24 rounds per super-round) and with the small one."""
+    tile geometry the headline runs (240 x 60 cells: elongated along the wind, 24 rounds per super-round), the square
+    one of the same size and the small one."""
     n, cycles = 1024, 1 << 18
     hm = noise_map(n, seed=1, layers=8, workers=8)
     r = compare(n, cycles, hm, opts={**TILES, swe.OPT_TILE_SHAPE: shape})
@@ -35,9 +36,10 @@ def test_tiles_headline_density_quarter_particle_per_cell(shape):
     assert r["drift"] < 2e-6, r
 
 
-@pytest.mark.parametrize("shape", [0, 1], ids=["60x60", "120x120"])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3], ids=["60x60", "120x120", "240x60", "60x240"])
 def test_tiles_quarter_particle_per_cell_512(shape):
-    """Both compiled tile geometries (a 512^2 map would pick 60 x 60 by itself; 4096^2 picks 120 x 120)."""
+    """Every compiled tile geometry (a 512^2 map would pick 60 x 60 by itself; 4096^2 with the wind along x picks 240 x 60;
+    60 x 240 is what a wind along z would pick -- here it is elongated ACROSS the wind, the unfavourable case)."""
     n, cycles = 512, 1 << 16
     hm = noise_map(n, seed=1, layers=8, workers=4)
     r = compare(n, cycles, hm, opts={**TILES, swe.OPT_TILE_SHAPE: shape})
@@ -78,7 +80,7 @@ def test_tiles_sparse_reference_frame():
     assert r["drift"] < 2e-6, r
 
 
-@pytest.mark.parametrize("shape", [0, 1], ids=["60x60", "120x120"])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3], ids=["60x60", "120x120", "240x60", "60x240"])
 @pytest.mark.parametrize("nx,nz", [(100, 100), (61, 59), (200, 90), (90, 333), (20, 500)])
 def test_tiles_odd_map_shapes_counters_and_mass_balance(nx, nz, shape):
     """Maps that are not multiples of the tile edge (60), smaller than a tile, and non-square: every particle is
@@ -168,7 +170,7 @@ def test_tiles_options_and_fallbacks():
     for bad in (-1, 65):
         with pytest.raises(swe.SweError):
             w.set_option(swe.OPT_TILE_ROUNDS, bad)
-    for bad in (-2, 2):
+    for bad in (-2, 4):
         with pytest.raises(swe.SweError):
             w.set_option(swe.OPT_TILE_SHAPE, bad)
     with pytest.raises(swe.SweError):

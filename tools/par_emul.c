@@ -329,15 +329,17 @@ long long emul_erode_tiles(swo_world* w, int cycles, int stagger, int T, int K, 
   int* home = (int*)malloc(sizeof(int) * (size_t)(n + 1));
   for (int i = 0; i < n; i++) { swo_spawn(w, &q[i]); alive[i] = 1; }
   int live = n, stamp = 0;
-  const int ntz = nz / T + 2;
+  /* T = tile edge, or TX * 1000 + TZ for a rectangular tile (TX rows along x, the wind axis) */
+  const int TX = T >= 1000 ? T / 1000 : T, TZ = T >= 1000 ? T % 1000 : T;
+  const int ntz = nz / TZ + 2;
   while (live > 0) {
-    const int off = (int)(sr % 3) * (T / 3);   /* three tilings: a cell lies on the x-ring of at most one and on the z-ring of at most one */
+    const int offx = (int)(sr % 3) * (TX / 3), offz = (int)(sr % 3) * (TZ / 3);   /* three tilings: a cell lies on the x-ring of at most one and on the z-ring of at most one */
     for (int i = 0; i < n; i++) {
       home[i] = -1;
       if (!alive[i]) continue;
       const int ix = (int)roundf(q[i].pos[0]), iz = (int)roundf(q[i].pos[2]);
       if (oob(w, ix, iz)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
-      home[i] = ((ix + off) / T) * ntz + (iz + off) / T;
+      home[i] = ((ix + offx) / TX) * ntz + (iz + offz) / TZ;
     }
     for (int r = 0; r < K; r++) {
       const long long round = sr * K + r;
@@ -352,9 +354,9 @@ long long emul_erode_tiles(swo_world* w, int cycles, int stagger, int T, int K, 
           const int ix = (int)roundf(q[i].pos[0]), iz = (int)roundf(q[i].pos[2]);
           if (oob(w, ix, iz)) { alive[i] = 0; live--; lost += (double)q[i].sediment; continue; }
           if ((ix % 3) * 3 + iz % 3 != c) continue;
-          if (((ix + off) / T) * ntz + (iz + off) / T != home[i]) continue;            /* left its tile: parked */
-          const int lx = (ix + off) % T, lz = (iz + off) % T;
-          if ((lx == 0 && ix != 0) || (lx == T - 1 && ix != nx - 1) || (lz == 0 && iz != 0) || (lz == T - 1 && iz != nz - 1))
+          if (((ix + offx) / TX) * ntz + (iz + offz) / TZ != home[i]) continue;            /* left its tile: parked */
+          const int lx = (ix + offx) % TX, lz = (iz + offz) % TZ;
+          if ((lx == 0 && ix != 0) || (lx == TX - 1 && ix != nx - 1) || (lz == 0 && iz != 0) || (lz == TZ - 1 && iz != nz - 1))
             continue;                                                                 /* border ring: parked */
           const size_t ind = (size_t)ix * nz + iz;
           if (claim[ind] == stamp) continue;
