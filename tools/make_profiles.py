@@ -32,7 +32,7 @@ if os.path.exists(src):
 if os.path.exists(os.path.join(G, f"launches_{tag}.csv")):
     launches(os.path.join(G, f"launches_{tag}.csv"), os.path.join(P, f"{tag}_launches_summary.md"))
 traffic = {}
-for name, title in (("tile_fly", "tile_fly_kernel<120,256> (Wind::fly + erosion + World::cascade per particle step; one super-round = 24 rounds x 9 micro-rounds of every 120x120 tile), 4096^2 FBm map, 4,194,304 particles per call, launch 41 of ~97 (mid-call, tiles fully populated)"),
+for name, title in (("tile_fly", "tile_fly_kernel<240,60,256> (Wind::fly + erosion + World::cascade per particle step; one super-round = 24 rounds x 9 micro-rounds of every 240x60 tile), 4096^2 FBm map, 4,194,304 particles per call, launch 41 of ~97 (mid-call, tiles fully populated)"),
                     ("colour_persistent", "colour_persistent_kernel (Wind::fly + erosion + World::cascade per particle step, all micro-rounds of one World::erode), 4096^2 FBm map, 4,194,304 particles"),
                     ("par_round", "par_round_kernel, 4096^2 FBm map, 4,194,304 particles, one round (step ~150 of a call)"),
                     ("cascade_stamped", "cascade_tile_kernel<stamped,TMA>, same run: World::cascade at the cells touched in the round"),
