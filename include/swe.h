@@ -196,6 +196,13 @@ typedef struct swe_engine swe_engine;
 
 /* ---- lifecycle -------------------------------------------------------------------- */
 int swe_abi_version(void);
+/* Tile-resident schedule, introspection (host arithmetic only, no device needed). swe_tile_geometry: rows, columns and
+ * threads per CTA of a compiled tile geometry (SWE_OPT_TILE_SHAPE value). swe_tile_owned_rows: on a map of nx rows cut
+ * into row stripes, the tile rows [*first, *end) of tiling `tiling` (the three shifted tilings: 0, 1, 2) that the rank
+ * owning global rows [own_lo, own_hi) launches -- a tile belongs to the rank that owns the row of its centre --, and
+ * the number of tile rows of that tiling. */
+int swe_tile_geometry(int shape, int* edge_x, int* edge_z, int* threads);
+int swe_tile_owned_rows(int nx, int shape, int tiling, int own_lo, int own_hi, int* first, int* end, int* total);
 const char* swe_last_error(void);
 int swe_params_default(swe_params* p);
 

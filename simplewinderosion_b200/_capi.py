@@ -87,6 +87,8 @@ _E = C.c_void_p
 _F = C.POINTER(C.c_float)
 PROTOTYPES = {
     "swe_abi_version": (C.c_int, []),
+    "swe_tile_geometry": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "swe_tile_owned_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "swe_last_error": (C.c_char_p, []),
     "swe_params_default": (C.c_int, [C.POINTER(Params)]),
     "swe_create": (C.c_int, [C.POINTER(_E), C.c_int, C.c_int, C.POINTER(Params), C.c_int]),

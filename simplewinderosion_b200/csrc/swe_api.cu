@@ -895,6 +895,21 @@ void finish_timers(swe_engine* e) {
 extern "C" {
 
 int swe_abi_version(void) { return SWE_ABI_VERSION; }
+
+int swe_tile_geometry(int shape, int* edge_x, int* edge_z, int* threads) {
+  if (shape < 0 || shape >= tile_shapes()) return fail(SWE_ERR_INVALID, "tile shape must be in [0, %d)", tile_shapes());
+  if (edge_x) *edge_x = tile_edge_x(shape);
+  if (edge_z) *edge_z = tile_edge_z(shape);
+  if (threads) *threads = tile_threads(shape);
+  return SWE_OK;
+}
+
+int swe_tile_owned_rows(int nx, int shape, int tiling, int own_lo, int own_hi, int* first, int* end, int* total) {
+  if (shape < 0 || shape >= tile_shapes() || tiling < 0 || nx < 1 || own_lo < 0 || own_hi > nx || own_lo >= own_hi || !first || !end || !total)
+    return fail(SWE_ERR_INVALID, "bad argument");
+  tile_owned_rows(nx, shape, tiling, own_lo, own_hi, first, end, total);
+  return SWE_OK;
+}
 const char* swe_last_error(void) { return g_err.c_str(); }
 
 int swe_params_default(swe_params* p) {

@@ -256,6 +256,7 @@ int launch_tile_phase(int phase, const MapView& m, const swe_params& p, const Ti
                       int inj_lo, int inj_hi, uint64_t seed, uint32_t call, DevStats* stats, cudaStream_t st,
                       const TileStripeHost* H);
 void launch_tile_xbar(void* const* mailboxes, int rank, int nranks, unsigned long long seq, unsigned* info, bool want_sum, cudaStream_t st);
+void tile_owned_rows(int nx, int shape, int tiling, int own_lo, int own_hi, int* a_lo, int* a_hi, int* ntx);
 int tile_shapes();                   // tile geometries compiled in (0 = 60 x 60 cells / 128 threads; 256 threads: 1 = 120 x 120, 2 = 240 x 60, 3 = 60 x 240)
 int tile_edge_x(int shape);
 int tile_edge_z(int shape);

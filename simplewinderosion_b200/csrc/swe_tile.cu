@@ -619,6 +619,15 @@ static int first_tile_row(int x, int tt, int off, int nx) {
   return a > ntx ? ntx : a;
 }
 
+// Host arithmetic of the stripe ownership, exported for tests (no device needed): the tile rows [a_lo, a_hi) of
+// tiling `tiling` (0, 1, 2) that the rank owning global rows [own_lo, own_hi) launches, and the number of tile rows.
+void tile_owned_rows(int nx, int shape, int tiling, int own_lo, int own_hi, int* a_lo, int* a_hi, int* ntx) {
+  const int tt = kShapes[shape].ex, off = (tiling % 3) * (tt / 3);
+  *a_lo = first_tile_row(own_lo, tt, off, nx);
+  *a_hi = first_tile_row(own_hi, tt, off, nx);
+  *ntx = (nx + off + tt - 1) / tt;
+}
+
 template <int TX, int TZ, int TNT>
 static void launch_fly(bool layered, bool stripe, int grid, size_t smem, cudaStream_t st, const MapView& m, const ParConst& C,
                        const block::Thr& T, const TileSched& S, const TileGeom& G, uint2 key, uint32_t call, DevStats* stats,

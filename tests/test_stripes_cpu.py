@@ -69,3 +69,51 @@ def test_ipc_blob_exchange_gloo_world2():
     assert res[0][1] and res[1][1]
     assert res[0][2] == res[1][2] == [(0, 2048), (2048, 4096)]
     assert res[0][3] == [1] and res[1][3] == [0]
+
+
+def test_tile_ownership_partitions_the_tile_rows():
+    """Tile-resident schedule on stripes (host arithmetic, no GPU): for every compiled tile geometry, each of the
+    three shifted tilings and a range of stripe cuts, the ranks' tile-row ranges partition [0, ntx) in rank order, and
+    every tile row's centre row (clamped to the map) lies in its owner's rows."""
+    import ctypes as C
+
+    from simplewinderosion_b200 import stripes
+    from simplewinderosion_b200._capi import check, lib
+
+    def geometry(shape):
+        ex, ez, nt = C.c_int(), C.c_int(), C.c_int()
+        check(lib.swe_tile_geometry(shape, C.byref(ex), C.byref(ez), C.byref(nt)))
+        return ex.value, ez.value, nt.value
+
+    shapes = []
+    for shape in range(8):
+        if lib.swe_tile_geometry(shape, None, None, None) != 0:
+            break
+        shapes.append(shape)
+    assert len(shapes) >= 2 and geometry(0)[:2] == (60, 60)
+    for shape in shapes:
+        ex, ez, nt = geometry(shape)
+        assert ex % 3 == 0 and ez % 3 == 0 and nt % 32 == 0 and ex * ez <= 14400
+        for nx, world in ((2 * ex + 8, 1), (4 * ex + 40, 2), (4096, 4), (4096, 8), (16384, 8), (3 * ex * 3 + 17, 3)):
+            if nx // world - 8 < 2 * ex:
+                continue
+            bounds = stripes.stripe_bounds(nx, world)
+            for tiling in range(3):
+                off = tiling * (ex // 3)
+                prev_end, total = 0, None
+                for lo, hi in bounds:
+                    a, b, n = C.c_int(), C.c_int(), C.c_int()
+                    check(lib.swe_tile_owned_rows(nx, shape, tiling, lo, hi, C.byref(a), C.byref(b), C.byref(n)))
+                    assert a.value == prev_end and b.value >= a.value + 1, (shape, nx, world, tiling, lo, hi, a.value, b.value)
+                    total = n.value
+                    assert total == (nx + off + ex - 1) // ex
+                    for row in range(a.value, b.value):
+                        centre = min(max(row * ex - off + ex // 2, 0), nx - 1)
+                        assert lo <= centre < hi, (shape, nx, world, tiling, row, centre, lo, hi)
+                        # the tile reaches at most into the two neighbouring stripes
+                        top, bottom = max(row * ex - off, 0), min((row + 1) * ex - off, nx)
+                        r = bounds.index((lo, hi))
+                        assert top >= (bounds[r - 1][0] if r > 0 else 0) and bottom <= (bounds[r + 1][1] if r + 1 < world else nx)
+                    prev_end = b.value
+                assert prev_end == total
+    assert lib.swe_tile_owned_rows(100, 0, 0, 50, 40, None, None, None) != 0      # bad arguments are refused
