@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out/final_r2t
 mkdir -p $O
-for shape in 0 1; do
+for shape in 0 1 2; do
   for tool in memcheck racecheck; do
     TILE_SHAPE=$shape NO_ORACLE=1 timeout 400 compute-sanitizer --tool $tool --print-limit 5 python tools/colour_probe.py 250 0.25 -1 2 > $O/${tool}_shape$shape.log 2>&1
     echo "$tool shape $shape: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $O/${tool}_shape$shape.log)"

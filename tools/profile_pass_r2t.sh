@@ -4,6 +4,7 @@
 cd "$(dirname "$0")/.."
 TAG=r2t
 O=gpurun_out
+mkdir -p $O
 NCU="ncu --clock-control none"
 # launch list of ONE timed headline call (three warm-up calls of ~300 launches each are skipped)
 $NCU --metrics gpu__time_duration.sum --launch-skip 900 -c 330 --csv --log-file $O/launches_$TAG.csv \
@@ -16,7 +17,9 @@ echo "# tools/colour_probe.py on B200 (round 2): parallel mode, TILE-RESIDENT sc
 echo "# columns: n density stagger schedule map calls" >> $P
 probe() { echo "## $*" >> $P; timeout 600 python tools/colour_probe.py "$@" 2>&1 | grep "^call" >> $P; }
 probe 1024 0.25 -1 2 noise 1
-echo "## (TILE_SHAPE=1: the 120x120 geometry of the headline)" >> $P
+echo "## (TILE_SHAPE=2: 240x60 tiles, long side along the wind -- the geometry the 4096^2 headline picks)" >> $P
+TILE_SHAPE=2 probe 1024 0.25 -1 2 noise 1
+echo "## (TILE_SHAPE=1: 120x120 tiles)" >> $P
 TILE_SHAPE=1 probe 1024 0.25 -1 2 noise 1
 probe 512 0.25 -1 2 noise 2
 probe 256 1.0 -1 2 flat 1
