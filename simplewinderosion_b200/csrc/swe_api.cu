@@ -772,6 +772,7 @@ int erode_tile(swe_engine* e, int cycles) {
 // barrier kernel follows each phase of a super-round; the completion check reads the GLOBAL number of records,
 // which the barrier after the scan sums over all ranks, so every rank takes the same decision.
 int erode_tile_stripes(swe_engine** engines, int n, int cycles) {
+  if (n < 1 || n > SWE_MAX_STRIPE_RANKS) return fail(SWE_ERR_INVALID, "a stripe group on the tile schedule has 1..%d engines", SWE_MAX_STRIPE_RANKS);
   TilePlan P{};
   for (int i = 0; i < n; i++) {
     swe_engine* e = engines[i];
@@ -812,7 +813,7 @@ int erode_tile_stripes(swe_engine** engines, int n, int cycles) {
     const bool check = s + 1 >= P.first_check && (s + 1 - P.first_check) % 4 == 0;
     if (int rc = round(s, lo, hi, check)) return rc;
     if (check) {
-      unsigned info[SWE_MAX_STRIPE_RANKS * 4][4];
+      unsigned info[SWE_MAX_STRIPE_RANKS][4];
       for (int i = 0; i < n; i++) {
         if (int rc = bind(engines[i])) return rc;
         if (int rc = check_launch(engines[i], "tile super-round (stripes)", i == 0 ? nl : 0)) return rc;
