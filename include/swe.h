@@ -268,7 +268,10 @@ int swe_host_free(void* p);
 /* World::erode(cycles) (world.hpp:36-77): zero the track planes, spawn `cycles`
  * particles and fly each to its death, then EMA-update the flow fields. The work is
  * enqueued on the engine's stream; every swe_download_* / swe_get_stats / swe_sync / query
- * call waits for it, so the map a consumer reads afterwards is always the eroded one. */
+ * call waits for it, so the map a consumer reads afterwards is always the eroded one.
+ * Parallel mode on the tile-resident schedule (SWE_OPT_SCHEDULE = 2, the default) enqueues super-rounds until the
+ * device reports that no particle is left, so the call returns when the particle phase is over (the EMA pass may
+ * still be in flight); the other paths return as soon as the work is enqueued. */
 int swe_erode(swe_engine* e, int cycles, int mode);
 
 /* World::cascade(vec2 pos) (world.hpp:79-153) at one cell. */
