@@ -99,7 +99,7 @@ def main():
             Cm = -1
         else:
             B, S, V, Cm, K = (int(x) for x in v.split(","))
-        wv = make(n, kind, hm); L.swo_srand(C.byref(wv.contents.rng), 3)
+        wv = make(n, kind, hm); L.swo_srand(C.byref(wv.contents.rng), int(os.environ.get("EMUL_SEED", "3")))
         sg, lg, rounds = 0, 0.0, 0
         lost, rr = C.c_double(), C.c_longlong()
         t0 = time.time()
